@@ -1,0 +1,743 @@
+// ebm.cu -- sm_100a kernels + C-ABI for the classical (EBM) side of the hot path:
+// bitstring packing, first-occurrence unique-with-counts, energy evaluation, the
+// exhaustive 2^n logits / logsumexp / entropy sweep, categorical and Bernoulli
+// sampling, count-weighted reductions.  Reference interfaces replaced are cited in
+// include/qhbm_b200.h.  These are HBM/latency-bound integer and fp32 kernels: no
+// tensor cores (energies feed exp() and must keep fp32 accuracy).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/qhbm_b200.h"
+#include "common.h"
+
+namespace qhbm {
+
+// ------------------------------------------------------------------ Philox4x32-10
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ uint4 operator()(uint64_t counter, uint32_t stream_hi) const {
+    uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = stream_hi, c3 = 0x9E3779B9u;
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+__device__ __forceinline__ Philox make_philox(uint64_t seed0, uint64_t seed1) {
+  Philox p;
+  p.k0 = (uint32_t)seed0 ^ (uint32_t)(seed1 >> 32);
+  p.k1 = (uint32_t)(seed0 >> 32) ^ (uint32_t)seed1 * 0x85EBCA6Bu;
+  return p;
+}
+__device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
+  const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+  return (double)v * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ float u01_24(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// ------------------------------------------------------------------ pack / unpack
+struct ShiftTable {
+  int8_t s[64];
+};
+
+__global__ void pack_kernel(const int8_t* __restrict__ bits, int64_t n_rows, int n_bits, ShiftTable st,
+                            uint64_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int8_t* row = bits + i * n_bits;
+  uint64_t k = 0;
+  for (int j = 0; j < n_bits; ++j) k |= (uint64_t)(row[j] & 1) << st.s[j];
+  keys[i] = k;
+}
+__global__ void unpack_kernel(const uint64_t* __restrict__ keys, int64_t n_rows, int n_bits, ShiftTable st,
+                              int8_t* __restrict__ bits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * n_bits) return;
+  const int64_t r = i / n_bits;
+  const int j = (int)(i - r * n_bits);
+  bits[i] = (int8_t)((keys[r] >> st.s[j]) & 1);
+}
+
+// ------------------------------------------------------------------ unique with counts
+constexpr uint64_t kEmptyKey = ~0ull;
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+struct UniqueWs {
+  unsigned long long* tkeys;  // [cap]
+  int32_t* tfirst;            // [cap] first row of the key, later its rank
+  int32_t* tcount;            // [cap]
+  int32_t* slot;              // [N]
+  int32_t* rank;              // [N] exclusive scan of first-occurrence flags
+  int32_t* bsum;              // [nblocks + 1]
+  uint64_t cap;
+};
+__global__ void uq_init(UniqueWs w) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < w.cap) { w.tkeys[i] = kEmptyKey; w.tfirst[i] = 0x7fffffff; w.tcount[i] = 0; }
+}
+__global__ void uq_insert(const uint64_t* __restrict__ keys, int64_t n, UniqueWs w) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  uint64_t h = mix64(k) & (w.cap - 1);
+  while (true) {
+    const unsigned long long old = atomicCAS(&w.tkeys[h], kEmptyKey, k);
+    if (old == kEmptyKey || old == k) break;
+    h = (h + 1) & (w.cap - 1);
+  }
+  atomicMin(&w.tfirst[h], (int32_t)i);
+  atomicAdd(&w.tcount[h], 1);
+  w.slot[i] = (int32_t)h;
+}
+constexpr int kScanBlock = 1024;
+// flags -> per-block exclusive scan (in rank) + block totals
+__global__ void __launch_bounds__(kScanBlock) uq_flag_scan(int64_t n, UniqueWs w) {
+  __shared__ int32_t s_w[32];
+  const int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t f = 0;
+  if (i < n) f = (w.tfirst[w.slot[i]] == (int32_t)i) ? 1 : 0;
+  int32_t v = f;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) s_w[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    int32_t x = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += t;
+    }
+    s_w[lane] = x;
+  }
+  __syncthreads();
+  const int32_t incl = v + (wid ? s_w[wid - 1] : 0);
+  if (i < n) w.rank[i] = incl - f;
+  if (threadIdx.x == kScanBlock - 1) w.bsum[blockIdx.x] = incl;
+}
+// exclusive scan of the block totals by ONE block (nblocks <= ~1e6 is fine)
+__global__ void __launch_bounds__(1024) uq_scan_blocks(int64_t nblocks, UniqueWs w, int64_t* n_unique) {
+  __shared__ int32_t s_w[32];
+  __shared__ int32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int64_t i = b0 + threadIdx.x;
+    const int32_t f = i < nblocks ? w.bsum[i] : 0;
+    int32_t v = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) s_w[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      int32_t x = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += t;
+      }
+      s_w[lane] = x;
+    }
+    __syncthreads();
+    const int32_t carry = s_carry;
+    const int32_t incl = v + (wid ? s_w[wid - 1] : 0) + carry;
+    if (i < nblocks) w.bsum[i] = incl - f;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_unique = s_carry;
+}
+__global__ void uq_emit(const uint64_t* __restrict__ keys, int64_t n, UniqueWs w, uint64_t* __restrict__ uniq,
+                        int32_t* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t s = w.slot[i];
+  const int32_t r = w.rank[i] + w.bsum[i / kScanBlock];
+  w.rank[i] = r;
+  if (w.tfirst[s] == (int32_t)i) {
+    uniq[r] = keys[i];
+    count[r] = w.tcount[s];
+  }
+}
+// second phase: slot -> rank of its first occurrence (first rows hold their own rank)
+__global__ void uq_index(int64_t n, UniqueWs w, int32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  idx[i] = w.rank[w.tfirst[w.slot[i]]];
+}
+
+__global__ void segsum_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx, int64_t n_rows,
+                              int width, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * width) return;
+  const int64_t r = i / width;
+  const int c = (int)(i - r * width);
+  atomicAdd(&out[(int64_t)idx[r] * width + c], vals[i]);
+}
+
+constexpr int kWsumStrip = 256;
+__global__ void wsum_kernel(const int32_t* __restrict__ counts, const float* __restrict__ vals, int64_t n_rows,
+                            int width, double* __restrict__ out) {
+  const int64_t r0 = (int64_t)blockIdx.x * kWsumStrip;
+  const int64_t r1 = min(n_rows, r0 + kWsumStrip);
+  for (int c = threadIdx.x; c <= width; c += blockDim.x) {
+    double s = 0.0;
+    if (c < width) {
+      for (int64_t r = r0; r < r1; ++r) s += (double)counts[r] * (double)vals[r * width + c];
+    } else {
+      for (int64_t r = r0; r < r1; ++r) s += (double)counts[r];
+    }
+    atomicAdd(&out[c], s);
+  }
+}
+
+// ------------------------------------------------------------------ energies
+constexpr int kMaxWidth = 64;
+struct EnergyArgs {
+  qhbm_energy_desc_t d;
+};
+
+// Dense stack on the raw bits; one row per thread, activations in registers, weights in
+// shared memory read as broadcast float4 (4 output neurons per load).
+__device__ __forceinline__ float mlp_energy(const EnergyArgs& ea, const float* s_w, uint64_t key) {
+  const qhbm_energy_desc_t& d = ea.d;
+  float x[kMaxWidth], y[kMaxWidth];
+  const int n = d.n_bits;
+#pragma unroll
+  for (int j = 0; j < kMaxWidth; ++j) x[j] = j < n ? (float)((key >> (n - 1 - j)) & 1) : 0.f;
+  int off = 0;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const int in = d.widths[l], out = d.widths[l + 1];
+    const int out4 = (out + 3) & ~3;  // rows padded to 4 outputs in smem
+    const float* W = s_w + off;
+    const float* Bv = W + in * out4;
+#pragma unroll
+    for (int o = 0; o < kMaxWidth; o += 4) {
+      if (o < out) {
+        const float4 b = *reinterpret_cast<const float4*>(Bv + o);
+        y[o] = b.x; y[o + 1] = b.y; y[o + 2] = b.z; y[o + 3] = b.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxWidth; ++i) {
+      if (i < in) {
+        const float xi = x[i];
+#pragma unroll
+        for (int o = 0; o < kMaxWidth; o += 4) {
+          if (o < out) {
+            const float4 w4 = *reinterpret_cast<const float4*>(W + i * out4 + o);
+            y[o] = fmaf(xi, w4.x, y[o]);
+            y[o + 1] = fmaf(xi, w4.y, y[o + 1]);
+            y[o + 2] = fmaf(xi, w4.z, y[o + 2]);
+            y[o + 3] = fmaf(xi, w4.w, y[o + 3]);
+          }
+        }
+      }
+    }
+    const int act = d.act[l];
+#pragma unroll
+    for (int o = 0; o < kMaxWidth; ++o) {
+      float v = y[o];
+      if (act == 1) v = tanhf(v);
+      else if (act == 2) v = fmaxf(v, 0.f);
+      x[o] = o < out ? v : 0.f;
+    }
+    off += in * out4 + out4;
+  }
+  return x[0];
+}
+
+__device__ __forceinline__ float parity_energy(const EnergyArgs& ea, const float* s_theta, const uint32_t* s_mask,
+                                               uint64_t key) {
+  const uint32_t k = (uint32_t)key;
+  float e = 0.f;
+  for (int t = 0; t < ea.d.n_terms; ++t) {
+    const uint32_t sgn = (uint32_t)(__popc(k & s_mask[t]) & 1) << 31;
+    e += __uint_as_float(__float_as_uint(s_theta[t]) ^ sgn);
+  }
+  return e;
+}
+
+// Stages the energy parameters in shared memory.  Returns the float count used.
+__device__ __forceinline__ void stage_energy(const EnergyArgs& ea, float* s_f) {
+  const qhbm_energy_desc_t& d = ea.d;
+  if (d.kind == QHBM_ENERGY_MLP) {
+    int off = 0;
+    for (int l = 0; l < d.n_layers; ++l) {
+      const int in = d.widths[l], out = d.widths[l + 1];
+      const int out4 = (out + 3) & ~3;
+      for (int i = threadIdx.x; i < in * out4; i += blockDim.x) {
+        const int r = i / out4, c = i - r * out4;
+        s_f[off + i] = c < out ? d.d_weights[l][r * out + c] : 0.f;
+      }
+      for (int i = threadIdx.x; i < out4; i += blockDim.x) s_f[off + in * out4 + i] = i < out ? d.d_bias[l][i] : 0.f;
+      off += in * out4 + out4;
+    }
+  } else {
+    uint32_t* s_m = reinterpret_cast<uint32_t*>(s_f + d.n_terms);
+    for (int i = threadIdx.x; i < d.n_terms; i += blockDim.x) {
+      s_f[i] = d.d_theta[i];
+      s_m[i] = d.d_masks[i];
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float eval_energy(const EnergyArgs& ea, const float* s_f, uint64_t key) {
+  if (ea.d.kind == QHBM_ENERGY_MLP) return mlp_energy(ea, s_f, key);
+  return parity_energy(ea, s_f, reinterpret_cast<const uint32_t*>(s_f + ea.d.n_terms), key);
+}
+
+size_t energy_smem_bytes(const qhbm_energy_desc_t& d) {
+  if (d.kind == QHBM_ENERGY_MLP) {
+    size_t f = 0;
+    for (int l = 0; l < d.n_layers; ++l) {
+      const int out4 = (d.widths[l + 1] + 3) & ~3;
+      f += (size_t)d.widths[l] * out4 + out4;
+    }
+    return f * 4;
+  }
+  return (size_t)d.n_terms * 8;
+}
+
+void validate_energy(const qhbm_energy_desc_t* e) {
+  if (!e) throw std::runtime_error("null energy descriptor");
+  if (e->n_bits < 1 || e->n_bits > 62) throw std::runtime_error("energy n_bits out of range");
+  if (e->kind == QHBM_ENERGY_MLP) {
+    if (e->n_layers < 1 || e->n_layers > 8) throw std::runtime_error("MLP energy: 1..8 layers supported");
+    if (e->widths[0] != e->n_bits) throw std::runtime_error("MLP energy: widths[0] must equal n_bits");
+    for (int l = 0; l <= e->n_layers; ++l)
+      if (e->widths[l] < 1 || e->widths[l] > kMaxWidth) throw std::runtime_error("MLP energy: widths must be in [1, 64]");
+    if (e->widths[e->n_layers] != 1) throw std::runtime_error("MLP energy: last layer must have one output");
+    for (int l = 0; l < e->n_layers; ++l)
+      if (!e->d_weights[l] || !e->d_bias[l]) throw std::runtime_error("MLP energy: null layer pointer");
+  } else if (e->kind == QHBM_ENERGY_BERNOULLI || e->kind == QHBM_ENERGY_KOBE) {
+    if (e->n_bits > 32) throw std::runtime_error("parity energies support up to 32 bits");
+    if (e->n_terms < 0 || (e->n_terms > 0 && (!e->d_masks || !e->d_theta))) throw std::runtime_error("bad parity energy tables");
+  } else {
+    throw std::runtime_error("unknown energy kind");
+  }
+  if (energy_smem_bytes(*e) > 200 * 1024) throw std::runtime_error("energy parameters do not fit shared memory");
+}
+
+constexpr int kEnergyThreads = 256;
+
+__global__ void __launch_bounds__(kEnergyThreads) energy_rows_kernel(const __grid_constant__ EnergyArgs ea,
+                                                                     const uint64_t* __restrict__ keys,
+                                                                     int64_t n_rows, float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_f[];
+  stage_energy(ea, s_f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = eval_energy(ea, s_f, keys[i]);
+}
+
+// online (max, sum exp, sum exp*l) triple
+struct Stat {
+  double m, s, t;
+};
+__device__ __forceinline__ Stat stat_merge(Stat a, Stat b) {
+  if (b.s == 0.0) return a;
+  if (a.s == 0.0) return b;
+  Stat r;
+  r.m = fmax(a.m, b.m);
+  const double fa = exp(a.m - r.m), fb = exp(b.m - r.m);
+  r.s = a.s * fa + b.s * fb;
+  r.t = a.t * fa + b.t * fb;
+  return r;
+}
+__device__ __forceinline__ Stat stat_warp(Stat v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Stat w;
+    w.m = __shfl_xor_sync(0xffffffffu, v.m, o);
+    w.s = __shfl_xor_sync(0xffffffffu, v.s, o);
+    w.t = __shfl_xor_sync(0xffffffffu, v.t, o);
+    v = stat_merge(v, w);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kEnergyThreads) ebm_sweep_kernel(const __grid_constant__ EnergyArgs ea, uint64_t lo,
+                                                                   uint64_t hi, float* __restrict__ logits,
+                                                                   Stat* __restrict__ partial) {
+  extern __shared__ __align__(16) float s_f[];
+  __shared__ Stat s_st[kEnergyThreads / 32];
+  stage_energy(ea, s_f);
+  Stat acc;
+  acc.m = 0.0; acc.s = 0.0; acc.t = 0.0;
+  for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float l = -eval_energy(ea, s_f, i);
+    if (logits) logits[i - lo] = l;
+    Stat one;
+    one.m = (double)l; one.s = 1.0; one.t = (double)l;
+    acc = stat_merge(acc, one);
+  }
+  acc = stat_warp(acc);
+  if ((threadIdx.x & 31) == 0) s_st[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Stat v;
+    v.m = 0.0; v.s = 0.0; v.t = 0.0;
+    if (threadIdx.x < kEnergyThreads / 32) v = s_st[threadIdx.x];
+    v = stat_warp(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(256) stat_final_kernel(const Stat* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ Stat s_st[8];
+  Stat acc;
+  acc.m = 0.0; acc.s = 0.0; acc.t = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = stat_merge(acc, partial[i]);
+  acc = stat_warp(acc);
+  if ((threadIdx.x & 31) == 0) s_st[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Stat v;
+    v.m = 0.0; v.s = 0.0; v.t = 0.0;
+    if (threadIdx.x < 8) v = s_st[threadIdx.x];
+    v = stat_warp(v);
+    if (threadIdx.x == 0) { out[0] = v.m; out[1] = v.s; out[2] = v.t; }
+  }
+}
+
+// ------------------------------------------------------------------ categorical sampling
+constexpr int kCatBlock = 256;  // rows per prefix block
+__global__ void __launch_bounds__(256) cat_max_kernel(const float* __restrict__ logits, int64_t n, float* __restrict__ gmax) {
+  float m = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, logits[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) {
+    // float atomic max via int ordering trick
+    int* a = reinterpret_cast<int*>(gmax);
+    if (m >= 0.f) atomicMax(a, __float_as_int(m));
+    else atomicMin(reinterpret_cast<unsigned int*>(a), __float_as_uint(m));
+  }
+}
+__global__ void __launch_bounds__(kCatBlock) cat_blocksum_kernel(const float* __restrict__ logits, int64_t n,
+                                                                 const float* __restrict__ gmax, double* __restrict__ bsum) {
+  __shared__ double s_w[kCatBlock / 32];
+  const int64_t i = (int64_t)blockIdx.x * kCatBlock + threadIdx.x;
+  double v = i < n ? exp((double)logits[i] - (double)*gmax) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int k = 0; k < kCatBlock / 32; ++k) s += s_w[k];
+    bsum[blockIdx.x] = s;
+  }
+}
+// exclusive scan of block sums (float64) by one block; total -> bsum[nblocks]
+__global__ void __launch_bounds__(1024) cat_scan_kernel(double* __restrict__ bsum, int64_t nblocks) {
+  __shared__ double s_w[32];
+  __shared__ double s_carry;
+  if (threadIdx.x == 0) s_carry = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int64_t i = b0 + threadIdx.x;
+    const double f = i < nblocks ? bsum[i] : 0.0;
+    double v = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) s_w[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      double x = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += t;
+      }
+      s_w[lane] = x;
+    }
+    __syncthreads();
+    const double incl = v + (wid ? s_w[wid - 1] : 0.0) + s_carry;
+    if (i < nblocks) bsum[i] = incl - f;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bsum[nblocks] = s_carry;
+}
+__global__ void cat_sample_kernel(const float* __restrict__ logits, int64_t n, const float* __restrict__ gmax,
+                                  const double* __restrict__ bpre, int64_t nblocks, uint64_t row_offset,
+                                  uint64_t seed0, uint64_t seed1, uint64_t first, int64_t n_samples,
+                                  uint64_t* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_samples) return;
+  const Philox ph = make_philox(seed0, seed1);
+  const uint4 r = ph(first + (uint64_t)k, 0x43415453u);
+  const double total = bpre[nblocks];
+  const double target = u01_53(r.x, r.y) * total;
+  // largest block b with bpre[b] <= target
+  int64_t lo = 0, hi = nblocks - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (bpre[mid] <= target) lo = mid; else hi = mid - 1;
+  }
+  const double m = (double)*gmax;
+  double acc = bpre[lo];
+  const int64_t i0 = lo * kCatBlock, i1 = min(n, i0 + kCatBlock);
+  int64_t pick = i1 - 1;
+  int64_t last_pos = -1;
+  for (int64_t i = i0; i < i1; ++i) {
+    const double w = exp((double)logits[i] - m);
+    if (w > 0.0) last_pos = i;
+    acc += w;
+    if (target < acc) { pick = i; last_pos = -2; break; }
+  }
+  if (last_pos >= 0) pick = last_pos;  // rounding pushed the target past the block: last positive weight
+  out[k] = row_offset + (uint64_t)pick;
+}
+
+__global__ void bern_sample_kernel(const float* __restrict__ logits, int n_bits, ShiftTable st, uint64_t seed0,
+                                   uint64_t seed1, uint64_t first, int64_t n_samples, uint64_t* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_samples) return;
+  const Philox ph = make_philox(seed0, seed1);
+  uint64_t key = 0;
+  for (int j0 = 0; j0 < n_bits; j0 += 4) {
+    const uint4 r = ph(first + (uint64_t)k, 0x42524E00u + (uint32_t)(j0 >> 2));
+    const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + q;
+      if (j < n_bits) {
+        const float p1 = 1.f / (1.f + expf(-logits[j]));
+        if (u01_24(rv[q]) < p1) key |= 1ull << st.s[j];
+      }
+    }
+  }
+  out[k] = key;
+}
+
+static ShiftTable make_shift(const int32_t* h_shift, int n_bits) {
+  if (n_bits < 1 || n_bits > 63) throw std::runtime_error("n_bits must be in [1, 63]");
+  if (!h_shift) throw std::runtime_error("h_shift is null");
+  ShiftTable st;
+  for (int j = 0; j < 64; ++j) st.s[j] = 0;
+  for (int j = 0; j < n_bits; ++j) {
+    if (h_shift[j] < 0 || h_shift[j] > 62) throw std::runtime_error("shift out of range");
+    st.s[j] = (int8_t)h_shift[j];
+  }
+  return st;
+}
+
+static uint64_t next_pow2(uint64_t x) {
+  uint64_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static UniqueWs carve_unique(void* ws, int64_t n) {
+  UniqueWs w;
+  w.cap = std::max<uint64_t>(1024, next_pow2((uint64_t)n * 2));
+  const int64_t nblocks = (n + kScanBlock - 1) / kScanBlock;
+  char* p = reinterpret_cast<char*>(ws);
+  w.tkeys = reinterpret_cast<unsigned long long*>(p); p += align_up(w.cap * 8);
+  w.tfirst = reinterpret_cast<int32_t*>(p); p += align_up(w.cap * 4);
+  w.tcount = reinterpret_cast<int32_t*>(p); p += align_up(w.cap * 4);
+  w.slot = reinterpret_cast<int32_t*>(p); p += align_up((size_t)n * 4);
+  w.rank = reinterpret_cast<int32_t*>(p); p += align_up((size_t)n * 4);
+  w.bsum = reinterpret_cast<int32_t*>(p); p += align_up((size_t)(nblocks + 1) * 4);
+  return w;
+}
+
+}  // namespace qhbm
+
+using namespace qhbm;
+
+extern "C" {
+
+int qhbm_pack_bits(const int8_t* d_bits, int64_t n_rows, int32_t n_bits, const int32_t* h_shift, uint64_t* d_keys,
+                   void* stream) {
+  return guarded([&] {
+    const ShiftTable st = make_shift(h_shift, n_bits);
+    if (n_rows <= 0) return;
+    pack_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_bits, n_rows, n_bits, st, d_keys);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+int qhbm_unpack_bits(const uint64_t* d_keys, int64_t n_rows, int32_t n_bits, const int32_t* h_shift, int8_t* d_bits,
+                     void* stream) {
+  return guarded([&] {
+    const ShiftTable st = make_shift(h_shift, n_bits);
+    if (n_rows <= 0) return;
+    const int64_t tot = n_rows * n_bits;
+    unpack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_keys, n_rows, n_bits, st, d_bits);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+int64_t qhbm_unique_workspace_bytes(int64_t n_rows) {
+  if (n_rows < 0) return -1;
+  const uint64_t cap = std::max<uint64_t>(1024, next_pow2((uint64_t)n_rows * 2));
+  const int64_t nblocks = (n_rows + kScanBlock - 1) / kScanBlock;
+  return (int64_t)(align_up(cap * 8) + 2 * align_up(cap * 4) + 2 * align_up((size_t)n_rows * 4) +
+                   align_up((size_t)(nblocks + 1) * 4) + 256);
+}
+
+int qhbm_unique_with_counts(const uint64_t* d_keys, int64_t n_rows, uint64_t* d_unique, int32_t* d_idx,
+                            int32_t* d_count, int64_t* d_n_unique, void* d_workspace, void* stream) {
+  return guarded([&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_rows < 0 || n_rows > 0x7fffffff) throw std::runtime_error("n_rows out of range");
+    if (n_rows == 0) {
+      QHBM_CUDA(cudaMemsetAsync(d_n_unique, 0, sizeof(int64_t), s));
+      return;
+    }
+    if (!d_workspace) throw std::runtime_error("workspace is null");
+    UniqueWs w = carve_unique(d_workspace, n_rows);
+    const int64_t nblocks = (n_rows + kScanBlock - 1) / kScanBlock;
+    const unsigned g = (unsigned)((n_rows + 255) / 256);
+    uq_init<<<(unsigned)((w.cap + 255) / 256), 256, 0, s>>>(w);
+    uq_insert<<<g, 256, 0, s>>>(d_keys, n_rows, w);
+    uq_flag_scan<<<(unsigned)nblocks, kScanBlock, 0, s>>>(n_rows, w);
+    uq_scan_blocks<<<1, 1024, 0, s>>>(nblocks, w, d_n_unique);
+    uq_emit<<<g, 256, 0, s>>>(d_keys, n_rows, w, d_unique, d_count);
+    uq_index<<<g, 256, 0, s>>>(n_rows, w, d_idx);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+int qhbm_segment_sum(const float* d_vals, const int32_t* d_idx, int64_t n_rows, int32_t width, float* d_out,
+                     int64_t n_unique, void* stream) {
+  return guarded([&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (width < 1) throw std::runtime_error("width must be >= 1");
+    QHBM_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * n_unique * width, s));
+    const int64_t tot = n_rows * width;
+    if (tot <= 0) return;
+    segsum_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_vals, d_idx, n_rows, width, d_out);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+int qhbm_weighted_sum(const int32_t* d_counts, const float* d_vals, int64_t n_rows, int32_t width, double* d_out,
+                      void* stream) {
+  return guarded([&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (width < 0) throw std::runtime_error("width must be >= 0");
+    QHBM_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (width + 1), s));
+    if (n_rows <= 0) return;
+    const int threads = std::min(1024, ((width + 1 + 31) / 32) * 32);
+    wsum_kernel<<<(unsigned)((n_rows + kWsumStrip - 1) / kWsumStrip), threads, 0, s>>>(d_counts, d_vals, n_rows, width, d_out);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+int qhbm_energy_rows(const qhbm_energy_desc_t* e, const uint64_t* d_keys, int64_t n_rows, float* d_energy,
+                     void* stream) {
+  return guarded([&] {
+    validate_energy(e);
+    if (n_rows <= 0) return;
+    EnergyArgs ea;
+    ea.d = *e;
+    const size_t smem = energy_smem_bytes(*e);
+    QHBM_CUDA(cudaFuncSetAttribute(energy_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const int64_t blocks = std::min<int64_t>((n_rows + kEnergyThreads - 1) / kEnergyThreads, 148 * 8);
+    energy_rows_kernel<<<(unsigned)blocks, kEnergyThreads, smem, (cudaStream_t)stream>>>(ea, d_keys, n_rows, d_energy);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+static void* g_sweep_partial = nullptr;
+static int g_sweep_partial_cap = 0;
+
+int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float* d_logits, double* d_stats,
+                   void* stream) {
+  return guarded([&] {
+    validate_energy(e);
+    if (hi < lo) throw std::runtime_error("hi < lo");
+    if (e->n_bits < 63 && hi > (1ull << e->n_bits)) throw std::runtime_error("row range exceeds 2^n_bits");
+    if (!d_stats) throw std::runtime_error("d_stats is null");
+    cudaStream_t s = (cudaStream_t)stream;
+    EnergyArgs ea;
+    ea.d = *e;
+    const size_t smem = energy_smem_bytes(*e);
+    const uint64_t rows = hi - lo;
+    int blocks = (int)std::min<uint64_t>((rows + kEnergyThreads - 1) / kEnergyThreads, 148 * 8);
+    blocks = std::max(blocks, 1);
+    if (g_sweep_partial_cap < blocks) {
+      if (g_sweep_partial) QHBM_CUDA(cudaFree(g_sweep_partial));
+      QHBM_CUDA(cudaMalloc(&g_sweep_partial, sizeof(Stat) * 148 * 8));
+      g_sweep_partial_cap = 148 * 8;
+    }
+    QHBM_CUDA(cudaFuncSetAttribute(ebm_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ebm_sweep_kernel<<<blocks, kEnergyThreads, smem, s>>>(ea, lo, hi, d_logits, (Stat*)g_sweep_partial);
+    stat_final_kernel<<<1, 256, 0, s>>>((const Stat*)g_sweep_partial, blocks, d_stats);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+int64_t qhbm_sample_workspace_bytes(int64_t n_rows) {
+  if (n_rows < 0) return -1;
+  const int64_t nblocks = (n_rows + kCatBlock - 1) / kCatBlock;
+  return 256 + 8 * (nblocks + 2);
+}
+
+int qhbm_categorical_sample(const float* d_logits, int64_t n_rows, uint64_t row_offset, uint64_t seed0,
+                            uint64_t seed1, uint64_t first_sample, int64_t n_samples, uint64_t* d_samples,
+                            void* d_workspace, void* stream) {
+  return guarded([&] {
+    if (n_rows < 1) throw std::runtime_error("n_rows must be >= 1");
+    if (n_samples < 0) throw std::runtime_error("n_samples must be >= 0");
+    if (!d_workspace) throw std::runtime_error("workspace is null");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* gmax = reinterpret_cast<float*>(d_workspace);
+    double* bsum = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + 256);
+    const int64_t nblocks = (n_rows + kCatBlock - 1) / kCatBlock;
+    const float ninf = -INFINITY;
+    QHBM_CUDA(cudaMemcpyAsync(gmax, &ninf, sizeof(float), cudaMemcpyHostToDevice, s));
+    cat_max_kernel<<<(unsigned)std::min<int64_t>((n_rows + 255) / 256, 148 * 8), 256, 0, s>>>(d_logits, n_rows, gmax);
+    cat_blocksum_kernel<<<(unsigned)nblocks, kCatBlock, 0, s>>>(d_logits, n_rows, gmax, bsum);
+    cat_scan_kernel<<<1, 1024, 0, s>>>(bsum, nblocks);
+    if (n_samples > 0)
+      cat_sample_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, s>>>(d_logits, n_rows, gmax, bsum, nblocks, row_offset,
+                                                                           seed0, seed1, first_sample, n_samples, d_samples);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+int qhbm_bernoulli_sample(const float* d_logits, int32_t n_bits, const int32_t* h_shift, uint64_t seed0,
+                          uint64_t seed1, uint64_t first_sample, int64_t n_samples, uint64_t* d_samples,
+                          void* stream) {
+  return guarded([&] {
+    const ShiftTable st = make_shift(h_shift, n_bits);
+    if (n_samples <= 0) return;
+    bern_sample_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_logits, n_bits, st, seed0, seed1, first_sample, n_samples, d_samples);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+}  // extern "C"

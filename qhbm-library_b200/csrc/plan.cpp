@@ -1,0 +1,647 @@
+// plan.cpp -- compiles a gate table + Pauli sums into the sweep/pass/op program.
+//
+// What the reference does instead: qhbmlib builds one serialized circuit proto per
+// unique bitstring (qhbmlib/models/circuit.py:129-136) and TFQ's C++ op parses,
+// resolves and fuses it again for every row (TfqSimulateExpectation / TfqAdjointGradient,
+// reached from qhbmlib/inference/qnn.py:134-138).  Here the circuit is compiled ONCE
+// per (circuit, observables) into a schedule that is independent of the symbol
+// values and of the bitstrings; only a small coefficient buffer is recomputed per call.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
+#include "gate_math.h"
+
+namespace qhbm {
+
+static std::string gate_err(int i, const char* what) {
+  return "gate " + std::to_string(i) + ": " + what;
+}
+
+void validate_circuit(const CircuitIR& c) {
+  if (c.n_qubits < 1 || c.n_qubits > kMaxQubits)
+    throw std::runtime_error("n_qubits must be in [1, " + std::to_string(kMaxQubits) + "]");
+  if (c.n_symbols < 0) throw std::runtime_error("n_symbols must be >= 0");
+  for (size_t i = 0; i < c.gates.size(); ++i) {
+    const qhbm_gate_t& g = c.gates[i];
+    if (g.type < 0 || g.type >= QHBM_GATE_NUM_TYPES) throw std::runtime_error(gate_err(i, "unknown type"));
+    if (g.q0 < 0 || g.q0 >= c.n_qubits) throw std::runtime_error(gate_err(i, "q0 out of range"));
+    if (gate_is_two_qubit(g.type)) {
+      if (g.q1 < 0 || g.q1 >= c.n_qubits) throw std::runtime_error(gate_err(i, "q1 out of range"));
+      if (g.q1 == g.q0) throw std::runtime_error(gate_err(i, "q0 == q1"));
+    }
+    if (g.nparams != gate_num_params(g.type)) throw std::runtime_error(gate_err(i, "wrong nparams for type"));
+    for (int k = 0; k < g.nparams; ++k)
+      if (g.sym[k] >= c.n_symbols) throw std::runtime_error(gate_err(i, "symbol index out of range"));
+  }
+}
+
+void validate_ops(const OpsIR& o) {
+  if (o.offsets.empty() || o.offsets[0] != 0) throw std::runtime_error("term_offsets must start at 0");
+  for (size_t j = 0; j + 1 < o.offsets.size(); ++j)
+    if (o.offsets[j + 1] < o.offsets[j]) throw std::runtime_error("term_offsets must be non-decreasing");
+  if (o.offsets.back() != (int)o.terms.size()) throw std::runtime_error("term_offsets/terms size mismatch");
+  const uint32_t lim = o.n_qubits >= 32 ? 0xffffffffu : ((1u << o.n_qubits) - 1u);
+  for (const auto& t : o.terms)
+    if ((t.xmask & ~lim) || (t.zmask & ~lim)) throw std::runtime_error("Pauli term acts outside the qubits");
+}
+
+namespace {
+
+struct Atom {
+  bool diag = false;
+  int nq = 1;
+  int bit[2] = {-1, -1};
+  std::vector<int> gates;
+};
+
+struct SweepOut {
+  std::vector<int> tile_bits;  // ascending state-index bits; local bit j = tile_bits[j]
+  int pass_begin = 0, pass_end = 0;
+};
+
+struct DiagRun {
+  std::vector<int32_t> reg_list;
+  std::vector<std::vector<int32_t>> grp_list;
+  std::vector<DevOp> pair_ops, cross_ops, gd_ops;
+  bool any = false, any_const = false;
+};
+
+DevOp make_op(int type) {
+  DevOp o;
+  std::memset(&o, 0, sizeof(o));
+  o.type = type;
+  o.p0 = o.p1 = -1;
+  o.coef = -1;
+  o.gslot = -1;
+  o.aux0 = o.aux1 = -1;
+  return o;
+}
+
+class Compiler {
+ public:
+  explicit Compiler(HostPlan& hp) : hp_(hp) {}
+
+  int bit_of(int q) const { return hp_.n - 1 - q; }
+
+  int32_t alloc_coef(int nfloats) {
+    int32_t off = hp_.ncoef;
+    hp_.ncoef += (nfloats + 3) & ~3;
+    return off;
+  }
+  void add_job(int kind, int32_t out, int a, int b, int c, int d, const std::vector<int32_t>& list) {
+    PrepJob j;
+    j.kind = kind; j.out = out; j.a = a; j.b = b; j.c = c; j.d = d;
+    j.list_off = (int32_t)hp_.lists.size();
+    j.list_len = (int32_t)list.size();
+    hp_.lists.insert(hp_.lists.end(), list.begin(), list.end());
+    hp_.jobs.push_back(j);
+  }
+
+  std::vector<Atom> forward_atoms() const {
+    std::vector<Atom> atoms;
+    std::vector<int> last(hp_.n_eff, -1);  // last atom touching each bit
+    for (int gi = 0; gi < (int)hp_.gates.size(); ++gi) {
+      const qhbm_gate_t& g = hp_.gates[gi];
+      if (g.type == QHBM_GATE_I) continue;
+      const bool two = gate_is_two_qubit(g.type);
+      const bool diag = gate_is_diagonal(g.type);
+      if (!two) {
+        int b = bit_of(g.q0);
+        int la = last[b];
+        if (la >= 0 && atoms[la].nq == 1) {  // fuse into the 1-qubit chain
+          atoms[la].gates.push_back(gi);
+          atoms[la].diag = atoms[la].diag && diag;
+          continue;
+        }
+        Atom a;
+        a.diag = diag; a.nq = 1; a.bit[0] = b; a.gates.push_back(gi);
+        last[b] = (int)atoms.size();
+        atoms.push_back(a);
+      } else {
+        Atom a;
+        a.diag = diag; a.nq = 2; a.bit[0] = bit_of(g.q0); a.bit[1] = bit_of(g.q1);
+        a.gates.push_back(gi);
+        last[a.bit[0]] = last[a.bit[1]] = (int)atoms.size();
+        atoms.push_back(a);
+      }
+    }
+    return atoms;
+  }
+
+  std::vector<Atom> backward_atoms() const {
+    std::vector<Atom> atoms;
+    for (int gi = (int)hp_.gates.size() - 1; gi >= 0; --gi) {
+      const qhbm_gate_t& g = hp_.gates[gi];
+      if (g.type == QHBM_GATE_I) continue;
+      Atom a;
+      a.diag = gate_is_diagonal(g.type);
+      a.nq = gate_is_two_qubit(g.type) ? 2 : 1;
+      a.bit[0] = bit_of(g.q0);
+      if (a.nq == 2) a.bit[1] = bit_of(g.q1);
+      a.gates.push_back(gi);
+      atoms.push_back(a);
+    }
+    return atoms;
+  }
+
+  // ---- readiness bookkeeping -------------------------------------------------
+  struct Block {
+    std::vector<char> nd, d;
+    explicit Block(int n) : nd(n, 0), d(n, 0) {}
+    bool ready(const Atom& a) const {
+      for (int i = 0; i < a.nq; ++i) {
+        if (nd[a.bit[i]]) return false;
+        if (!a.diag && d[a.bit[i]]) return false;
+      }
+      return true;
+    }
+    void block(const Atom& a) {
+      for (int i = 0; i < a.nq; ++i) (a.diag ? d : nd)[a.bit[i]] = 1;
+    }
+  };
+
+  std::vector<int> choose_tile(const std::vector<Atom>& atoms, const std::vector<char>& done) const {
+    const int n = hp_.n_eff, T = hp_.T;
+    std::vector<char> in(n, 0);
+    int cnt = 0;
+    if (n <= T) {
+      std::vector<int> all(n);
+      for (int i = 0; i < n; ++i) all[i] = i;
+      return all;
+    }
+    for (int b = 0; b < 5; ++b) { in[b] = 1; ++cnt; }  // 256-byte contiguous global segments
+    Block blk(n);
+    std::vector<int> later;
+    for (size_t ai = 0; ai < atoms.size(); ++ai) {
+      if (done[ai]) continue;
+      const Atom& a = atoms[ai];
+      if (!blk.ready(a)) { blk.block(a); if (!a.diag) later.push_back((int)ai); continue; }
+      if (a.diag) continue;
+      int need = 0;
+      for (int i = 0; i < a.nq; ++i) if (!in[a.bit[i]]) ++need;
+      if (a.nq == 2 && a.bit[0] == a.bit[1]) need = std::min(need, 1);
+      if (cnt + need <= T) {
+        for (int i = 0; i < a.nq; ++i) if (!in[a.bit[i]]) { in[a.bit[i]] = 1; ++cnt; }
+      } else {
+        blk.block(a);
+        later.push_back((int)ai);
+      }
+    }
+    for (int ai : later) {
+      const Atom& a = atoms[ai];
+      int need = 0;
+      for (int i = 0; i < a.nq; ++i) if (!in[a.bit[i]]) ++need;
+      if (cnt + need <= T)
+        for (int i = 0; i < a.nq; ++i) if (!in[a.bit[i]]) { in[a.bit[i]] = 1; ++cnt; }
+    }
+    for (int b = n - 1; b >= 0 && cnt < T; --b) if (!in[b]) { in[b] = 1; ++cnt; }
+    std::vector<int> out;
+    for (int b = 0; b < n; ++b) if (in[b]) out.push_back(b);
+    return out;
+  }
+
+  // Register-position allocator: positions (1,0) and (3,2) can host a 2-qubit block.
+  struct RegAlloc {
+    int K;
+    int pos_bit[kMaxRegQubits];  // position -> tile-local bit, -1 free
+    explicit RegAlloc(int k) : K(k) { for (int i = 0; i < kMaxRegQubits; ++i) pos_bit[i] = -1; }
+    int pos_of(int lb) const { for (int i = 0; i < K; ++i) if (pos_bit[i] == lb) return i; return -1; }
+    int nfree() const { int c = 0; for (int i = 0; i < K; ++i) c += pos_bit[i] < 0; return c; }
+    bool place1(int lb) {
+      if (pos_of(lb) >= 0) return true;
+      for (int i = K - 1; i >= 0; --i) if (pos_bit[i] < 0) { pos_bit[i] = lb; return true; }
+      return false;
+    }
+    bool place2(int la, int lb) {
+      int pa = pos_of(la), pb = pos_of(lb);
+      if (pa >= 0 && pb >= 0) return (pa ^ pb) == 1 && std::max(pa, pb) < 4;
+      if (pa >= 0 || pb >= 0) {
+        int p = pa >= 0 ? pa : pb;
+        int other = pa >= 0 ? lb : la;
+        if (p >= 4 || (p ^ 1) >= K || pos_bit[p ^ 1] >= 0) return false;
+        pos_bit[p ^ 1] = other;
+        return true;
+      }
+      for (int base = 0; base + 1 < std::min(K, 4); base += 2)
+        if (pos_bit[base] < 0 && pos_bit[base + 1] < 0) { pos_bit[base + 1] = la; pos_bit[base] = lb; return true; }
+      return false;
+    }
+  };
+
+  // Schedules `atoms` (already in execution order) into sweeps and passes.
+  void schedule(const std::vector<Atom>& atoms, bool backward, std::vector<SweepOut>& sweeps) {
+    const int n = hp_.n_eff, K = hp_.K;
+    std::vector<char> done(atoms.size(), 0);
+    size_t remaining = atoms.size();
+    const int max_slots = 4 * (1 << K);  // gradient scratch = the two dead smem tiles
+    while (remaining > 0) {
+      SweepOut sw;
+      sw.tile_bits = choose_tile(atoms, done);
+      sw.pass_begin = (int)hp_.passes.size();
+      std::vector<int> local_of(n, -1);
+      for (size_t j = 0; j < sw.tile_bits.size(); ++j) local_of[sw.tile_bits[j]] = (int)j;
+      const int Tloc = (int)sw.tile_bits.size();
+      size_t executed_in_sweep = 0;
+      while (remaining > 0) {
+        // -- tentative scan: pick the register qubits
+        RegAlloc ra(K);
+        {
+          Block blk(n);
+          for (size_t ai = 0; ai < atoms.size(); ++ai) {
+            if (done[ai]) continue;
+            const Atom& a = atoms[ai];
+            if (!blk.ready(a)) { blk.block(a); continue; }
+            if (a.diag) continue;
+            bool ok = true;
+            for (int i = 0; i < a.nq; ++i) ok = ok && local_of[a.bit[i]] >= 0;
+            if (ok) {
+              RegAlloc trial = ra;
+              ok = a.nq == 1 ? trial.place1(local_of[a.bit[0]])
+                             : trial.place2(local_of[a.bit[0]], local_of[a.bit[1]]);
+              if (ok) ra = trial;
+            }
+            if (!ok) blk.block(a);
+          }
+        }
+        const bool have_nondiag = ra.nfree() < K;
+        // pad the register set from the top of the tile
+        for (int lb = Tloc - 1; lb >= 0 && ra.nfree() > 0; --lb)
+          if (ra.pos_of(lb) < 0) ra.place1(lb);
+        // -- final scan: emit
+        DevPass ps;
+        std::memset(&ps, 0, sizeof(ps));
+        for (int j = 0; j < kMaxRegQubits; ++j) { ps.regbit[j] = 0; ps.sorted[j] = 0; }
+        for (int j = 0; j < K; ++j) ps.regbit[j] = ra.pos_bit[j];
+        {
+          std::vector<int> s(ps.regbit, ps.regbit + K);
+          std::sort(s.begin(), s.end());
+          for (int j = 0; j < K; ++j) ps.sorted[j] = s[j];
+        }
+        ps.op_begin = (int)hp_.ops.size();
+        ps.gsym_off = (int)hp_.gsym.size();
+        ps.ngrad = 0;
+        std::vector<int> regpos(n, -1);  // state bit -> register position
+        for (int j = 0; j < K; ++j) regpos[sw.tile_bits[ra.pos_bit[j]]] = j;
+
+        DiagRun run;
+        run.grp_list.assign((n + kConstGroupBits - 1) / kConstGroupBits, {});
+        size_t executed = 0;
+        Block blk(n);
+        for (size_t ai = 0; ai < atoms.size(); ++ai) {
+          if (done[ai]) continue;
+          const Atom& a = atoms[ai];
+          if (!blk.ready(a)) { blk.block(a); continue; }
+          bool ok = true;
+          int ngrads = 0;
+          if (backward) {
+            const qhbm_gate_t& g = hp_.gates[a.gates[0]];
+            for (int k = 0; k < g.nparams; ++k) ngrads += g.sym[k] >= 0;
+            if (ps.ngrad + ngrads > max_slots) ok = false;
+          }
+          if (ok && !a.diag) {
+            for (int i = 0; i < a.nq; ++i) ok = ok && regpos[a.bit[i]] >= 0;
+            if (ok && a.nq == 2) {
+              int pa = regpos[a.bit[0]], pb = regpos[a.bit[1]];
+              ok = (pa ^ pb) == 1 && std::max(pa, pb) < 4;
+            }
+          }
+          if (!ok) { blk.block(a); continue; }
+          if (a.diag) emit_diag(a, backward, regpos, ps, run);
+          else {
+            flush_diag(run, backward);
+            emit_nondiag(a, backward, regpos, ps);
+          }
+          done[ai] = 1;
+          --remaining;
+          ++executed;
+        }
+        flush_diag(run, backward);
+        if (executed == 0) break;  // nothing runnable with this tile: next sweep
+        ps.op_end = (int)hp_.ops.size();
+        hp_.passes.push_back(ps);
+        executed_in_sweep += executed;
+        if (!have_nondiag && remaining > 0) {
+          // only diagonal work was possible; a different tile is needed for the rest
+          break;
+        }
+      }
+      sw.pass_end = (int)hp_.passes.size();
+      if (executed_in_sweep == 0)
+        throw std::runtime_error("internal: scheduler made no progress");
+      sweeps.push_back(sw);
+    }
+  }
+
+  void emit_nondiag(const Atom& a, bool backward, const std::vector<int>& regpos, DevPass& ps) {
+    if (a.nq == 1) {
+      const int p = regpos[a.bit[0]];
+      if (backward) {
+        const int gi = a.gates[0];
+        const qhbm_gate_t& g = hp_.gates[gi];
+        for (int k = 0; k < g.nparams; ++k) {
+          if (g.sym[k] < 0) continue;
+          DevOp o = make_op(OP_GRAD_MAT1);
+          o.p0 = p;
+          o.coef = alloc_coef(8);
+          o.gslot = ps.ngrad++;
+          hp_.gsym.push_back(g.sym[k]);
+          add_job(PJ_GRAD1, o.coef, 0, 0, k, 0, {gi});
+          hp_.ops.push_back(o);
+        }
+      }
+      DevOp o = make_op(OP_MAT1);
+      o.p0 = p;
+      o.coef = alloc_coef(8);
+      add_job(PJ_MAT1, o.coef, backward ? 1 : 0, 0, 0, 0, std::vector<int32_t>(a.gates.begin(), a.gates.end()));
+      hp_.ops.push_back(o);
+    } else {
+      const int pa = regpos[a.bit[0]], pb = regpos[a.bit[1]];
+      const int pair = std::max(pa, pb) == 1 ? 0 : 1;
+      const int swap = pa < pb ? 1 : 0;  // matrix index = 2*bit(hi position) + bit(lo position)
+      const int gi = a.gates[0];
+      if (backward) {
+        const qhbm_gate_t& g = hp_.gates[gi];
+        for (int k = 0; k < g.nparams; ++k) {
+          if (g.sym[k] < 0) continue;
+          DevOp o = make_op(OP_GRAD_MAT2);
+          o.p0 = pair;
+          o.coef = alloc_coef(32);
+          o.gslot = ps.ngrad++;
+          hp_.gsym.push_back(g.sym[k]);
+          add_job(PJ_GRAD2, o.coef, 0, swap, k, 0, {gi});
+          hp_.ops.push_back(o);
+        }
+      }
+      DevOp o = make_op(OP_MAT2);
+      o.p0 = pair;
+      o.coef = alloc_coef(32);
+      add_job(PJ_MAT2, o.coef, backward ? 1 : 0, swap, 0, 0, {gi});
+      hp_.ops.push_back(o);
+    }
+  }
+
+  void emit_diag(const Atom& a, bool backward, const std::vector<int>& regpos, DevPass& ps, DiagRun& run) {
+    run.any = true;
+    const int dag = backward ? 1 : 0;
+    const int pa = regpos[a.bit[0]];
+    const int pb = a.nq == 2 ? regpos[a.bit[1]] : -1;
+    const bool reg_a = pa >= 0, reg_b = a.nq == 2 && pb >= 0;
+    const bool all_reg = a.nq == 1 ? reg_a : (reg_a && reg_b);
+    const bool all_const = a.nq == 1 ? !reg_a : (!reg_a && !reg_b);
+    for (int gi : a.gates) {
+      const qhbm_gate_t& g = hp_.gates[gi];
+      // ---- gradient inner products (before the un-apply; they commute with the whole run)
+      if (backward) {
+        for (int k = 0; k < g.nparams; ++k) {
+          if (g.sym[k] < 0) continue;
+          DevOp o = make_op(OP_GD_CONST);
+          int swap = 0;
+          if (all_const) {
+            o.type = OP_GD_CONST;
+            o.aux0 = a.bit[0];
+            o.aux1 = a.nq == 2 ? a.bit[1] : -1;
+          } else if (all_reg && a.nq == 1) {
+            o.type = OP_GD_REG1;
+            o.p0 = pa;
+          } else if (all_reg) {
+            o.type = OP_GD_REG2;  // kernel wants p0 > p1
+            if (pa > pb) { o.p0 = pa; o.p1 = pb; } else { o.p0 = pb; o.p1 = pa; swap = 1; }
+          } else {
+            o.type = OP_GD_MIX;  // entries indexed [2*bit(const) + regbit]
+            if (reg_a) { o.p0 = pa; o.aux0 = a.bit[1]; swap = 1; } else { o.p0 = pb; o.aux0 = a.bit[0]; }
+          }
+          o.coef = alloc_coef(8);
+          o.gslot = ps.ngrad++;
+          hp_.gsym.push_back(g.sym[k]);
+          add_job(PJ_GDIAG, o.coef, 0, swap, k, 0, {gi});
+          run.gd_ops.push_back(o);
+        }
+      }
+      // ---- the phase itself
+      if (all_reg) {
+        run.reg_list.push_back(gi);
+        run.reg_list.push_back(pa);
+        run.reg_list.push_back(a.nq == 2 ? pb : -1);
+      } else if (all_const) {
+        run.any_const = true;
+        const int ga = a.bit[0] / kConstGroupBits;
+        const int gb = a.nq == 2 ? a.bit[1] / kConstGroupBits : ga;
+        if (ga == gb) {
+          run.grp_list[ga].push_back(gi);
+          run.grp_list[ga].push_back(a.bit[0] - ga * kConstGroupBits);
+          run.grp_list[ga].push_back(a.nq == 2 ? a.bit[1] - ga * kConstGroupBits : -1);
+        } else {
+          DevOp o = make_op(OP_DCONST_PAIR);
+          o.aux0 = a.bit[0];
+          o.aux1 = a.bit[1];
+          o.coef = alloc_coef(8);
+          add_job(PJ_DPAIR, o.coef, dag, 0, 0, 0, {gi});
+          run.pair_ops.push_back(o);
+        }
+      } else {
+        DevOp o = make_op(OP_DCROSS);  // entries indexed [2*bit(const) + regbit]
+        int swap;
+        if (reg_a) { o.p0 = pa; o.aux0 = a.bit[1]; swap = 1; } else { o.p0 = pb; o.aux0 = a.bit[0]; swap = 0; }
+        o.coef = alloc_coef(8);
+        add_job(PJ_DPAIR, o.coef, dag, swap, 0, 0, {gi});
+        run.cross_ops.push_back(o);
+      }
+    }
+  }
+
+  void flush_diag(DiagRun& run, bool backward) {
+    if (!run.any) return;
+    const int dag = backward ? 1 : 0;
+    if (!run.gd_ops.empty()) {
+      DevOp b = make_op(OP_GD_BEGIN);
+      b.aux0 = (int)run.gd_ops.size();
+      hp_.ops.push_back(b);
+      for (auto& o : run.gd_ops) hp_.ops.push_back(o);
+    }
+    for (size_t g = 0; g < run.grp_list.size(); ++g) {
+      if (run.grp_list[g].empty()) continue;
+      DevOp o = make_op(OP_DCONST_TAB);
+      o.aux0 = (int)g * kConstGroupBits;
+      o.aux1 = (1 << kConstGroupBits) - 1;
+      o.coef = alloc_coef(2 << kConstGroupBits);
+      add_job(PJ_DTAB, o.coef, dag, 0, 0, kConstGroupBits, run.grp_list[g]);
+      hp_.ops.push_back(o);
+    }
+    for (auto& o : run.pair_ops) hp_.ops.push_back(o);
+    if (!run.reg_list.empty()) {
+      DevOp o = make_op(OP_DREG_TAB);
+      o.coef = alloc_coef(2 << hp_.K);
+      add_job(PJ_DTAB, o.coef, dag, 0, 0, hp_.K, run.reg_list);
+      hp_.ops.push_back(o);
+    } else if (run.any_const) {
+      hp_.ops.push_back(make_op(OP_DAPPLY));
+    }
+    for (auto& o : run.cross_ops) hp_.ops.push_back(o);
+    const size_t ng = run.grp_list.size();
+    run = DiagRun();
+    run.grp_list.assign(ng, {});
+  }
+
+  void fill_runs(const std::vector<int>& tile_bits, LaunchDesc& L) const {
+    const int n = hp_.n_eff;
+    std::vector<char> in(n, 0);
+    for (int b : tile_bits) in[b] = 1;
+    L.tile_mask = 0;
+    for (int b : tile_bits) L.tile_mask |= 1u << b;
+    auto build = [&](const std::vector<int>& bits, BitRun* runs, int32_t& nr) {
+      nr = 0;
+      size_t j = 0;
+      while (j < bits.size()) {
+        size_t e = j + 1;
+        while (e < bits.size() && bits[e] == bits[e - 1] + 1) ++e;
+        if (nr >= kMaxRuns) throw std::runtime_error("internal: too many bit runs in a tile map");
+        runs[nr].local_start = (int8_t)j;
+        runs[nr].global_start = (int8_t)bits[j];
+        runs[nr].len = (int8_t)(e - j);
+        runs[nr].pad = 0;
+        ++nr;
+        j = e;
+      }
+    };
+    std::vector<int> obits;
+    for (int b = 0; b < n; ++b) if (!in[b]) obits.push_back(b);
+    build(tile_bits, L.runs, L.n_runs);
+    build(obits, L.oruns, L.n_oruns);
+  }
+
+  void build_terms(const OpsIR& o) {
+    // k = coeff * (-i)^{ny}; sign from parity(i & z) of the OUTPUT index i (derivation in DESIGN.md).
+    const uint32_t tile_mask = hp_.n_eff <= hp_.T ? 0xffffffffu : ((1u << hp_.T) - 1u);
+    for (int j = 0; j < o.n_ops(); ++j) {
+      DevOpRange r;
+      r.group_begin = (int32_t)hp_.groups.size();
+      std::vector<int> idx;
+      for (int t = o.offsets[j]; t < o.offsets[j + 1]; ++t) idx.push_back(t);
+      std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return o.terms[a].xmask < o.terms[b].xmask; });
+      size_t i = 0;
+      while (i < idx.size()) {
+        const uint32_t x = o.terms[idx[i]].xmask;
+        DevTermGroup g;
+        g.x = x;
+        g.xl = (x & ~tile_mask) ? -1 : (int32_t)x;
+        g.term_begin = (int32_t)hp_.terms.size();
+        while (i < idx.size() && o.terms[idx[i]].xmask == x) {
+          const qhbm_pauli_term_t& t = o.terms[idx[i]];
+          const int ny = __builtin_popcount(t.xmask & t.zmask) & 3;
+          DevTerm d;
+          d.kr = ny == 0 ? t.coeff : (ny == 2 ? -t.coeff : 0.f);
+          d.ki = ny == 1 ? -t.coeff : (ny == 3 ? t.coeff : 0.f);
+          d.z = t.zmask;
+          d.pad = 0;
+          hp_.terms.push_back(d);
+          ++i;
+        }
+        g.term_end = (int32_t)hp_.terms.size();
+        hp_.groups.push_back(g);
+      }
+      r.group_end = (int32_t)hp_.groups.size();
+      hp_.opranges.push_back(r);
+    }
+  }
+
+  void compile(const CircuitIR& c, const OpsIR& o) {
+    std::vector<Atom> fwd = forward_atoms();
+    std::vector<SweepOut> fs, bs;
+    schedule(fwd, false, fs);
+    if (hp_.grad) {
+      std::vector<Atom> bwd = backward_atoms();
+      schedule(bwd, true, bs);
+    }
+    hp_.n_sweeps_fwd = (int)fs.size();
+    hp_.n_sweeps_bwd = (int)bs.size();
+    build_terms(o);
+    std::vector<int> contiguous;
+    for (int b = 0; b < std::min(hp_.T, hp_.n_eff); ++b) contiguous.push_back(b);
+
+    auto blank = [&]() {
+      LaunchDesc L;
+      std::memset(&L, 0, sizeof(L));
+      return L;
+    };
+    if (hp_.n_eff <= hp_.T) {
+      // whole state in one tile: one launch does forward, expectation and backward
+      LaunchDesc L = blank();
+      L.flags = LF_INIT_BASIS | LF_EXPECT;
+      fill_runs(contiguous, L);
+      L.pass_a_begin = fs.empty() ? 0 : fs.front().pass_begin;
+      L.pass_a_end = fs.empty() ? 0 : fs.back().pass_end;
+      L.pass_b_begin = bs.empty() ? 0 : bs.front().pass_begin;
+      L.pass_b_end = bs.empty() ? 0 : bs.back().pass_end;
+      hp_.launches.push_back(L);
+      hp_.n_fwd_launches = 1;
+      return;
+    }
+    if (fs.empty()) {
+      SweepOut sw;
+      sw.tile_bits = contiguous;
+      sw.pass_begin = sw.pass_end = 0;
+      fs.push_back(sw);
+    }
+    for (size_t i = 0; i < fs.size(); ++i) {
+      LaunchDesc L = blank();
+      L.flags = (i == 0 ? LF_INIT_BASIS : LF_LOAD_PSI) | LF_STORE_PSI;
+      fill_runs(fs[i].tile_bits, L);
+      L.pass_a_begin = fs[i].pass_begin;
+      L.pass_a_end = fs[i].pass_end;
+      hp_.launches.push_back(L);
+    }
+    hp_.n_fwd_launches = (int)fs.size();
+    {
+      LaunchDesc L = blank();
+      L.flags = LF_LOAD_PSI | LF_EXPECT | (hp_.grad ? LF_STORE_LAM : 0);
+      fill_runs(contiguous, L);
+      hp_.launches.push_back(L);
+    }
+    for (size_t i = 0; i < bs.size(); ++i) {
+      LaunchDesc L = blank();
+      L.flags = LF_LOAD_PSI | LF_LOAD_LAM;
+      if (i + 1 < bs.size()) L.flags |= LF_STORE_PSI | LF_STORE_LAM;
+      fill_runs(bs[i].tile_bits, L);
+      L.pass_b_begin = bs[i].pass_begin;
+      L.pass_b_end = bs[i].pass_end;
+      hp_.launches.push_back(L);
+    }
+    (void)c;
+  }
+
+ private:
+  HostPlan& hp_;
+};
+
+}  // namespace
+
+HostPlan compile_plan(const CircuitIR& c, const OpsIR& o, bool with_gradient, int tile_qubits,
+                      int reg_qubits) {
+  validate_circuit(c);
+  validate_ops(o);
+  if (c.n_qubits != o.n_qubits) throw std::runtime_error("circuit and observables act on different qubit counts");
+  HostPlan hp;
+  hp.n = c.n_qubits;
+  hp.P = c.n_symbols;
+  hp.O = o.n_ops();
+  hp.grad = with_gradient;
+  hp.K = reg_qubits > 0 ? reg_qubits : (with_gradient ? 4 : 5);
+  if (hp.K < 2 || hp.K > kMaxRegQubits) throw std::runtime_error("reg_qubits must be in [2, 5]");
+  int T = tile_qubits > 0 ? tile_qubits : 13;
+  const int t_max = with_gradient ? 13 : 14;  // 2 tiles (psi, lambda) of 8*2^T bytes must fit 227 KB
+  if (T > t_max) throw std::runtime_error("tile_qubits too large for shared memory");
+  if (T < hp.K + 5) throw std::runtime_error("tile_qubits must be >= reg_qubits + 5");
+  if (T - hp.K > 9) throw std::runtime_error("tile_qubits - reg_qubits must be <= 9 (512 threads per CTA)");
+  if (hp.K != 4 && hp.K != 5) throw std::runtime_error("reg_qubits must be 4 or 5");
+  hp.n_eff = std::max(hp.n, hp.K + 5);
+  hp.T = std::min(T, hp.n_eff);
+  hp.gates = c.gates;
+  Compiler comp(hp);
+  comp.compile(c, o);
+  return hp;
+}
+
+}  // namespace qhbm

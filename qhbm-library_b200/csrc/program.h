@@ -1,0 +1,123 @@
+// program.h -- the compiled "sweep / pass / op" program shared by the host
+// compiler (plan.cpp), the CUDA kernels (kernels.cu) and the test-only schedule
+// verifier (tests/native/verify_plan.cpp).  Plain-old-data only.
+//
+// Vocabulary
+//   state    complex64[2^n] amplitudes of one unique bitstring's circuit
+//   tile     2^T amplitudes of one state that one CTA holds in shared memory
+//   sweep    one pass of every tile of every state through shared memory
+//            (global -> smem -> [passes] -> global); the tile <-> state bit map is
+//            chosen per sweep so that the gates it runs act inside the tile
+//   pass     smem -> registers -> [ops] -> smem with K "register qubits": each
+//            thread holds the 2^K amplitudes that differ only in those K bits
+//   op       one fused gate block (or gradient inner product) applied in registers
+#pragma once
+#include <stdint.h>
+
+namespace qhbm {
+
+constexpr int kMaxRegQubits = 5;
+constexpr int kMaxTileQubits = 14;
+constexpr int kMaxQubits = 30;
+constexpr int kConstGroupBits = 7;  // width of one "thread-constant" phase table
+constexpr int kMaxRuns = 16;
+
+enum OpType : int32_t {
+  OP_NOP = 0,
+  OP_MAT1,        // p0: register position; coef -> 2x2 complex (8 floats)
+  OP_MAT2,        // p0: 0 -> positions (1,0), 1 -> positions (3,2); coef -> 4x4 (32 floats),
+                  //     matrix index = 2*bit(hi position) + bit(lo position)
+  OP_DCONST_TAB,  // F *= tab[(gidx >> aux0) & aux1]; coef -> complex table
+  OP_DCONST_PAIR, // F *= c[2*bit(aux0) + bit(aux1)] (aux1 < 0: c[bit(aux0)]); coef -> 4 complex
+  OP_DREG_TAB,    // amp[r] *= F * tab[r]; F = 1; coef -> 2^K complex
+  OP_DAPPLY,      // amp[r] *= F; F = 1
+  OP_DCROSS,      // amps with register bit p0 = v: *= c[2*bit(aux0) + v]; coef -> 4 complex
+  // gradient ops (adjoint sweeps only); value lands in scratch slot gslot
+  OP_GRAD_MAT1,   // 2 Re <lam| M |psi>, M 2x2 at coef, position p0
+  OP_GRAD_MAT2,   // same for 4x4, p0 as in OP_MAT2
+  OP_GD_BEGIN,    // starts a run of aux0 diagonal-gradient ops (they share conj(lam)*psi)
+  OP_GD_CONST,    // entries M[sel] at coef (complex); sel = 2*bit(aux0)+bit(aux1) (aux1<0: bit(aux0))
+  OP_GD_REG1,     // sel = register bit p0; coef -> 2 complex
+  OP_GD_REG2,     // sel = 2*regbit(p0) + regbit(p1); coef -> 4 complex
+  OP_GD_MIX,      // one register bit p0 and one constant bit aux0; coef -> 4 complex indexed
+                  //     [2*bit(aux0) + regbit(p0)]
+};
+
+struct DevOp {  // 32 bytes
+  int32_t type;
+  int32_t p0, p1;
+  int32_t coef;   // float offset into the coefficient buffer
+  int32_t gslot;  // gradient scratch slot within the pass, or -1
+  int32_t aux0, aux1;
+  int32_t pad;
+};
+
+struct DevPass {  // 64 bytes
+  int32_t regbit[kMaxRegQubits];     // tile-local bit of register position j
+  int32_t sorted[kMaxRegQubits];     // the same bits in ascending order
+  int32_t op_begin, op_end;
+  int32_t ngrad, gsym_off;           // gradient slots of this pass -> symbols gsym[gsym_off..]
+  int32_t pad[2];
+};
+
+// Contiguous run of tile-local bits mapped to contiguous state-index bits.
+struct BitRun {
+  int8_t local_start, global_start, len, pad;
+};
+
+enum LaunchFlags : uint32_t {
+  LF_INIT_BASIS = 1u << 0,  // tile := |basis> restricted to the tile (no load)
+  LF_LOAD_PSI = 1u << 1,
+  LF_LOAD_LAM = 1u << 2,
+  LF_EXPECT = 1u << 3,      // expectation values (+ lambda = sum_j g_j H_j psi if adjoint)
+  LF_STORE_PSI = 1u << 4,
+  LF_STORE_LAM = 1u << 5,
+  LF_WRITE_STATE = 1u << 6, // debug: store psi into a caller buffer
+};
+
+// One kernel launch = one sweep of one chunk of states.
+struct LaunchDesc {
+  uint32_t flags;
+  int32_t pass_a_begin, pass_a_end;  // passes run before the expectation phase (psi only)
+  int32_t pass_b_begin, pass_b_end;  // passes run after it (psi and lambda, with gradients)
+  int32_t n_runs, n_oruns;
+  BitRun runs[kMaxRuns];             // tile-local bits -> state bits
+  BitRun oruns[kMaxRuns];            // tile-id bits -> state bits (the out-of-tile bits)
+  uint32_t tile_mask;                // state-index bits covered by the tile
+  int32_t group_set;                 // which term-group table to use for LF_EXPECT
+};
+
+// Pauli-sum tables for the expectation phase.
+struct DevTerm {  // coefficient(i) += (kr + i ki) * (-1)^{parity(i & z)}
+  float kr, ki;
+  uint32_t z;
+  uint32_t pad;
+};
+struct DevTermGroup {  // terms sharing one x-mask: H psi[i] += coefficient(i) * psi[i ^ x]
+  uint32_t x;          // state-index xor mask
+  int32_t xl;          // tile-local xor mask if the partner is inside the tile, else -1
+  int32_t term_begin, term_end;
+};
+struct DevOpRange {
+  int32_t group_begin, group_end;
+};
+
+// Coefficient-preparation jobs (run on the device once per call, from the symbols).
+enum PrepKind : int32_t {
+  PJ_MAT1 = 0,   // product of list gates (application order); a: dagger
+  PJ_MAT2,       // single gate; a: dagger; b: swap qubit roles
+  PJ_GRAD1,      // M = dG G^dagger for (gate list[0], param c)
+  PJ_GRAD2,      // same, 4x4; b: swap qubit roles
+  PJ_GDIAG,      // diagonal of M for a diagonal gate; b: swap roles (4 entries) ; 1q gate: 2 entries
+  PJ_DTAB,       // phase table with 2^d entries; list = triples (gate, posA, posB): entry[v] =
+                 //   prod_g diag_g[2*bit(v,posA) + bit(v,posB)] (posB < 0 -> 1q gate); a: dagger
+  PJ_DPAIR,      // 4 (or 2) diagonal entries of one gate; a: dagger; b: swap roles
+};
+struct PrepJob {  // 32 bytes
+  int32_t kind;
+  int32_t out;        // float offset into the coefficient buffer
+  int32_t a, b, c, d;
+  int32_t list_off, list_len;
+};
+
+}  // namespace qhbm

@@ -1,0 +1,390 @@
+// sim.cu -- C-ABI entry points of the state-vector path (plan handles, expectation
+// forward / adjoint).  Declarations and the reference interfaces they replace are in
+// include/qhbm_b200.h.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "plan.h"
+#include "sim_kernels.cuh"
+
+namespace qhbm {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void upload(const std::vector<T>& v) {
+    reserve(std::max<size_t>(v.size(), 1));
+    if (!v.empty()) QHBM_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) QHBM_CUDA(cudaFree(p));
+    p = nullptr;
+    QHBM_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    cap = n;
+  }
+};
+
+}  // namespace qhbm
+
+using namespace qhbm;
+
+struct qhbm_circuit {
+  CircuitIR ir;
+};
+struct qhbm_ops {
+  OpsIR ir;
+};
+
+struct qhbm_plan {
+  HostPlan hp;
+  DevBuf<DevPass> d_passes;
+  DevBuf<DevOp> d_ops;
+  DevBuf<int32_t> d_gsym;
+  DevBuf<PrepJob> d_jobs;
+  DevBuf<int32_t> d_lists;
+  DevBuf<qhbm_gate_t> d_gates;
+  DevBuf<DevTerm> d_terms;
+  DevBuf<DevTermGroup> d_groups;
+  DevBuf<DevOpRange> d_opranges;
+  DevBuf<float> d_coef;
+  // workspace (grown on demand)
+  DevBuf<float2> d_psi, d_lam;
+  DevBuf<double> d_eacc, d_gacc;
+  // staging for the host-buffer entry point
+  DevBuf<uint64_t> d_basis;
+  DevBuf<float> d_sym, d_dgrad, d_out, d_gout;
+  int chunk = 1;
+  int sm_count = 148;
+  std::mutex mu;
+};
+
+namespace {
+
+template <int K, bool ADJ>
+void launch_sweep(const KernelArgs& ka, int n_states, int tiles, int threads, size_t smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  sweep_kernel<K, ADJ><<<(unsigned)(n_states * tiles), threads, smem, s>>>(ka);
+  QHBM_CUDA(cudaGetLastError());
+}
+
+void launch_any(const qhbm_plan* p, bool adj, const KernelArgs& ka, int n_states, cudaStream_t s) {
+  const HostPlan& hp = p->hp;
+  const int threads = 1 << (hp.T - hp.K);
+  const size_t smem = (size_t)(adj ? 2 : 1) * 8u * (1u << hp.T);
+  const int tiles = hp.tiles();
+  if (hp.K == 4) {
+    if (adj) launch_sweep<4, true>(ka, n_states, tiles, threads, smem, s);
+    else launch_sweep<4, false>(ka, n_states, tiles, threads, smem, s);
+  } else {
+    if (adj) launch_sweep<5, true>(ka, n_states, tiles, threads, smem, s);
+    else launch_sweep<5, false>(ka, n_states, tiles, threads, smem, s);
+  }
+}
+
+int default_chunk(const qhbm_plan* p) {
+  const HostPlan& hp = p->hp;
+  if (const char* e = std::getenv("QHBM_CHUNK")) {
+    int v = std::atoi(e);
+    if (v > 0) return v;
+  }
+  const int tiles = hp.tiles();
+  if (tiles == 1) return 1 << 20;  // single launch, no workspace
+  // keep the in-flight states L2-resident (126 MB) and the grid a multiple of the SM count
+  const size_t state_bytes = (size_t)8 << hp.n_eff;
+  const size_t per_state = state_bytes * (hp.grad ? 2 : 1);
+  const size_t budget = (size_t)80 << 20;
+  int c = (int)std::max<size_t>(1, budget / per_state);
+  const int waves = std::max(1, (c * tiles) / p->sm_count);
+  c = std::max(1, (waves * p->sm_count) / tiles);
+  return c;
+}
+
+void fill_common(const qhbm_plan* p, KernelArgs& ka) {
+  const HostPlan& hp = p->hp;
+  std::memset(&ka, 0, sizeof(ka));
+  ka.passes = p->d_passes.p;
+  ka.ops = p->d_ops.p;
+  ka.coef = p->d_coef.p;
+  ka.gsym = p->d_gsym.p;
+  ka.terms = p->d_terms.p;
+  ka.groups = p->d_groups.p;
+  ka.opranges = p->d_opranges.p;
+  ka.n = hp.n_eff;
+  ka.T = hp.T;
+  ka.O = hp.O;
+  ka.P = hp.P;
+}
+
+void run_prep(qhbm_plan* p, const float* d_symbols, int mode, cudaStream_t s) {
+  const HostPlan& hp = p->hp;
+  if (hp.jobs.empty()) return;
+  prep_kernel<<<(unsigned)hp.jobs.size(), kPrepThreads, 0, s>>>(p->d_jobs.p, p->d_lists.p, p->d_gates.p,
+                                                                d_symbols, p->d_coef.p, mode);
+  QHBM_CUDA(cudaGetLastError());
+}
+
+// Core driver shared by the forward and adjoint entry points.
+void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const float* d_symbols,
+                     const float* d_dgrad, float* d_out, float* d_grad_out, int per_state, int mode,
+                     bool adjoint, cudaStream_t s) {
+  const HostPlan& hp = p->hp;
+  if (adjoint && !hp.grad) throw std::runtime_error("plan was created without with_gradient");
+  if (U < 0) throw std::runtime_error("n_states must be >= 0");
+  if (U > (int64_t)1 << 30) throw std::runtime_error("n_states too large");
+  const int tiles = hp.tiles();
+  const bool multi = tiles > 1;
+  const int64_t grows = adjoint ? (per_state ? U : 1) : 0;
+  if (U == 0) {
+    if (adjoint && !per_state && hp.P > 0) QHBM_CUDA(cudaMemsetAsync(d_grad_out, 0, sizeof(float) * hp.P, s));
+    return;
+  }
+  p->d_eacc.reserve((size_t)U * hp.O);
+  if (grows) p->d_gacc.reserve((size_t)std::max<int64_t>(1, grows * hp.P));
+  const int chunk = (int)std::min<int64_t>(p->chunk, U);
+  if (multi) {
+    p->d_psi.reserve((size_t)chunk << hp.n_eff);
+    if (adjoint) p->d_lam.reserve((size_t)chunk << hp.n_eff);
+  }
+  run_prep(p, d_symbols, mode, s);
+  QHBM_CUDA(cudaMemsetAsync(p->d_eacc.p, 0, sizeof(double) * U * hp.O, s));
+  if (grows && hp.P > 0) QHBM_CUDA(cudaMemsetAsync(p->d_gacc.p, 0, sizeof(double) * grows * hp.P, s));
+
+  KernelArgs ka;
+  fill_common(p, ka);
+  ka.per_state = per_state;
+  ka.gacc = p->d_gacc.p;
+  // forward-only runs on an adjoint plan stop after the expectation launch
+  for (int64_t u0 = 0; u0 < U; u0 += chunk) {
+    const int c = (int)std::min<int64_t>(chunk, U - u0);
+    ka.basis = d_basis + u0;
+    ka.dgrad = (adjoint && d_dgrad) ? d_dgrad + u0 * hp.O : nullptr;
+    ka.eacc = p->d_eacc.p + u0 * hp.O;
+    ka.grow0 = (int)u0;
+    ka.psi = multi ? p->d_psi.p : nullptr;
+    ka.lam = (multi && adjoint) ? p->d_lam.p : nullptr;
+    for (size_t li = 0; li < hp.launches.size(); ++li) {
+      ka.L = hp.launches[li];
+      if (!adjoint) {
+        if (ka.L.pass_b_end > ka.L.pass_b_begin && !(ka.L.flags & LF_EXPECT)) break;  // backward sweeps
+        ka.L.pass_b_begin = ka.L.pass_b_end = 0;
+        ka.L.flags &= ~(uint32_t)LF_STORE_LAM;
+        if (ka.L.flags & LF_EXPECT) ka.L.flags &= ~(uint32_t)(LF_STORE_PSI);
+      }
+      launch_any(p, hp.grad, ka, c, s);
+    }
+  }
+  {
+    const int64_t ne = U * hp.O;
+    finalize_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(p->d_eacc.p, d_out, ne);
+    QHBM_CUDA(cudaGetLastError());
+  }
+  if (grows && hp.P > 0) {
+    const int64_t ng = grows * hp.P;
+    finalize_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, s>>>(p->d_gacc.p, d_grad_out, ng);
+    QHBM_CUDA(cudaGetLastError());
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* qhbm_last_error(void) { return g_last_error.c_str(); }
+int qhbm_version(void) { return 100; }
+
+int qhbm_circuit_create(const qhbm_gate_t* gates, int32_t n_gates, int32_t n_qubits, int32_t n_symbols,
+                        qhbm_circuit_t** out) {
+  return guarded([&] {
+    if (!out) throw std::runtime_error("out is null");
+    if (n_gates < 0 || (n_gates > 0 && !gates)) throw std::runtime_error("bad gate table");
+    auto* c = new qhbm_circuit;
+    c->ir.n_qubits = n_qubits;
+    c->ir.n_symbols = n_symbols;
+    c->ir.gates.assign(gates, gates + n_gates);
+    try {
+      validate_circuit(c->ir);
+    } catch (...) {
+      delete c;
+      throw;
+    }
+    *out = c;
+  });
+}
+void qhbm_circuit_destroy(qhbm_circuit_t* c) { delete c; }
+
+int qhbm_ops_create(const qhbm_pauli_term_t* terms, const int32_t* term_offsets, int32_t n_ops,
+                    int32_t n_qubits, qhbm_ops_t** out) {
+  return guarded([&] {
+    if (!out || !term_offsets || n_ops < 0) throw std::runtime_error("bad arguments");
+    auto* o = new qhbm_ops;
+    o->ir.n_qubits = n_qubits;
+    o->ir.offsets.assign(term_offsets, term_offsets + n_ops + 1);
+    const int nt = o->ir.offsets.back();
+    if (nt < 0 || (nt > 0 && !terms)) { delete o; throw std::runtime_error("bad term table"); }
+    o->ir.terms.assign(terms, terms + nt);
+    try {
+      if (n_qubits < 1 || n_qubits > kMaxQubits) throw std::runtime_error("n_qubits out of range");
+      validate_ops(o->ir);
+    } catch (...) {
+      delete o;
+      throw;
+    }
+    *out = o;
+  });
+}
+void qhbm_ops_destroy(qhbm_ops_t* o) { delete o; }
+
+int qhbm_plan_create(const qhbm_circuit_t* c, const qhbm_ops_t* o, int32_t with_gradient, int32_t tile_qubits,
+                     int32_t reg_qubits, qhbm_plan_t** out) {
+  return guarded([&] {
+    if (!c || !o || !out) throw std::runtime_error("null handle");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw std::runtime_error("no CUDA device: the qhbm_b200 engine has no CPU fallback");
+    if (tile_qubits == 0) if (const char* e = std::getenv("QHBM_TILE_QUBITS")) tile_qubits = std::atoi(e);
+    if (reg_qubits == 0) if (const char* e = std::getenv("QHBM_REG_QUBITS")) reg_qubits = std::atoi(e);
+    auto* p = new qhbm_plan;
+    try {
+      p->hp = compile_plan(c->ir, o->ir, with_gradient != 0, tile_qubits, reg_qubits);
+      const HostPlan& hp = p->hp;
+      p->d_passes.upload(hp.passes);
+      p->d_ops.upload(hp.ops);
+      p->d_gsym.upload(hp.gsym);
+      p->d_jobs.upload(hp.jobs);
+      p->d_lists.upload(hp.lists);
+      p->d_gates.upload(hp.gates);
+      p->d_terms.upload(hp.terms);
+      p->d_groups.upload(hp.groups);
+      p->d_opranges.upload(hp.opranges);
+      p->d_coef.reserve(std::max(hp.ncoef, 4));
+      int dev = 0;
+      QHBM_CUDA(cudaGetDevice(&dev));
+      QHBM_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev));
+      p->chunk = default_chunk(p);
+    } catch (...) {
+      delete p;
+      throw;
+    }
+    *out = p;
+  });
+}
+void qhbm_plan_destroy(qhbm_plan_t* p) { delete p; }
+
+int qhbm_plan_info(const qhbm_plan_t* p, int64_t* out8) {
+  return guarded([&] {
+    if (!p || !out8) throw std::runtime_error("null argument");
+    out8[0] = p->hp.n_sweeps_fwd;
+    out8[1] = p->hp.n_sweeps_bwd;
+    out8[2] = (int64_t)p->hp.passes.size();
+    out8[3] = (int64_t)p->hp.ops.size();
+    out8[4] = p->hp.T;
+    out8[5] = p->hp.K;
+    out8[6] = (int64_t)p->hp.launches.size();
+    out8[7] = p->chunk;
+  });
+}
+
+int qhbm_expectation_forward(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_states,
+                             const float* d_symbols, float* d_out, void* stream) {
+  return guarded([&] {
+    if (!p) throw std::runtime_error("null plan");
+    std::lock_guard<std::mutex> lk(p->mu);
+    run_expectation(p, d_basis_idx, n_states, d_symbols, nullptr, d_out, nullptr, 0, QHBM_GRAD_EXACT, false,
+                    (cudaStream_t)stream);
+  });
+}
+
+int qhbm_expectation_adjoint(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_states,
+                             const float* d_symbols, const float* d_dgrad, float* d_out, float* d_grad_out,
+                             int32_t per_state, int32_t grad_mode, void* stream) {
+  return guarded([&] {
+    if (!p) throw std::runtime_error("null plan");
+    if (grad_mode < 0 || grad_mode > 2) throw std::runtime_error("bad grad_mode");
+    if (!d_dgrad) throw std::runtime_error("d_dgrad is null");
+    std::lock_guard<std::mutex> lk(p->mu);
+    run_expectation(p, d_basis_idx, n_states, d_symbols, d_dgrad, d_out, d_grad_out, per_state, grad_mode, true,
+                    (cudaStream_t)stream);
+  });
+}
+
+int qhbm_expectation_host(qhbm_plan_t* p, const uint64_t* h_basis_idx, int64_t n_states, const float* h_symbols,
+                          const float* h_dgrad, float* h_out, float* h_grad_out, int32_t grad_mode,
+                          void* stream) {
+  return guarded([&] {
+    if (!p) throw std::runtime_error("null plan");
+    std::lock_guard<std::mutex> lk(p->mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    const HostPlan& hp = p->hp;
+    const int64_t U = n_states;
+    const bool adjoint = h_dgrad != nullptr && h_grad_out != nullptr;
+    p->d_basis.reserve(std::max<int64_t>(U, 1));
+    p->d_sym.reserve(std::max(hp.P, 1));
+    p->d_out.reserve(std::max<int64_t>(U * hp.O, 1));
+    QHBM_CUDA(cudaMemcpyAsync(p->d_basis.p, h_basis_idx, sizeof(uint64_t) * U, cudaMemcpyHostToDevice, s));
+    if (hp.P) QHBM_CUDA(cudaMemcpyAsync(p->d_sym.p, h_symbols, sizeof(float) * hp.P, cudaMemcpyHostToDevice, s));
+    if (adjoint) {
+      p->d_dgrad.reserve(std::max<int64_t>(U * hp.O, 1));
+      p->d_gout.reserve(std::max(hp.P, 1));
+      QHBM_CUDA(cudaMemcpyAsync(p->d_dgrad.p, h_dgrad, sizeof(float) * U * hp.O, cudaMemcpyHostToDevice, s));
+    }
+    run_expectation(p, p->d_basis.p, U, p->d_sym.p, adjoint ? p->d_dgrad.p : nullptr, p->d_out.p,
+                    adjoint ? p->d_gout.p : nullptr, 0, grad_mode, adjoint, s);
+    QHBM_CUDA(cudaMemcpyAsync(h_out, p->d_out.p, sizeof(float) * U * hp.O, cudaMemcpyDeviceToHost, s));
+    if (adjoint && hp.P)
+      QHBM_CUDA(cudaMemcpyAsync(h_grad_out, p->d_gout.p, sizeof(float) * hp.P, cudaMemcpyDeviceToHost, s));
+    QHBM_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int qhbm_debug_state(qhbm_plan_t* p, uint64_t basis_idx, const float* d_symbols, float* d_state_out,
+                     void* stream) {
+  return guarded([&] {
+    if (!p) throw std::runtime_error("null plan");
+    std::lock_guard<std::mutex> lk(p->mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    const HostPlan& hp = p->hp;
+    const bool multi = hp.tiles() > 1;
+    p->d_basis.reserve(1);
+    QHBM_CUDA(cudaMemcpyAsync(p->d_basis.p, &basis_idx, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    QHBM_CUDA(cudaStreamSynchronize(s));
+    p->d_eacc.reserve(std::max(hp.O, 1));
+    if (multi) {
+      p->d_psi.reserve((size_t)1 << hp.n_eff);
+      if (hp.grad) p->d_lam.reserve((size_t)1 << hp.n_eff);
+    }
+    run_prep(p, d_symbols, QHBM_GRAD_EXACT, s);
+    KernelArgs ka;
+    fill_common(p, ka);
+    ka.basis = p->d_basis.p;
+    ka.eacc = p->d_eacc.p;
+    ka.psi = multi ? p->d_psi.p : nullptr;
+    ka.lam = (multi && hp.grad) ? p->d_lam.p : nullptr;
+    ka.state_out = reinterpret_cast<float2*>(d_state_out);
+    for (int li = 0; li < hp.n_fwd_launches; ++li) {
+      ka.L = hp.launches[li];
+      ka.L.pass_b_begin = ka.L.pass_b_end = 0;
+      ka.L.flags &= ~(uint32_t)(LF_EXPECT | LF_STORE_LAM);
+      if (!multi) ka.L.flags |= LF_WRITE_STATE;
+      launch_any(p, hp.grad, ka, 1, s);
+    }
+    if (multi)
+      QHBM_CUDA(cudaMemcpyAsync(d_state_out, p->d_psi.p, sizeof(float2) << hp.n_eff, cudaMemcpyDeviceToDevice, s));
+  });
+}
+
+}  // extern "C"

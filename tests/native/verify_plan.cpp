@@ -1,0 +1,258 @@
+// verify_plan.cpp -- TEST-ONLY scalar interpreter of the compiled sweep/pass/op program.
+//
+// It executes exactly the program that plan.cpp emits (same sweeps, tiles, passes, ops,
+// coefficient jobs) with plain loops on the host, so that the scheduler and the op
+// semantics can be checked against oracle/ without a GPU.  It is NOT part of the
+// product library (libqhbm_b200.so does not contain it) and is never a fallback.
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../qhbm-library_b200/csrc/gate_math.h"
+#include "../../qhbm-library_b200/csrc/plan.h"
+
+using namespace qhbm;
+typedef std::complex<double> cplx;
+
+static std::string g_err;
+
+static uint32_t scatter(uint32_t l, const BitRun* runs, int nr) {
+  uint32_t g = 0;
+  for (int i = 0; i < nr; ++i) g |= ((l >> runs[i].local_start) & ((1u << runs[i].len) - 1u)) << runs[i].global_start;
+  return g;
+}
+
+static void prep(const HostPlan& hp, const float* symbols, int mode, std::vector<float>& coef) {
+  coef.assign(hp.ncoef + 4, 0.f);
+  auto wr = [&](int off, int i, cd v) { coef[off + 2 * i] = (float)v.re; coef[off + 2 * i + 1] = (float)v.im; };
+  for (const PrepJob& job : hp.jobs) {
+    const int32_t* list = hp.lists.data() + job.list_off;
+    cd m[16], t[16], w[16];
+    switch (job.kind) {
+      case PJ_MAT1: {
+        cd acc[4] = {mk(1, 0), mk(0, 0), mk(0, 0), mk(1, 0)};
+        for (int i = 0; i < job.list_len; ++i) {
+          gate_matrix_of(hp.gates[list[i]], symbols, m);
+          matmul(m, acc, 2, t);
+          for (int k = 0; k < 4; ++k) acc[k] = t[k];
+        }
+        if (job.a) { dagger(acc, 2, t); for (int k = 0; k < 4; ++k) acc[k] = t[k]; }
+        for (int k = 0; k < 4; ++k) wr(job.out, k, acc[k]);
+      } break;
+      case PJ_MAT2: {
+        gate_matrix_of(hp.gates[list[0]], symbols, m);
+        if (job.b) { swap_qubits(m, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
+        if (job.a) { dagger(m, 4, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
+        for (int k = 0; k < 16; ++k) wr(job.out, k, m[k]);
+      } break;
+      case PJ_GRAD1: case PJ_GRAD2: case PJ_GDIAG: {
+        const qhbm_gate_t g = hp.gates[list[0]];
+        const int dim = gate_matrix_of(g, symbols, m);
+        gate_derivative(g, symbols, job.c, mode, t);
+        dagger(m, dim, w);
+        matmul(t, w, dim, m);
+        if (dim == 4 && job.b) { swap_qubits(m, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
+        if (job.kind == PJ_GDIAG) for (int k = 0; k < 4; ++k) wr(job.out, k, k < dim ? m[k * dim + k] : mk(0, 0));
+        else for (int k = 0; k < dim * dim; ++k) wr(job.out, k, m[k]);
+      } break;
+      case PJ_DPAIR: {
+        const int dim = gate_matrix_of(hp.gates[list[0]], symbols, m);
+        if (dim == 4 && job.b) { swap_qubits(m, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
+        for (int k = 0; k < 4; ++k) { cd v = k < dim ? m[k * dim + k] : mk(1, 0); wr(job.out, k, job.a ? conj(v) : v); }
+      } break;
+      case PJ_DTAB: {
+        const int entries = 1 << job.d;
+        for (int v = 0; v < entries; ++v) {
+          cd acc = mk(1, 0);
+          for (int q = 0; q < job.list_len / 3; ++q) {
+            const int dim = gate_matrix_of(hp.gates[list[3 * q]], symbols, m);
+            int sel = (v >> list[3 * q + 1]) & 1;
+            if (list[3 * q + 2] >= 0) sel = 2 * sel + ((v >> list[3 * q + 2]) & 1);
+            cd d = m[sel * dim + sel];
+            acc = acc * (job.a ? conj(d) : d);
+          }
+          wr(job.out, v, acc);
+        }
+      } break;
+    }
+  }
+}
+
+struct Ctx {
+  const HostPlan* hp;
+  std::vector<float> coef;
+  std::vector<cplx> psi, lam;  // global state
+  std::vector<double> eacc, gacc;
+  const float* dgrad;
+};
+
+static cplx cf(const Ctx& c, int off, int i) { return cplx(c.coef[off + 2 * i], c.coef[off + 2 * i + 1]); }
+
+static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector<cplx>& tp, std::vector<cplx>& tl,
+                     uint32_t goff, bool both) {
+  const HostPlan& hp = *c.hp;
+  const int K = hp.K, R = 1 << K, nthr = 1 << (hp.T - K);
+  std::vector<double> gsum(ps.ngrad, 0.0);
+  for (int tid = 0; tid < nthr; ++tid) {
+    uint32_t base = tid;
+    for (int j = 0; j < K; ++j) { int sp = ps.sorted[j]; base = ((base >> sp) << (sp + 1)) | (base & ((1u << sp) - 1u)); }
+    const uint32_t gbase = goff | scatter(base, L.runs, L.n_runs);
+    std::vector<uint32_t> idx(R);
+    for (int r = 0; r < R; ++r) { uint32_t dep = 0; for (int j = 0; j < K; ++j) if ((r >> j) & 1) dep |= 1u << ps.regbit[j]; idx[r] = base | dep; }
+    std::vector<cplx> a(R), b(R);
+    for (int r = 0; r < R; ++r) { a[r] = tp[idx[r]]; if (both) b[r] = tl[idx[r]]; }
+    cplx F(1, 0);
+    auto mat1 = [&](std::vector<cplx>& v, int p, int off) {
+      for (int r = 0; r < R; ++r) if (!(r & (1 << p))) {
+        cplx x0 = v[r], x1 = v[r | (1 << p)];
+        v[r] = cf(c, off, 0) * x0 + cf(c, off, 1) * x1;
+        v[r | (1 << p)] = cf(c, off, 2) * x0 + cf(c, off, 3) * x1;
+      }
+    };
+    auto mat2 = [&](std::vector<cplx>& v, int lo, int off, const std::vector<cplx>* bb, double* gout) {
+      double s = 0;
+      for (int r = 0; r < R; ++r) if (!(r & (3 << lo))) {
+        cplx x[4], y[4];
+        for (int j = 0; j < 4; ++j) x[j] = v[r | (j << lo)];
+        for (int i = 0; i < 4; ++i) { y[i] = 0; for (int j = 0; j < 4; ++j) y[i] += cf(c, off, 4 * i + j) * x[j]; }
+        if (bb) for (int i = 0; i < 4; ++i) s += (std::conj((*bb)[r | (i << lo)]) * y[i]).real();
+        else for (int i = 0; i < 4; ++i) v[r | (i << lo)] = y[i];
+      }
+      if (gout) *gout = 2 * s;
+    };
+    for (int oi = ps.op_begin; oi < ps.op_end; ++oi) {
+      const DevOp& op = hp.ops[oi];
+      switch (op.type) {
+        case OP_MAT1: mat1(a, op.p0, op.coef); if (both) mat1(b, op.p0, op.coef); break;
+        case OP_MAT2: mat2(a, op.p0 ? 2 : 0, op.coef, nullptr, nullptr); if (both) mat2(b, op.p0 ? 2 : 0, op.coef, nullptr, nullptr); break;
+        case OP_DCONST_TAB: F *= cf(c, op.coef, (gbase >> op.aux0) & op.aux1); break;
+        case OP_DCONST_PAIR: { int sel = (gbase >> op.aux0) & 1; if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1); F *= cf(c, op.coef, sel); } break;
+        case OP_DREG_TAB: for (int r = 0; r < R; ++r) { cplx k = F * cf(c, op.coef, r); a[r] *= k; if (both) b[r] *= k; } F = 1; break;
+        case OP_DAPPLY: for (int r = 0; r < R; ++r) { a[r] *= F; if (both) b[r] *= F; } F = 1; break;
+        case OP_DCROSS: { int cb = (gbase >> op.aux0) & 1; for (int r = 0; r < R; ++r) { cplx k = cf(c, op.coef, 2 * cb + ((r >> op.p0) & 1)); a[r] *= k; if (both) b[r] *= k; } } break;
+        case OP_GRAD_MAT1: {
+          double s = 0;
+          for (int r = 0; r < R; ++r) if (!(r & (1 << op.p0))) {
+            cplx x0 = a[r], x1 = a[r | (1 << op.p0)];
+            s += (std::conj(b[r]) * (cf(c, op.coef, 0) * x0 + cf(c, op.coef, 1) * x1)).real();
+            s += (std::conj(b[r | (1 << op.p0)]) * (cf(c, op.coef, 2) * x0 + cf(c, op.coef, 3) * x1)).real();
+          }
+          gsum[op.gslot] += 2 * s;
+        } break;
+        case OP_GRAD_MAT2: { double g = 0; mat2(a, op.p0 ? 2 : 0, op.coef, &b, &g); gsum[op.gslot] += g; } break;
+        case OP_GD_BEGIN: break;
+        case OP_GD_CONST: case OP_GD_REG1: case OP_GD_REG2: case OP_GD_MIX: {
+          double s = 0;
+          for (int r = 0; r < R; ++r) {
+            int sel;
+            if (op.type == OP_GD_CONST) { sel = (gbase >> op.aux0) & 1; if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1); }
+            else if (op.type == OP_GD_REG1) sel = (r >> op.p0) & 1;
+            else if (op.type == OP_GD_REG2) sel = 2 * ((r >> op.p0) & 1) + ((r >> op.p1) & 1);
+            else sel = 2 * ((gbase >> op.aux0) & 1) + ((r >> op.p0) & 1);
+            s += (cf(c, op.coef, sel) * std::conj(b[r]) * a[r]).real();
+          }
+          gsum[op.gslot] += 2 * s;
+        } break;
+        default: throw std::runtime_error("verify: unknown op");
+      }
+    }
+    for (int r = 0; r < R; ++r) { tp[idx[r]] = a[r]; if (both) tl[idx[r]] = b[r]; }
+  }
+  for (int g = 0; g < ps.ngrad; ++g) c.gacc[hp.gsym[ps.gsym_off + g]] += gsum[g];
+}
+
+static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
+  const HostPlan& hp = *c.hp;
+  const int tiles = hp.tiles(), tsz = 1 << hp.T;
+  std::vector<std::vector<cplx>> new_psi, new_lam;
+  // process all tiles reading the OLD global arrays for cross-tile gathers (launch semantics)
+  std::vector<cplx> psi_next = c.psi, lam_next = c.lam;
+  for (int tile = 0; tile < tiles; ++tile) {
+    const uint32_t goff = scatter(tile, L.oruns, L.n_oruns);
+    std::vector<cplx> tp(tsz, 0), tl(tsz, 0);
+    bool active = true;
+    if (L.flags & LF_INIT_BASIS) {
+      active = (basis & ~L.tile_mask) == goff;
+      for (int l = 0; l < tsz; ++l) if (active && (goff | scatter(l, L.runs, L.n_runs)) == basis) tp[l] = 1;
+    } else if (L.flags & LF_LOAD_PSI) {
+      for (int l = 0; l < tsz; ++l) tp[l] = c.psi[goff | scatter(l, L.runs, L.n_runs)];
+    }
+    if (L.flags & LF_LOAD_LAM) for (int l = 0; l < tsz; ++l) tl[l] = c.lam[goff | scatter(l, L.runs, L.n_runs)];
+    if (active) for (int p = L.pass_a_begin; p < L.pass_a_end; ++p) run_pass(c, L, hp.passes[p], tp, tl, goff, false);
+    if (L.flags & LF_EXPECT) {
+      for (int j = 0; j < hp.O; ++j) {
+        const double gj = (adjoint && c.dgrad) ? c.dgrad[j] : 0.0;
+        double ej = 0;
+        for (int g = hp.opranges[j].group_begin; g < hp.opranges[j].group_end; ++g) {
+          const DevTermGroup& G = hp.groups[g];
+          for (int l = 0; l < tsz; ++l) {
+            const uint32_t gi = goff | scatter(l, L.runs, L.n_runs);
+            cplx k = 0;
+            for (int t = G.term_begin; t < G.term_end; ++t) {
+              const DevTerm& T = hp.terms[t];
+              const double sg = (__builtin_popcount(gi & T.z) & 1) ? -1.0 : 1.0;
+              k += sg * cplx(T.kr, T.ki);
+            }
+            const cplx pv = G.xl >= 0 ? tp[l ^ (uint32_t)G.xl] : c.psi[gi ^ G.x];
+            const cplx h = k * pv;
+            ej += (std::conj(tp[l]) * h).real();
+            tl[l] += gj * h;
+          }
+        }
+        c.eacc[j] += ej;
+      }
+    }
+    for (int p = L.pass_b_begin; p < L.pass_b_end; ++p) run_pass(c, L, hp.passes[p], tp, tl, goff, true);
+    for (int l = 0; l < tsz; ++l) {
+      const uint32_t gi = goff | scatter(l, L.runs, L.n_runs);
+      if ((L.flags & LF_STORE_PSI) || tiles == 1) psi_next[gi] = tp[l];
+      if ((L.flags & LF_STORE_LAM) || tiles == 1) lam_next[gi] = tl[l];
+    }
+  }
+  c.psi.swap(psi_next);
+  c.lam.swap(lam_next);
+}
+
+extern "C" {
+
+const char* verify_last_error() { return g_err.c_str(); }
+
+// Runs the compiled program for ONE basis state on the host.  state_out (2*2^n_eff doubles)
+// receives U|basis> (state after the forward launches).  info_out[8] as qhbm_plan_info.
+int verify_run(const qhbm_gate_t* gates, int n_gates, int n, int P, const qhbm_pauli_term_t* terms,
+               const int32_t* offs, int O, int with_grad, int T, int K, int mode, const float* symbols,
+               uint64_t basis, const float* dgrad, double* e_out, double* g_out, double* state_out,
+               int64_t* info_out) {
+  try {
+    CircuitIR c; c.n_qubits = n; c.n_symbols = P; c.gates.assign(gates, gates + n_gates);
+    OpsIR o; o.n_qubits = n; o.offsets.assign(offs, offs + O + 1); o.terms.assign(terms, terms + offs[O]);
+    HostPlan hp = compile_plan(c, o, with_grad != 0, T, K);
+    Ctx ctx; ctx.hp = &hp; ctx.dgrad = dgrad;
+    prep(hp, symbols, mode, ctx.coef);
+    ctx.psi.assign((size_t)1 << hp.n_eff, 0); ctx.lam.assign((size_t)1 << hp.n_eff, 0);
+    ctx.eacc.assign(O, 0); ctx.gacc.assign(std::max(P, 1), 0);
+    for (size_t li = 0; li < hp.launches.size(); ++li) {
+      LaunchDesc L = hp.launches[li];
+      if (hp.tiles() == 1 && state_out) {
+        // single launch: capture the forward state by running the forward part alone first
+        LaunchDesc F = L; F.flags &= ~(uint32_t)LF_EXPECT; F.pass_b_begin = F.pass_b_end = 0;
+        Ctx tmp = ctx; run_launch(tmp, F, (uint32_t)basis, false);
+        for (size_t i = 0; i < tmp.psi.size(); ++i) { state_out[2 * i] = tmp.psi[i].real(); state_out[2 * i + 1] = tmp.psi[i].imag(); }
+      }
+      run_launch(ctx, L, (uint32_t)basis, with_grad != 0);
+      if (hp.tiles() > 1 && state_out && (int)li == hp.n_fwd_launches - 1)
+        for (size_t i = 0; i < ctx.psi.size(); ++i) { state_out[2 * i] = ctx.psi[i].real(); state_out[2 * i + 1] = ctx.psi[i].imag(); }
+    }
+    for (int j = 0; j < O; ++j) e_out[j] = ctx.eacc[j];
+    if (with_grad) for (int s = 0; s < P; ++s) g_out[s] = ctx.gacc[s];
+    if (info_out) {
+      info_out[0] = hp.n_sweeps_fwd; info_out[1] = hp.n_sweeps_bwd; info_out[2] = hp.passes.size();
+      info_out[3] = hp.ops.size(); info_out[4] = hp.T; info_out[5] = hp.K; info_out[6] = hp.launches.size(); info_out[7] = hp.n_eff;
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+}

@@ -1,0 +1,200 @@
+"""GPU parity tests of the state-vector path, through the C ABI (libqhbm_b200.so).
+
+Oracle: oracle/qhbm_oracle.py (complex128).  Tolerance: north_star asks 1e-5 relative for
+complex64 results; here every comparison uses rtol 1e-5 with an absolute floor of
+1e-5 * sum|coeff| (expectations of many cancelling terms)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import qhbm_oracle as orc
+import helpers as hp
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _plan(gates, n, nsym, ops, grad=True, T=0, K=0):
+  from qhbmlib import engine
+  terms, offs = hp.ops_to_tables(ops, n)
+  return engine.ExpectationPlan(gates, n, nsym, terms, offs, grad, T, K)
+
+
+def _scale(ops):
+  return np.array([sum(abs(c) for c, _ in op) for op in ops])
+
+
+def _compare(gates, n, nsym, ops, rng, n_states, T=0, K=0, mode="exact", check_state=True):
+  plan = _plan(gates, n, nsym, ops, True, T, K)
+  phi = rng.uniform(-1, 1, max(nsym, 1)).astype(np.float32)[:nsym]
+  basis = rng.choice(1 << n, size=min(n_states, 1 << n), replace=False).astype(np.int64)
+  dg = rng.uniform(-1, 1, (len(basis), len(ops))).astype(np.float32)
+  d_phi = torch.tensor(phi, device="cuda")
+  d_basis = torch.tensor(basis, device="cuda")
+  d_dg = torch.tensor(dg, device="cuda")
+  e_ref, g_ref = orc.batch_expectation_and_gradient(gates, n, phi, basis, ops, dg, mode)
+  scale = _scale(ops)
+  # forward only
+  e_fwd = plan.forward(d_basis, d_phi).cpu().numpy()
+  np.testing.assert_allclose(e_fwd, e_ref, rtol=RTOL, atol=RTOL * scale.max())
+  # forward + adjoint, reduced gradient
+  e, g = plan.forward_adjoint(d_basis, d_phi, d_dg, grad_mode=mode)
+  np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=RTOL, atol=RTOL * scale.max())
+  gscale = np.abs(g_ref).sum(0).max() + 1e-30
+  np.testing.assert_allclose(g.cpu().numpy(), g_ref.sum(0), rtol=RTOL, atol=RTOL * gscale)
+  # un-reduced gradient (the TFQ op's own output shape)
+  _, gp = plan.forward_adjoint(d_basis, d_phi, d_dg, per_state=True, grad_mode=mode)
+  np.testing.assert_allclose(gp.cpu().numpy(), g_ref, rtol=RTOL,
+                             atol=RTOL * (np.abs(g_ref).max() + 1e-30) * 3)
+  if check_state:
+    st = plan.state(int(basis[0]), d_phi).cpu().numpy()
+    np.testing.assert_allclose(st, orc.simulate(gates, n, phi, basis[0]), atol=3e-6)
+  return plan
+
+
+@pytest.mark.parametrize("n,layers,T,K", [(3, 2, 0, 4), (4, 2, 0, 5), (6, 3, 0, 4), (10, 2, 10, 5),
+                                           (11, 2, 9, 4), (12, 2, 10, 5), (12, 3, 9, 4), (12, 2, 0, 0),
+                                           (13, 2, 0, 0), (13, 2, 0, 5)])
+def test_hea_against_oracle(n, layers, T, K):
+  rng = np.random.default_rng(100 + n)
+  gates, names = orc.hea_circuit(n, layers)
+  ops = [orc.tfim_ring(n), orc.xxz_ring(n)] + orc.kobe_shards(n, 2)[:5]
+  _compare(gates, n, len(names), ops, rng, 5, T, K)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("n,T,K", [(2, 0, 4), (5, 0, 5), (11, 9, 4), (11, 10, 5)])
+def test_random_circuits_all_gate_types(seed, n, T, K):
+  rng = np.random.default_rng(1000 * n + seed)
+  gates = hp.random_circuit(n, 30, 6, rng)
+  ops = hp.random_ops(n, 3, rng)
+  _compare(gates, n, 6, ops, rng, 4, T, K)
+
+
+@pytest.mark.parametrize("n,T,K", [(4, 0, 4), (11, 9, 4)])
+def test_tfq_fd_mode(n, T, K):
+  rng = np.random.default_rng(7)
+  gates = hp.random_circuit(n, 25, 5, rng)
+  ops = hp.random_ops(n, 2, rng)
+  _compare(gates, n, 5, ops, rng, 3, T, K, mode="tfq_fd")
+
+
+def test_config1_4q_tfim_bernoulli_samples():
+  """BASELINE config 1: 4-qubit TFIM, 2-layer HEA, 1k Bernoulli samples -> unique -> weighted mean."""
+  rng = np.random.default_rng(5)
+  n = 4
+  gates, names = orc.hea_circuit(n, 2)
+  phi = np.random.default_rng(11).uniform(-1, 1, len(names)).astype(np.float32)
+  thetas = rng.uniform(-1, 1, n)
+  p1 = 1 / (1 + np.exp(-2 * thetas))
+  samples = (rng.random((1000, n)) < p1).astype(np.int8)
+  y, idx, counts = orc.unique_bitstrings_with_counts(samples)
+  ops = [orc.tfim_ring(n)]
+  ref_avg, ref_vals = orc.qhbm_expectation(gates, n, phi, y, counts, ops)
+  plan = _plan(gates, n, len(names), ops)
+  basis = torch.tensor(orc.bitstrings_to_index(y), device="cuda")
+  vals = plan.forward(basis, torch.tensor(phi, device="cuda")).cpu().numpy()
+  np.testing.assert_allclose(vals, ref_vals, rtol=RTOL, atol=RTOL * 8)
+  np.testing.assert_allclose(orc.weighted_average(counts, vals), ref_avg, rtol=RTOL, atol=RTOL * 8)
+
+
+def test_config3_16q_xxz_adjoint_sample_against_oracle():
+  """BASELINE config 3 (headline): 16-qubit XXZ, HEA L=2, adjoint gradient; oracle on a sample."""
+  rng = np.random.default_rng(3)
+  n = 16
+  gates, names = orc.hea_circuit(n, 2)
+  _compare(gates, n, len(names), [orc.xxz_ring(n)], rng, 3, check_state=True)
+
+
+def test_config3_full_size_properties():
+  """4096 unique 16-qubit bitstrings: size-independent checks (no oracle at this size):
+  the identity observable gives exactly 1 (norm), expectations are linear in the
+  observable, the gradient is linear in dgrad, and chunking does not change results."""
+  rng = np.random.default_rng(33)
+  n, u = 16, 4096
+  gates, names = orc.hea_circuit(n, 2)
+  h1, h2 = orc.xxz_ring(n), orc.tfim_ring(n)
+  ops = [[(1.0, {})], h1, h2, h1 + h2]
+  plan = _plan(gates, n, len(names), ops)
+  phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+  basis = torch.tensor(rng.choice(1 << n, u, replace=False).astype(np.int64), device="cuda")
+  dg = torch.tensor(rng.uniform(0, 1, (u, 4)).astype(np.float32), device="cuda")
+  e, g = plan.forward_adjoint(basis, phi, dg)
+  e = e.cpu().numpy().astype(np.float64)
+  np.testing.assert_allclose(e[:, 0], 1.0, atol=2e-6)
+  np.testing.assert_allclose(e[:, 3], e[:, 1] + e[:, 2], atol=2e-4)
+  _, g2 = plan.forward_adjoint(basis, phi, 2 * dg)
+  np.testing.assert_allclose(g2.cpu().numpy(), 2 * g.cpu().numpy(), rtol=1e-5, atol=1e-3)
+  # first half + second half == whole
+  _, ga = plan.forward_adjoint(basis[:u // 2], phi, dg[:u // 2])
+  _, gb = plan.forward_adjoint(basis[u // 2:], phi, dg[u // 2:])
+  np.testing.assert_allclose((ga + gb).cpu().numpy(), g.cpu().numpy(), rtol=1e-5,
+                             atol=1e-5 * float(g.abs().max()))
+  # identity observable has zero gradient
+  dg0 = torch.zeros_like(dg)
+  dg0[:, 0] = 1.0
+  _, g0 = plan.forward_adjoint(basis, phi, dg0)
+  assert float(g0.abs().max()) < 2e-3 * 1e-2 * u
+
+
+def test_trace_property_all_basis_states():
+  """sum over ALL basis states of <x|U^dag H U|x> = Tr H = 0 for a traceless H (n=12, 4096 rows)."""
+  n = 12
+  gates, names = orc.hea_circuit(n, 2)
+  ops = [orc.xxz_ring(n), [(1.0, {})]]
+  plan = _plan(gates, n, len(names), ops, grad=False)
+  rng = np.random.default_rng(8)
+  phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+  basis = torch.arange(1 << n, device="cuda", dtype=torch.int64)
+  e = plan.forward(basis, phi).double()
+  assert abs(float(e[:, 0].sum())) < 1e-2
+  np.testing.assert_allclose(e[:, 1].cpu().numpy(), 1.0, atol=2e-6)
+
+
+def test_host_buffer_entry_point():
+  rng = np.random.default_rng(12)
+  n = 6
+  gates, names = orc.hea_circuit(n, 2)
+  ops = [orc.tfim_ring(n), orc.xxz_ring(n)]
+  plan = _plan(gates, n, len(names), ops)
+  phi = rng.uniform(-1, 1, len(names)).astype(np.float32)
+  basis = rng.choice(1 << n, 7, replace=False).astype(np.uint64)
+  dg = rng.uniform(-1, 1, (7, 2)).astype(np.float32)
+  e, g = plan.run_host(basis, phi, dg)
+  e_ref, g_ref = orc.batch_expectation_and_gradient(gates, n, phi, basis, ops, dg)
+  np.testing.assert_allclose(e, e_ref, rtol=RTOL, atol=RTOL * 12)
+  np.testing.assert_allclose(g, g_ref.sum(0), rtol=RTOL, atol=RTOL * np.abs(g_ref).sum(0).max())
+  e2, g2 = plan.run_host(basis, phi)
+  assert g2 is None
+  np.testing.assert_allclose(e2, e_ref, rtol=RTOL, atol=RTOL * 12)
+
+
+def test_errors_are_reported():
+  from qhbmlib import _native as nat
+  from qhbmlib import engine
+  gates, names = orc.hea_circuit(3, 1)
+  terms, offs = hp.ops_to_tables([orc.tfim_ring(3)], 3)
+  bad = gates.copy()
+  bad["q0"][0] = 7
+  with pytest.raises(nat.NativeError, match="q0 out of range"):
+    engine.ExpectationPlan(bad, 3, len(names), terms, offs)
+  plan = engine.ExpectationPlan(gates, 3, len(names), terms, offs, with_gradient=False)
+  with pytest.raises(nat.NativeError, match="without with_gradient"):
+    plan.forward_adjoint(torch.zeros(1, dtype=torch.int64, device="cuda"),
+                         torch.zeros(len(names), device="cuda"),
+                         torch.zeros((1, 1), device="cuda"))
+  with pytest.raises(TypeError):
+    plan.forward(torch.zeros(1, dtype=torch.int64), torch.zeros(len(names)))
+
+
+def test_empty_batch_and_empty_circuit():
+  n = 5
+  gates = np.zeros(0, dtype=orc.GATE_DTYPE)
+  ops = [[(1.5, {}), (0.5, {0: "Z"})], [(2.0, {n - 1: "X"})]]
+  plan = _plan(gates, n, 0, ops)
+  basis = torch.tensor([0, 16, 31], device="cuda", dtype=torch.int64)
+  e = plan.forward(basis, torch.zeros(0, device="cuda")).cpu().numpy()
+  np.testing.assert_allclose(e, [[2.0, 0.0], [1.0, 0.0], [1.0, 0.0]], atol=1e-6)
+  e0 = plan.forward(basis[:0], torch.zeros(0, device="cuda"))
+  assert tuple(e0.shape) == (0, 2)

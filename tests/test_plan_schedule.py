@@ -1,0 +1,72 @@
+"""CPU tests of the host compiler (plan.cpp): the compiled sweep/pass/op program, run by
+the TEST-ONLY scalar interpreter in tests/native/, must reproduce the oracle.
+
+This covers the scheduling logic (tiles, register qubits, diagonal-run tables, gradient
+slots) and the coefficient jobs without a GPU.  The CUDA kernels execute the same program;
+their parity tests are the `-m gpu` ones."""
+import numpy as np
+import pytest
+
+from oracle import qhbm_oracle as orc
+import helpers as hp
+
+
+def _check(gates, n, nsym, ops, rng, T, K, mode="exact", atol=2e-5):
+  phi = rng.uniform(-1, 1, max(nsym, 1)).astype(np.float32)[:nsym]
+  dg = rng.uniform(-1, 1, len(ops)).astype(np.float32)
+  basis = int(rng.integers(0, 1 << n))
+  e, g, state, info = hp.verify_run(gates, n, nsym, ops, phi, basis, dg, True, T, K,
+                                    {"exact": 0, "tfq_fd": 1}[mode])
+  ref_state = orc.simulate(gates, n, phi, basis)
+  np.testing.assert_allclose(state, ref_state, atol=atol)
+  e_ref, g_ref = orc.adjoint_gradient(gates, n, phi, basis, ops, dg, mode)
+  np.testing.assert_allclose(e, e_ref, atol=atol * 10)
+  np.testing.assert_allclose(g, g_ref, atol=atol * 20)
+  return info
+
+
+@pytest.mark.parametrize("n,layers,T,K", [(3, 2, 0, 4), (4, 2, 0, 5), (6, 3, 0, 4), (10, 2, 10, 5),
+                                           (11, 2, 9, 4), (12, 2, 10, 5), (12, 3, 9, 4)])
+def test_hea_tfim_xxz(n, layers, T, K):
+  rng = np.random.default_rng(100 + n)
+  gates, names = orc.hea_circuit(n, layers)
+  ops = [orc.tfim_ring(n), orc.xxz_ring(n)] + orc.kobe_shards(n, 2)[:5]
+  info = _check(gates, n, len(names), ops, rng, T, K)
+  assert info[4] == (T or min(13, max(n, K + 5)))
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("n,T,K", [(2, 0, 4), (5, 0, 5), (11, 9, 4), (11, 10, 5)])
+def test_random_circuits_all_gate_types(seed, n, T, K):
+  rng = np.random.default_rng(1000 * n + seed)
+  nsym = 6
+  gates = hp.random_circuit(n, 30, nsym, rng)
+  ops = hp.random_ops(n, 3, rng)
+  _check(gates, n, nsym, ops, rng, T, K)
+
+
+@pytest.mark.parametrize("n,T,K", [(4, 0, 4), (11, 9, 4)])
+def test_tfq_fd_mode(n, T, K):
+  rng = np.random.default_rng(7)
+  gates = hp.random_circuit(n, 25, 5, rng)
+  ops = hp.random_ops(n, 2, rng)
+  _check(gates, n, 5, ops, rng, T, K, mode="tfq_fd")
+
+
+def test_empty_circuit_and_identity_terms():
+  rng = np.random.default_rng(3)
+  for n, T, K in [(3, 0, 4), (11, 9, 4)]:
+    gates = np.zeros(0, dtype=orc.GATE_DTYPE)
+    ops = [[(1.5, {}), (0.5, {0: "Z"})], [(2.0, {n - 1: "X"})]]
+    _check(gates, n, 0, ops, rng, T, K)
+
+
+def test_qmhl_style_circuit_plus_dagger():
+  """U_data + U_model^-1 with Z-shard observables (qnn.py:69-72, hamiltonian.py:48-51)."""
+  rng = np.random.default_rng(11)
+  n = 11
+  g1, n1 = orc.hea_circuit(n, 1, "data")
+  g2, n2 = orc.hea_circuit(n, 1, "model")
+  total = orc.concat_circuits(g1, len(n1), orc.inverse_circuit(g2))
+  ops = orc.kobe_shards(n, 2)[:12]
+  _check(total, n, len(n1) + len(n2), ops, rng, 9, 4)

@@ -73,10 +73,10 @@ namespace {
 
 template <int K, bool ADJ>
 void launch_sweep(const KernelArgs& ka, int n_states, int tiles, int threads, size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+  static size_t configured = 0;
+  if (smem > configured) {
+    QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
   }
   sweep_kernel<K, ADJ><<<(unsigned)(n_states * tiles), threads, smem, s>>>(ka);
   QHBM_CUDA(cudaGetLastError());

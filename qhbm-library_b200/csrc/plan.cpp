@@ -111,9 +111,11 @@ class Compiler {
       if (!two) {
         int b = bit_of(g.q0);
         int la = last[b];
-        if (la >= 0 && atoms[la].nq == 1) {  // fuse into the 1-qubit chain
+        // consecutive 1-qubit gates of the same class fuse (non-diagonal: one 2x2 product;
+        // diagonal: one phase-table entry).  Mixed classes stay apart so that X/Y powers keep
+        // their cheap rotation form and diagonal gates fold into the pass's phase tables.
+        if (la >= 0 && atoms[la].nq == 1 && atoms[la].diag == diag) {
           atoms[la].gates.push_back(gi);
-          atoms[la].diag = atoms[la].diag && diag;
           continue;
         }
         Atom a;
@@ -280,6 +282,12 @@ class Compiler {
           std::sort(s.begin(), s.end());
           for (int j = 0; j < K; ++j) ps.sorted[j] = s[j];
         }
+        for (int r = 0; r < (1 << kMaxRegQubits); ++r) {
+          uint32_t dep = 0;
+          for (int j = 0; j < K; ++j) if ((r >> j) & 1) dep |= 1u << ps.regbit[j];
+          const uint32_t sw = (dep & ~15u) | ((dep ^ (dep >> 4) ^ (dep >> 8) ^ (dep >> 12)) & 15u);
+          ps.eoff[r] = r < (1 << K) ? (uint16_t)sw : 0;
+        }
         ps.op_begin = (int)hp_.ops.size();
         ps.gsym_off = (int)hp_.gsym.size();
         ps.ngrad = 0;
@@ -336,7 +344,32 @@ class Compiler {
   }
 
   void emit_nondiag(const Atom& a, bool backward, const std::vector<int>& regpos, DevPass& ps) {
-    if (a.nq == 1) {
+    if (a.nq == 1 && a.gates.size() == 1 &&
+        (hp_.gates[a.gates[0]].type == QHBM_GATE_XPOW || hp_.gates[a.gates[0]].type == QHBM_GATE_YPOW)) {
+      // two-level X/Y power: rotation form, global phase dropped (tracked for debug output)
+      const int p = regpos[a.bit[0]];
+      const int gi = a.gates[0];
+      const qhbm_gate_t& g = hp_.gates[gi];
+      const bool is_y = g.type == QHBM_GATE_YPOW;
+      if (backward) {
+        if (g.sym[0] >= 0) {
+          DevOp o = make_op(is_y ? OP_GRAD_Y : OP_GRAD_X);
+          o.p0 = p;
+          o.coef = alloc_coef(4);
+          o.gslot = ps.ngrad++;
+          hp_.gsym.push_back(g.sym[0]);
+          add_job(PJ_KAPPA, o.coef, 0, is_y ? 1 : 0, 0, 0, {gi});
+          hp_.ops.push_back(o);
+        }
+      } else {
+        phase_gates_.push_back(gi);
+      }
+      DevOp o = make_op(is_y ? OP_YROT : OP_XROT);
+      o.p0 = p;
+      o.coef = alloc_coef(4);
+      add_job(PJ_ROT, o.coef, backward ? 1 : 0, 0, 0, 0, {gi});
+      hp_.ops.push_back(o);
+    } else if (a.nq == 1) {
       const int p = regpos[a.bit[0]];
       if (backward) {
         const int gi = a.gates[0];
@@ -458,6 +491,8 @@ class Compiler {
     if (!run.gd_ops.empty()) {
       DevOp b = make_op(OP_GD_BEGIN);
       b.aux0 = (int)run.gd_ops.size();
+      b.aux1 = 0;
+      for (auto& o : run.gd_ops) if (o.type == OP_GD_REG2) b.aux1 = 1;
       hp_.ops.push_back(b);
       for (auto& o : run.gd_ops) hp_.ops.push_back(o);
     }
@@ -515,6 +550,7 @@ class Compiler {
   void build_terms(const OpsIR& o) {
     // k = coeff * (-i)^{ny}; sign from parity(i & z) of the OUTPUT index i (derivation in DESIGN.md).
     const uint32_t tile_mask = hp_.n_eff <= hp_.T ? 0xffffffffu : ((1u << hp_.T) - 1u);
+    const int mshift = hp_.T - hp_.K;  // the thread's m-th amplitude has tile-local index m << mshift | tid
     for (int j = 0; j < o.n_ops(); ++j) {
       DevOpRange r;
       r.group_begin = (int32_t)hp_.groups.size();
@@ -525,6 +561,7 @@ class Compiler {
       while (i < idx.size()) {
         const uint32_t x = o.terms[idx[i]].xmask;
         DevTermGroup g;
+        std::memset(&g, 0, sizeof(g));
         g.x = x;
         g.xl = (x & ~tile_mask) ? -1 : (int32_t)x;
         g.term_begin = (int32_t)hp_.terms.size();
@@ -535,8 +572,12 @@ class Compiler {
           d.kr = ny == 0 ? t.coeff : (ny == 2 ? -t.coeff : 0.f);
           d.ki = ny == 1 ? -t.coeff : (ny == 3 ? t.coeff : 0.f);
           d.z = t.zmask;
-          d.pad = 0;
-          hp_.terms.push_back(d);
+          d.mword = 0;
+          for (int m = 0; m < (1 << hp_.K); ++m)
+            if (__builtin_popcount(((uint32_t)m << mshift) & t.zmask) & 1) d.mword |= 1u << m;
+          if (d.ki != 0.f) g.is_complex = 1;
+          if (t.zmask == 0) { g.k0r += d.kr; g.k0i += d.ki; }
+          else hp_.terms.push_back(d);
           ++i;
         }
         g.term_end = (int32_t)hp_.terms.size();
@@ -558,6 +599,11 @@ class Compiler {
     hp_.n_sweeps_fwd = (int)fs.size();
     hp_.n_sweeps_bwd = (int)bs.size();
     build_terms(o);
+    hp_.phase_coef = -1;
+    if (!phase_gates_.empty()) {
+      hp_.phase_coef = alloc_coef(4);
+      add_job(PJ_PHASE, hp_.phase_coef, 0, 0, 0, 0, std::vector<int32_t>(phase_gates_.begin(), phase_gates_.end()));
+    }
     std::vector<int> contiguous;
     for (int b = 0; b < std::min(hp_.T, hp_.n_eff); ++b) contiguous.push_back(b);
 
@@ -614,6 +660,7 @@ class Compiler {
 
  private:
   HostPlan& hp_;
+  std::vector<int> phase_gates_;  // forward X/Y powers whose global phase was dropped
 };
 
 }  // namespace

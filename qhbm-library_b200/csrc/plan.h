@@ -40,6 +40,7 @@ struct HostPlan {
   std::vector<PrepJob> jobs;
   std::vector<int32_t> lists;
   int32_t ncoef = 0;
+  int32_t phase_coef = -1;  // coefficient slot of the dropped global phase (debug state output)
   std::vector<LaunchDesc> launches;       // forward (+ expectation + backward) program
   int n_fwd_launches = 0;                 // launches[0..n_fwd_launches) leave psi = U|basis>
 

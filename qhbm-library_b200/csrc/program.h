@@ -32,10 +32,15 @@ enum OpType : int32_t {
   OP_DREG_TAB,    // amp[r] *= F * tab[r]; F = 1; coef -> 2^K complex
   OP_DAPPLY,      // amp[r] *= F; F = 1
   OP_DCROSS,      // amps with register bit p0 = v: *= c[2*bit(aux0) + v]; coef -> 4 complex
+  OP_XROT,        // (c I - i s X) on register position p0, global phase dropped; coef -> (c, s)
+  OP_YROT,        // (c I - i s Y) on register position p0, global phase dropped; coef -> (c, s)
   // gradient ops (adjoint sweeps only); value lands in scratch slot gslot
   OP_GRAD_MAT1,   // 2 Re <lam| M |psi>, M 2x2 at coef, position p0
   OP_GRAD_MAT2,   // same for 4x4, p0 as in OP_MAT2
-  OP_GD_BEGIN,    // starts a run of aux0 diagonal-gradient ops (they share conj(lam)*psi)
+  OP_GRAD_X,      // kappa * Im <lam| X_p0 |psi>; coef -> kappa   (two-level X-type gate)
+  OP_GRAD_Y,      // kappa * Im <lam| Y_p0 |psi>; coef -> kappa
+  OP_GD_BEGIN,    // starts a run of aux0 diagonal-gradient ops (they share conj(lam)*psi);
+                  //     aux1 != 0: pair marginals are needed (some OP_GD_REG2 in the run)
   OP_GD_CONST,    // entries M[sel] at coef (complex); sel = 2*bit(aux0)+bit(aux1) (aux1<0: bit(aux0))
   OP_GD_REG1,     // sel = register bit p0; coef -> 2 complex
   OP_GD_REG2,     // sel = 2*regbit(p0) + regbit(p1); coef -> 4 complex
@@ -52,12 +57,13 @@ struct DevOp {  // 32 bytes
   int32_t pad;
 };
 
-struct DevPass {  // 64 bytes
+struct DevPass {  // 128 bytes
   int32_t regbit[kMaxRegQubits];     // tile-local bit of register position j
   int32_t sorted[kMaxRegQubits];     // the same bits in ascending order
   int32_t op_begin, op_end;
   int32_t ngrad, gsym_off;           // gradient slots of this pass -> symbols gsym[gsym_off..]
   int32_t pad[2];
+  uint16_t eoff[1 << kMaxRegQubits]; // swizzled smem offset of register amplitude r (XOR with the thread base)
 };
 
 // Contiguous run of tile-local bits mapped to contiguous state-index bits.
@@ -91,12 +97,16 @@ struct LaunchDesc {
 struct DevTerm {  // coefficient(i) += (kr + i ki) * (-1)^{parity(i & z)}
   float kr, ki;
   uint32_t z;
-  uint32_t pad;
+  uint32_t mword;      // bit m = parity(z & index bits of the thread's m-th amplitude) in the
+                       // expectation launch (contiguous tile, amplitude m = m * nthreads + tid)
 };
 struct DevTermGroup {  // terms sharing one x-mask: H psi[i] += coefficient(i) * psi[i ^ x]
   uint32_t x;          // state-index xor mask
   int32_t xl;          // tile-local xor mask if the partner is inside the tile, else -1
-  int32_t term_begin, term_end;
+  int32_t term_begin, term_end;  // terms with z != 0
+  float k0r, k0i;      // sum of the z == 0 terms (index-independent part of the coefficient)
+  int32_t is_complex;  // some term has an imaginary coefficient (odd number of Y)
+  int32_t pad;
 };
 struct DevOpRange {
   int32_t group_begin, group_end;
@@ -112,6 +122,10 @@ enum PrepKind : int32_t {
   PJ_DTAB,       // phase table with 2^d entries; list = triples (gate, posA, posB): entry[v] =
                  //   prod_g diag_g[2*bit(v,posA) + bit(v,posB)] (posB < 0 -> 1q gate); a: dagger
   PJ_DPAIR,      // 4 (or 2) diagonal entries of one gate; a: dagger; b: swap roles
+  PJ_ROT,        // (cos, sin)(pi t / 2) of an XPow / YPow gate; a: dagger (sin negated)
+  PJ_KAPPA,      // kappa of a two-level X/Y-type gate (b: 0 = X, 1 = Y) for param c:
+                 //   dG G^dagger = i(c0 I - kappa/2 A)  =>  d<H>/ds = kappa Im<lam|A|psi>
+  PJ_PHASE,      // product of the dropped global phases e^{i pi t (g + 1/2)} of the list gates
 };
 struct PrepJob {  // 32 bytes
   int32_t kind;

@@ -128,6 +128,7 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
   ka.T = hp.T;
   ka.O = hp.O;
   ka.P = hp.P;
+  ka.phase_coef = hp.phase_coef;
 }
 
 void run_prep(qhbm_plan* p, const float* d_symbols, int mode, cudaStream_t s) {
@@ -382,8 +383,13 @@ int qhbm_debug_state(qhbm_plan_t* p, uint64_t basis_idx, const float* d_symbols,
       if (!multi) ka.L.flags |= LF_WRITE_STATE;
       launch_any(p, hp.grad, ka, 1, s);
     }
-    if (multi)
-      QHBM_CUDA(cudaMemcpyAsync(d_state_out, p->d_psi.p, sizeof(float2) << hp.n_eff, cudaMemcpyDeviceToDevice, s));
+    if (multi) {
+      // one more launch: load the stored state and write it out with the dropped global phase
+      ka.L = hp.launches[hp.n_fwd_launches];  // the expectation launch has the contiguous tile map
+      ka.L.pass_a_begin = ka.L.pass_a_end = ka.L.pass_b_begin = ka.L.pass_b_end = 0;
+      ka.L.flags = LF_LOAD_PSI | LF_WRITE_STATE;
+      launch_any(p, hp.grad, ka, 1, s);
+    }
   });
 }
 

@@ -38,6 +38,7 @@ struct KernelArgs {
   int32_t n, T, O, P;
   int32_t grow0;          // accumulator row of this chunk's first state (per-state gradients)
   int32_t per_state;
+  int32_t phase_coef;     // coef offset of the dropped global phase (debug state output), or -1
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t x) {
@@ -66,9 +67,40 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+struct OpRec {
+  int type, p0, p1, coef, gslot, aux0, aux1;
+};
+__device__ __forceinline__ OpRec load_op(const DevOp* op) {
+  const int4 a = __ldg(reinterpret_cast<const int4*>(op));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(op) + 1);
+  OpRec r;
+  r.type = a.x; r.p0 = a.y; r.p1 = a.z; r.coef = a.w;
+  r.gslot = b.x; r.aux0 = b.y; r.aux1 = b.z;
+  return r;
+}
+
 // ---------------------------------------------------------------------------------
-// Register-level gate blocks.  P / LO are compile-time register positions.
+// Register-level gate blocks.  P / LO are compile-time register positions.  BOTH
+// applies the same block to psi (a) and lambda (b).
 // ---------------------------------------------------------------------------------
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+};
+// Calls f(IntC<p>{}) with the register position as a compile-time constant.
+template <int K, class F>
+__device__ __forceinline__ void dispatch_pos(int p, F&& f) {
+  switch (p) {
+    case 0: f(IntC<0>{}); break;
+    case 1: f(IntC<1>{}); break;
+    case 2: f(IntC<2>{}); break;
+    case 3: f(IntC<3>{}); break;
+    default:
+      if constexpr (K > 4) f(IntC<4>{});
+      break;
+  }
+}
+
 template <int K, int P>
 __device__ __forceinline__ void mat1(float2 (&a)[1 << K], const float4 m0, const float4 m1) {
 #pragma unroll
@@ -81,15 +113,54 @@ __device__ __forceinline__ void mat1(float2 (&a)[1 << K], const float4 m0, const
     a[r | (1 << P)].y = m1.x * x0.y + m1.y * x0.x + m1.z * x1.y + m1.w * x1.x;
   }
 }
-template <int K>
-__device__ __forceinline__ void mat1_dyn(float2 (&a)[1 << K], int p, const float4 m0, const float4 m1) {
-  switch (p) {
-    case 0: mat1<K, 0>(a, m0, m1); break;
-    case 1: mat1<K, 1>(a, m0, m1); break;
-    case 2: mat1<K, 2>(a, m0, m1); break;
-    case 3: mat1<K, 3>(a, m0, m1); break;
-    default: if constexpr (K > 4) mat1<K, 4>(a, m0, m1); break;
+// (c I - i s X): y0 = c x0 - i s x1, y1 = -i s x0 + c x1
+template <int K, int P>
+__device__ __forceinline__ void xrot(float2 (&a)[1 << K], const float c, const float s) {
+#pragma unroll
+  for (int r = 0; r < (1 << K); ++r) {
+    if (r & (1 << P)) continue;
+    const float2 x0 = a[r], x1 = a[r | (1 << P)];
+    a[r].x = fmaf(s, x1.y, c * x0.x);
+    a[r].y = fmaf(-s, x1.x, c * x0.y);
+    a[r | (1 << P)].x = fmaf(s, x0.y, c * x1.x);
+    a[r | (1 << P)].y = fmaf(-s, x0.x, c * x1.y);
   }
+}
+// (c I - i s Y) = [[c, -s], [s, c]]
+template <int K, int P>
+__device__ __forceinline__ void yrot(float2 (&a)[1 << K], const float c, const float s) {
+#pragma unroll
+  for (int r = 0; r < (1 << K); ++r) {
+    if (r & (1 << P)) continue;
+    const float2 x0 = a[r], x1 = a[r | (1 << P)];
+    a[r].x = fmaf(-s, x1.x, c * x0.x);
+    a[r].y = fmaf(-s, x1.y, c * x0.y);
+    a[r | (1 << P)].x = fmaf(s, x0.x, c * x1.x);
+    a[r | (1 << P)].y = fmaf(s, x0.y, c * x1.y);
+  }
+}
+// Im <b| X_P |a> and Im <b| Y_P |a> over the thread's amplitudes
+template <int K, int P>
+__device__ __forceinline__ float im_bxa(const float2 (&a)[1 << K], const float2 (&b)[1 << K]) {
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < (1 << K); ++r) {
+    if (r & (1 << P)) continue;
+    const int q = r | (1 << P);
+    s += b[r].x * a[q].y - b[r].y * a[q].x + b[q].x * a[r].y - b[q].y * a[r].x;
+  }
+  return s;
+}
+template <int K, int P>
+__device__ __forceinline__ float im_bya(const float2 (&a)[1 << K], const float2 (&b)[1 << K]) {
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < (1 << K); ++r) {
+    if (r & (1 << P)) continue;
+    const int q = r | (1 << P);
+    s += b[q].x * a[r].x + b[q].y * a[r].y - b[r].x * a[q].x - b[r].y * a[q].y;
+  }
+  return s;
 }
 
 // 2 Re sum_r conj(b_r) (M a)_r over the thread's amplitudes.
@@ -109,29 +180,11 @@ __device__ __forceinline__ float grad_mat1(const float2 (&a)[1 << K], const floa
   }
   return 2.f * s;
 }
-template <int K>
-__device__ __forceinline__ float grad_mat1_dyn(const float2 (&a)[1 << K], const float2 (&b)[1 << K], int p,
-                                               const float4 m0, const float4 m1) {
-  switch (p) {
-    case 0: return grad_mat1<K, 0>(a, b, m0, m1);
-    case 1: return grad_mat1<K, 1>(a, b, m0, m1);
-    case 2: return grad_mat1<K, 2>(a, b, m0, m1);
-    case 3: return grad_mat1<K, 3>(a, b, m0, m1);
-    default: if constexpr (K > 4) return grad_mat1<K, 4>(a, b, m0, m1);
-  }
-  return 0.f;
-}
 
 // 4x4 block on register positions (LO+1, LO); matrix index = 2*bit(LO+1) + bit(LO).
+// GRAD: returns 2 Re <b| M |a> and leaves a untouched.
 template <int K, int LO, bool GRAD>
 __device__ __forceinline__ float mat2(float2 (&a)[1 << K], const float2 (&b)[1 << K], const float* __restrict__ mp) {
-  float2 m[16];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 v = ldg4(mp + 4 * i);
-    m[2 * i] = make_float2(v.x, v.y);
-    m[2 * i + 1] = make_float2(v.z, v.w);
-  }
   float s = 0.f;
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
@@ -141,13 +194,12 @@ __device__ __forceinline__ float mat2(float2 (&a)[1 << K], const float2 (&b)[1 <
     for (int j = 0; j < 4; ++j) x[j] = a[r | (j << LO)];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float yr = 0.f, yi = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        yr += m[4 * i + j].x * x[j].x - m[4 * i + j].y * x[j].y;
-        yi += m[4 * i + j].x * x[j].y + m[4 * i + j].y * x[j].x;
-      }
-      y[i] = make_float2(yr, yi);
+      // the matrix rows are re-read (uniform, L1-resident) instead of holding 32 registers
+      const float4 m01 = ldg4(mp + 8 * i), m23 = ldg4(mp + 8 * i + 4);
+      y[i].x = m01.x * x[0].x - m01.y * x[0].y + m01.z * x[1].x - m01.w * x[1].y +
+               m23.x * x[2].x - m23.y * x[2].y + m23.z * x[3].x - m23.w * x[3].y;
+      y[i].y = m01.x * x[0].y + m01.y * x[0].x + m01.z * x[1].y + m01.w * x[1].x +
+               m23.x * x[2].y + m23.y * x[2].x + m23.z * x[3].y + m23.w * x[3].x;
     }
     if constexpr (GRAD) {
 #pragma unroll
@@ -160,119 +212,98 @@ __device__ __forceinline__ float mat2(float2 (&a)[1 << K], const float2 (&b)[1 <
   return 2.f * s;
 }
 
+// amplitudes with register bit P = v are multiplied by e_v; exact identities are skipped
 template <int K, int P>
-__device__ __forceinline__ void mul_sel(float2 (&a)[1 << K], const float2 e0, const float2 e1) {
+__device__ __forceinline__ void mul_sel(float2 (&a)[1 << K], const float2 e0, const float2 e1, const bool id0,
+                                        const bool id1) {
 #pragma unroll
-  for (int r = 0; r < (1 << K); ++r) a[r] = cmul(a[r], (r & (1 << P)) ? e1 : e0);
-}
-template <int K>
-__device__ __forceinline__ void mul_sel_dyn(float2 (&a)[1 << K], int p, const float2 e0, const float2 e1) {
-  switch (p) {
-    case 0: mul_sel<K, 0>(a, e0, e1); break;
-    case 1: mul_sel<K, 1>(a, e0, e1); break;
-    case 2: mul_sel<K, 2>(a, e0, e1); break;
-    case 3: mul_sel<K, 3>(a, e0, e1); break;
-    default: if constexpr (K > 4) mul_sel<K, 4>(a, e0, e1); break;
+  for (int r = 0; r < (1 << K); ++r) {
+    if (r & (1 << P)) { if (!id1) a[r] = cmul(a[r], e1); }
+    else { if (!id0) a[r] = cmul(a[r], e0); }
   }
 }
 
-template <int K, int P>
-__device__ __forceinline__ float sum_bit(const float (&u)[1 << K]) {
-  float s = 0.f;
+template <int N>
+__device__ __forceinline__ float pick(const float (&v)[N], int i) {
+  float r = v[0];
 #pragma unroll
-  for (int r = 0; r < (1 << K); ++r)
-    if (r & (1 << P)) s += u[r];
-  return s;
-}
-template <int K>
-__device__ __forceinline__ float sum_bit_dyn(const float (&u)[1 << K], int p) {
-  switch (p) {
-    case 0: return sum_bit<K, 0>(u);
-    case 1: return sum_bit<K, 1>(u);
-    case 2: return sum_bit<K, 2>(u);
-    case 3: return sum_bit<K, 3>(u);
-    default: if constexpr (K > 4) return sum_bit<K, 4>(u);
-  }
-  return 0.f;
-}
-template <int K, int PH, int PL>
-__device__ __forceinline__ float sum_both(const float (&u)[1 << K]) {
-  float s = 0.f;
-#pragma unroll
-  for (int r = 0; r < (1 << K); ++r)
-    if ((r & (1 << PH)) && (r & (1 << PL))) s += u[r];
-  return s;
-}
-template <int K>
-__device__ __forceinline__ float sum_both_dyn(const float (&u)[1 << K], int ph, int pl) {
-  switch (ph * 8 + pl) {
-    case 8 + 0: return sum_both<K, 1, 0>(u);
-    case 16 + 0: return sum_both<K, 2, 0>(u);
-    case 16 + 1: return sum_both<K, 2, 1>(u);
-    case 24 + 0: return sum_both<K, 3, 0>(u);
-    case 24 + 1: return sum_both<K, 3, 1>(u);
-    case 24 + 2: return sum_both<K, 3, 2>(u);
-    default:
-      if constexpr (K > 4) {
-        switch (pl) {
-          case 0: return sum_both<K, 4, 0>(u);
-          case 1: return sum_both<K, 4, 1>(u);
-          case 2: return sum_both<K, 4, 2>(u);
-          default: return sum_both<K, 4, 3>(u);
-        }
-      }
-  }
-  return 0.f;
+  for (int k = 1; k < N; ++k) r = (i == k) ? v[k] : r;
+  return r;
 }
 
-// Run of diagonal-gate gradient ops: they all need only w_r = conj(lam_r) psi_r, which no
-// diagonal gate changes, so w is formed once per run.
+// Marginal sums of w_r = conj(b_r) a_r = u_r + i v_r over the register index r:
+// totals, per register bit, and per pair of register bits.  No diagonal gate changes w,
+// so one set of marginals serves a whole run of diagonal-gate gradients.
 template <int K>
-__device__ __noinline__ void grad_diag_run(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
-                                           const DevOp* __restrict__ ops, int count,
-                                           const float* __restrict__ coef, float* scratch, uint32_t gbase,
-                                           uint32_t tid, uint32_t nthr) {
-  constexpr int R = 1 << K;
-  float u[R], v[R];
-  float U = 0.f, V = 0.f;
+struct Marginals {
+  static constexpr int NP = K * (K - 1) / 2;
+  float U, V;
+  float Up[K], Vp[K];
+  float Upp[NP > 0 ? NP : 1], Vpp[NP > 0 ? NP : 1];
+};
+template <int K>
+__device__ __forceinline__ void compute_marginals(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
+                                                  Marginals<K>& mg, const bool pairs) {
+  mg.U = mg.V = 0.f;
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    u[r] = b[r].x * a[r].x + b[r].y * a[r].y;  // Re conj(b) a
-    v[r] = b[r].x * a[r].y - b[r].y * a[r].x;  // Im conj(b) a
-    U += u[r];
-    V += v[r];
-  }
-  for (int i = 0; i < count; ++i) {
-    const int type = __ldg(&ops[i].type);
-    const int p0 = __ldg(&ops[i].p0), p1 = __ldg(&ops[i].p1);
-    const int aux0 = __ldg(&ops[i].aux0), aux1 = __ldg(&ops[i].aux1);
-    const float* e = coef + __ldg(&ops[i].coef);
-    float val = 0.f;
-    if (type == OP_GD_CONST) {
-      int sel = (gbase >> aux0) & 1;
-      if (aux1 >= 0) sel = 2 * sel + ((gbase >> aux1) & 1);
-      const float2 m = ldg2(e + 2 * sel);
-      val = m.x * U - m.y * V;
-    } else if (type == OP_GD_REG1) {
-      const float U1 = sum_bit_dyn<K>(u, p0), V1 = sum_bit_dyn<K>(v, p0);
-      const float4 m = ldg4(e);
-      val = m.x * (U - U1) - m.y * (V - V1) + m.z * U1 - m.w * V1;
-    } else if (type == OP_GD_MIX) {
-      const int cb = (gbase >> aux0) & 1;
-      const float U1 = sum_bit_dyn<K>(u, p0), V1 = sum_bit_dyn<K>(v, p0);
-      const float4 m = ldg4(e + 4 * cb);
-      val = m.x * (U - U1) - m.y * (V - V1) + m.z * U1 - m.w * V1;
-    } else if (type == OP_GD_REG2) {
-      const float Uh = sum_bit_dyn<K>(u, p0), Vh = sum_bit_dyn<K>(v, p0);
-      const float Ul = sum_bit_dyn<K>(u, p1), Vl = sum_bit_dyn<K>(v, p1);
-      const float U11 = sum_both_dyn<K>(u, p0, p1), V11 = sum_both_dyn<K>(v, p0, p1);
-      const float4 m01 = ldg4(e), m23 = ldg4(e + 4);
-      val = m01.x * (U - Uh - Ul + U11) - m01.y * (V - Vh - Vl + V11)  // sel 0
-            + m01.z * (Ul - U11) - m01.w * (Vl - V11)                   // sel 1: lo bit only
-            + m23.x * (Uh - U11) - m23.y * (Vh - V11)                   // sel 2: hi bit only
-            + m23.z * U11 - m23.w * V11;                                // sel 3
+  for (int p = 0; p < K; ++p) mg.Up[p] = mg.Vp[p] = 0.f;
+#pragma unroll
+  for (int q = 0; q < Marginals<K>::NP; ++q) mg.Upp[q] = mg.Vpp[q] = 0.f;
+#pragma unroll
+  for (int r = 0; r < (1 << K); ++r) {
+    const float u = b[r].x * a[r].x + b[r].y * a[r].y;  // Re conj(b) a
+    const float v = b[r].x * a[r].y - b[r].y * a[r].x;  // Im conj(b) a
+    mg.U += u;
+    mg.V += v;
+#pragma unroll
+    for (int p = 0; p < K; ++p)
+      if (r & (1 << p)) { mg.Up[p] += u; mg.Vp[p] += v; }
+    if (pairs) {
+#pragma unroll
+      for (int ph = 1; ph < K; ++ph)
+#pragma unroll
+        for (int pl = 0; pl < ph; ++pl)
+          if ((r & (1 << ph)) && (r & (1 << pl))) {
+            mg.Upp[ph * (ph - 1) / 2 + pl] += u;
+            mg.Vpp[ph * (ph - 1) / 2 + pl] += v;
+          }
     }
-    scratch[__ldg(&ops[i].gslot) * nthr + tid] = 2.f * val;
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
+                                              const DevOp* __restrict__ ops, int count, bool pairs,
+                                              const float* __restrict__ coef, float* scratch, uint32_t gbase,
+                                              uint32_t tid, uint32_t nthr) {
+  Marginals<K> mg;
+  compute_marginals<K>(a, b, mg, pairs);
+  for (int i = 0; i < count; ++i) {
+    const OpRec op = load_op(ops + i);
+    const float* e = coef + op.coef;
+    float val;
+    if (op.type == OP_GD_CONST) {
+      int sel = (gbase >> op.aux0) & 1;
+      if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1);
+      const float2 m = ldg2(e + 2 * sel);
+      val = m.x * mg.U - m.y * mg.V;
+    } else if (op.type == OP_GD_REG1 || op.type == OP_GD_MIX) {
+      const int cb = op.type == OP_GD_MIX ? ((gbase >> op.aux0) & 1) : 0;
+      const float U1 = pick<K>(mg.Up, op.p0), V1 = pick<K>(mg.Vp, op.p0);
+      const float4 m = ldg4(e + 4 * cb);
+      val = m.x * (mg.U - U1) - m.y * (mg.V - V1) + m.z * U1 - m.w * V1;
+    } else {  // OP_GD_REG2, p0 > p1
+      const float Uh = pick<K>(mg.Up, op.p0), Vh = pick<K>(mg.Vp, op.p0);
+      const float Ul = pick<K>(mg.Up, op.p1), Vl = pick<K>(mg.Vp, op.p1);
+      const int pi = op.p0 * (op.p0 - 1) / 2 + op.p1;
+      const float U11 = pick<Marginals<K>::NP>(mg.Upp, pi), V11 = pick<Marginals<K>::NP>(mg.Vpp, pi);
+      const float4 m01 = ldg4(e), m23 = ldg4(e + 4);
+      val = m01.x * (mg.U - Uh - Ul + U11) - m01.y * (mg.V - Vh - Vl + V11)  // sel 0
+            + m01.z * (Ul - U11) - m01.w * (Vl - V11)                         // sel 1: lo bit only
+            + m23.x * (Uh - U11) - m23.y * (Vh - V11)                         // sel 2: hi bit only
+            + m23.z * U11 - m23.w * V11;                                      // sel 3
+    }
+    scratch[op.gslot * nthr + tid] = 2.f * val;
   }
 }
 
@@ -282,17 +313,9 @@ __device__ __noinline__ void grad_diag_run(const float2 (&a)[1 << K], const floa
 // ---------------------------------------------------------------------------------
 template <int K, bool BOTH>
 __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __restrict__ ps, float2* s_psi,
-                                         float2* s_lam, uint32_t* s_E, uint32_t goff, uint32_t u) {
+                                         float2* s_lam, uint32_t goff, uint32_t u) {
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-  __syncthreads();  // tile complete in smem; s_E reusable
-  if (tid < R) {
-    uint32_t dep = 0;
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-      if ((tid >> j) & 1) dep |= 1u << __ldg(&ps->regbit[j]);
-    s_E[tid] = swz(dep);
-  }
   uint32_t base = tid;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
@@ -301,14 +324,26 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   }
   const uint32_t B = swz(base);
   const uint32_t gbase = goff | scatter_bits(base, ka.L.runs, ka.L.n_runs);
-  __syncthreads();
+  uint32_t eo[R];
+  {
+    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
+#pragma unroll
+    for (int i = 0; i < R / 8; ++i) {
+      const uint4 w = __ldg(ep + i);
+      eo[8 * i + 0] = w.x & 0xffffu; eo[8 * i + 1] = w.x >> 16;
+      eo[8 * i + 2] = w.y & 0xffffu; eo[8 * i + 3] = w.y >> 16;
+      eo[8 * i + 4] = w.z & 0xffffu; eo[8 * i + 5] = w.z >> 16;
+      eo[8 * i + 6] = w.w & 0xffffu; eo[8 * i + 7] = w.w >> 16;
+    }
+  }
+  __syncthreads();  // tile complete in smem
 
   float2 a[R];
   float2 b[BOTH ? R : 1];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    a[r] = s_psi[B ^ s_E[r]];
-    if constexpr (BOTH) b[r] = s_lam[B ^ s_E[r]];
+    a[r] = s_psi[B ^ eo[r]];
+    if constexpr (BOTH) b[r] = s_lam[B ^ eo[r]];
   }
   const int ngrad = BOTH ? __ldg(&ps->ngrad) : 0;
   float* scratch = reinterpret_cast<float*>(s_psi);
@@ -316,19 +351,42 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
 
   float2 F = make_float2(1.f, 0.f);
   const int op_end = __ldg(&ps->op_end);
-  for (int oi = __ldg(&ps->op_begin); oi < op_end; ++oi) {
-    const DevOp* op = ka.ops + oi;
-    const int type = __ldg(&op->type);
-    const int p0 = __ldg(&op->p0);
-    const float* cf = ka.coef + __ldg(&op->coef);
-    switch (type) {
+  int oi = __ldg(&ps->op_begin);
+  OpRec nxt;
+  if (oi < op_end) nxt = load_op(ka.ops + oi);
+  while (oi < op_end) {
+    const OpRec op = nxt;
+    const float* cf = ka.coef + op.coef;
+    int step = 1;
+    if (op.type == OP_GD_BEGIN) step += op.aux0;
+    if (oi + step < op_end) nxt = load_op(ka.ops + oi + step);  // prefetch the next descriptor
+    switch (op.type) {
+      case OP_XROT: {
+        const float2 cs = ldg2(cf);
+        dispatch_pos<K>(op.p0, [&](auto pc) {
+          constexpr int P = decltype(pc)::value;
+          xrot<K, P>(a, cs.x, cs.y);
+          if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
+        });
+      } break;
+      case OP_YROT: {
+        const float2 cs = ldg2(cf);
+        dispatch_pos<K>(op.p0, [&](auto pc) {
+          constexpr int P = decltype(pc)::value;
+          yrot<K, P>(a, cs.x, cs.y);
+          if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
+        });
+      } break;
       case OP_MAT1: {
         const float4 m0 = ldg4(cf), m1 = ldg4(cf + 4);
-        mat1_dyn<K>(a, p0, m0, m1);
-        if constexpr (BOTH) mat1_dyn<K>(b, p0, m0, m1);
+        dispatch_pos<K>(op.p0, [&](auto pc) {
+          constexpr int P = decltype(pc)::value;
+          mat1<K, P>(a, m0, m1);
+          if constexpr (BOTH) mat1<K, P>(b, m0, m1);
+        });
       } break;
       case OP_MAT2: {
-        if (p0 == 0) {
+        if (op.p0 == 0) {
           mat2<K, 0, false>(a, a, cf);
           if constexpr (BOTH) mat2<K, 0, false>(b, b, cf);
         } else {
@@ -337,13 +395,12 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
         }
       } break;
       case OP_DCONST_TAB: {
-        const uint32_t idx = (gbase >> __ldg(&op->aux0)) & (uint32_t)__ldg(&op->aux1);
+        const uint32_t idx = (gbase >> op.aux0) & (uint32_t)op.aux1;
         F = cmul(F, ldg2(cf + 2 * idx));
       } break;
       case OP_DCONST_PAIR: {
-        const int a0 = __ldg(&op->aux0), a1 = __ldg(&op->aux1);
-        int sel = (gbase >> a0) & 1;
-        if (a1 >= 0) sel = 2 * sel + ((gbase >> a1) & 1);
+        int sel = (gbase >> op.aux0) & 1;
+        if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1);
         F = cmul(F, ldg2(cf + 2 * sel));
       } break;
       case OP_DREG_TAB: {
@@ -364,28 +421,45 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
         F = make_float2(1.f, 0.f);
       } break;
       case OP_DCROSS: {
-        const int cb = (gbase >> __ldg(&op->aux0)) & 1;
+        const int cb = (gbase >> op.aux0) & 1;
         const float4 e = ldg4(cf + 4 * cb);
         const float2 e0 = make_float2(e.x, e.y), e1 = make_float2(e.z, e.w);
-        mul_sel_dyn<K>(a, p0, e0, e1);
-        if constexpr (BOTH) mul_sel_dyn<K>(b, p0, e0, e1);
+        const bool id0 = e.x == 1.f && e.y == 0.f, id1 = e.z == 1.f && e.w == 0.f;
+        if (!(id0 && id1)) {
+          dispatch_pos<K>(op.p0, [&](auto pc) {
+            constexpr int P = decltype(pc)::value;
+            mul_sel<K, P>(a, e0, e1, id0, id1);
+            if constexpr (BOTH) mul_sel<K, P>(b, e0, e1, id0, id1);
+          });
+        }
       } break;
       default:
         if constexpr (BOTH) {
-          if (type == OP_GRAD_MAT1) {
+          if (op.type == OP_GRAD_X) {
+            const float kappa = __ldg(cf);
+            float v = 0.f;
+            dispatch_pos<K>(op.p0, [&](auto pc) { v = im_bxa<K, decltype(pc)::value>(a, b); });
+            scratch[op.gslot * nthr + tid] = kappa * v;
+          } else if (op.type == OP_GRAD_Y) {
+            const float kappa = __ldg(cf);
+            float v = 0.f;
+            dispatch_pos<K>(op.p0, [&](auto pc) { v = im_bya<K, decltype(pc)::value>(a, b); });
+            scratch[op.gslot * nthr + tid] = kappa * v;
+          } else if (op.type == OP_GRAD_MAT1) {
             const float4 m0 = ldg4(cf), m1 = ldg4(cf + 4);
-            scratch[__ldg(&op->gslot) * nthr + tid] = grad_mat1_dyn<K>(a, b, p0, m0, m1);
-          } else if (type == OP_GRAD_MAT2) {
-            const float g = p0 == 0 ? mat2<K, 0, true>(a, b, cf) : mat2<K, 2, true>(a, b, cf);
-            scratch[__ldg(&op->gslot) * nthr + tid] = g;
-          } else if (type == OP_GD_BEGIN) {
-            const int cnt = __ldg(&op->aux0);
-            grad_diag_run<K>(a, b, op + 1, cnt, ka.coef, scratch, gbase, tid, nthr);
-            oi += cnt;
+            float v = 0.f;
+            dispatch_pos<K>(op.p0, [&](auto pc) { v = grad_mat1<K, decltype(pc)::value>(a, b, m0, m1); });
+            scratch[op.gslot * nthr + tid] = v;
+          } else if (op.type == OP_GRAD_MAT2) {
+            const float g = op.p0 == 0 ? mat2<K, 0, true>(a, b, cf) : mat2<K, 2, true>(a, b, cf);
+            scratch[op.gslot * nthr + tid] = g;
+          } else if (op.type == OP_GD_BEGIN) {
+            grad_diag_run<K>(a, b, ka.ops + oi + 1, op.aux0, op.aux1 != 0, ka.coef, scratch, gbase, tid, nthr);
           }
         }
         break;
     }
+    oi += step;
   }
 
   if (ngrad > 0) {
@@ -403,64 +477,85 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    s_psi[B ^ s_E[r]] = a[r];
-    if constexpr (BOTH) s_lam[B ^ s_E[r]] = b[r];
+    s_psi[B ^ eo[r]] = a[r];
+    if constexpr (BOTH) s_lam[B ^ eo[r]] = b[r];
   }
 }
 
 // ---------------------------------------------------------------------------------
 // Expectation phase: E_j = Re <psi|H_j|psi>, and (adjoint) lambda = sum_j g_j H_j psi.
-// H psi[i] = sum_groups coefficient_g(i) psi[i ^ x_g]; all terms of a group share x.
+// H psi[i] = sum_groups c_g(i) psi[i ^ x_g]; c_g(i) = k0 + sum_t k_t (-1)^{parity(i & z_t)}.
+// The thread's amplitudes are i_m = m * nthreads + tid; parity(i_m & z) splits into a per-thread
+// bit and a per-m bit that the host precomputed (DevTerm::mword).
 // ---------------------------------------------------------------------------------
 template <int K, bool ADJ>
 __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi, float2* s_lam, uint32_t goff,
                                              uint32_t u, const float2* __restrict__ psi_u) {
   constexpr int R = 1 << K;
+  constexpr int MC = R < 16 ? R : 16;  // amplitudes per thread handled at a time
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-  __syncthreads();
-  float2 a[R];
-  float2 lam[ADJ ? R : 1];
-  const uint32_t gi_tid = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
-#pragma unroll
-  for (int m = 0; m < R; ++m) {
-    a[m] = s_psi[swz((uint32_t)m * nthr | tid)];
-    if constexpr (ADJ) lam[m] = make_float2(0.f, 0.f);
-  }
   const bool want_lam = ADJ && ka.dgrad != nullptr;
-  for (int j = 0; j < ka.O; ++j) {
-    const float gj = want_lam ? __ldg(&ka.dgrad[(size_t)u * ka.O + j]) : 0.f;
-    float ej = 0.f;
-    const int g_end = __ldg(&ka.opranges[j].group_end);
-    for (int g = __ldg(&ka.opranges[j].group_begin); g < g_end; ++g) {
-      const uint32_t x = __ldg(&ka.groups[g].x);
-      const int xl = __ldg(&ka.groups[g].xl);
-      const int t0 = __ldg(&ka.groups[g].term_begin), t1 = __ldg(&ka.groups[g].term_end);
+  const uint32_t gi_tid = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
+  const uint32_t ph_tid = swz(tid);
+  __syncthreads();
+  for (int m0 = 0; m0 < R; m0 += MC) {
+    float2 a[MC];
+    float2 lam[ADJ ? MC : 1];
+    uint32_t ph[MC];
 #pragma unroll
-      for (int m = 0; m < R; ++m) {
-        const uint32_t l = (uint32_t)m * nthr | tid;
-        const uint32_t gi = gi_tid | scatter_bits((uint32_t)m * nthr, ka.L.runs, ka.L.n_runs);
-        float cr = 0.f, ci = 0.f;
-        for (int t = t0; t < t1; ++t) {
+    for (int m = 0; m < MC; ++m) {
+      ph[m] = ph_tid ^ swz((uint32_t)(m0 + m) * nthr);
+      a[m] = s_psi[ph[m]];
+      if constexpr (ADJ) lam[m] = make_float2(0.f, 0.f);
+    }
+    for (int j = 0; j < ka.O; ++j) {
+      const float gj = want_lam ? __ldg(&ka.dgrad[(size_t)u * ka.O + j]) : 0.f;
+      float ej = 0.f;
+      const int g_end = __ldg(&ka.opranges[j].group_end);
+      for (int g = __ldg(&ka.opranges[j].group_begin); g < g_end; ++g) {
+        const int4 gh = __ldg(reinterpret_cast<const int4*>(ka.groups + g));
+        const int4 gk = __ldg(reinterpret_cast<const int4*>(ka.groups + g) + 1);
+        const uint32_t x = (uint32_t)gh.x;
+        const int xl = gh.y;
+        const float k0r = __int_as_float(gk.x), k0i = __int_as_float(gk.y);
+        const bool cplx = gk.z != 0;
+        float cr[MC], ci[MC];
+#pragma unroll
+        for (int m = 0; m < MC; ++m) { cr[m] = k0r; ci[m] = k0i; }
+        for (int t = gh.z; t < gh.w; ++t) {
           const float4 tv = __ldg(reinterpret_cast<const float4*>(ka.terms + t));
-          const uint32_t sgn = (uint32_t)(__popc(gi & __float_as_uint(tv.z)) & 1) << 31;
-          cr += __uint_as_float(__float_as_uint(tv.x) ^ sgn);
-          ci += __uint_as_float(__float_as_uint(tv.y) ^ sgn);
+          const uint32_t tp = (uint32_t)(__popc(gi_tid & __float_as_uint(tv.z)) & 1) << 31;
+          const uint32_t word = __float_as_uint(tv.w) >> m0;
+#pragma unroll
+          for (int m = 0; m < MC; ++m) {
+            const uint32_t sgn = tp ^ ((word >> m) << 31);
+            cr[m] += __uint_as_float(__float_as_uint(tv.x) ^ sgn);
+            if (cplx) ci[m] += __uint_as_float(__float_as_uint(tv.y) ^ sgn);
+          }
         }
-        const float2 p = xl >= 0 ? s_psi[swz(l ^ (uint32_t)xl)] : psi_u[gi ^ x];
-        const float hr = cr * p.x - ci * p.y, hi = cr * p.y + ci * p.x;
-        ej += a[m].x * hr + a[m].y * hi;
-        if constexpr (ADJ) {
-          lam[m].x += gj * hr;
-          lam[m].y += gj * hi;
+        const uint32_t pxor = xl >= 0 ? swz((uint32_t)xl) : 0u;
+#pragma unroll
+        for (int m = 0; m < MC; ++m) {
+          float2 p;
+          if (x == 0) p = a[m];
+          else if (xl >= 0) p = s_psi[ph[m] ^ pxor];
+          else p = psi_u[(gi_tid | scatter_bits((uint32_t)(m0 + m) * nthr, ka.L.runs, ka.L.n_runs)) ^ x];
+          float hr = cr[m] * p.x, hi = cr[m] * p.y;
+          if (cplx) { hr = fmaf(-ci[m], p.y, hr); hi = fmaf(ci[m], p.x, hi); }
+          ej = fmaf(a[m].x, hr, fmaf(a[m].y, hi, ej));
+          if constexpr (ADJ) {
+            lam[m].x = fmaf(gj, hr, lam[m].x);
+            lam[m].y = fmaf(gj, hi, lam[m].y);
+          }
         }
       }
+      ej = warp_sum(ej);
+      if ((tid & 31) == 0) atomicAdd(&ka.eacc[(size_t)u * ka.O + j], (double)ej);
     }
-    ej = warp_sum(ej);
-    if ((tid & 31) == 0) atomicAdd(&ka.eacc[(size_t)u * ka.O + j], (double)ej);
-  }
-  if constexpr (ADJ) {
+    if constexpr (ADJ) {
 #pragma unroll
-    for (int m = 0; m < R; ++m) s_lam[swz((uint32_t)m * nthr | tid)] = lam[m];
+      for (int m = 0; m < MC; ++m) s_lam[ph[m]] = lam[m];
+    }
   }
 }
 
@@ -469,20 +564,26 @@ __device__ __forceinline__ void load_tile(float2* s, const float2* __restrict__ 
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
   const uint32_t gt = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
+  const uint32_t pt = swz(tid);
   float2 v[R];
 #pragma unroll
   for (int m = 0; m < R; ++m) v[m] = g[gt | scatter_bits((uint32_t)m * nthr, ka.L.runs, ka.L.n_runs)];
 #pragma unroll
-  for (int m = 0; m < R; ++m) s[swz((uint32_t)m * nthr | tid)] = v[m];
+  for (int m = 0; m < R; ++m) s[pt ^ swz((uint32_t)m * nthr)] = v[m];
 }
 template <int K>
-__device__ __forceinline__ void store_tile(const float2* s, float2* __restrict__ g, uint32_t goff, const KernelArgs& ka) {
+__device__ __forceinline__ void store_tile(const float2* s, float2* __restrict__ g, uint32_t goff, const KernelArgs& ka,
+                                           const float2 scale) {
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
   const uint32_t gt = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
+  const uint32_t pt = swz(tid);
 #pragma unroll
-  for (int m = 0; m < R; ++m)
-    g[gt | scatter_bits((uint32_t)m * nthr, ka.L.runs, ka.L.n_runs)] = s[swz((uint32_t)m * nthr | tid)];
+  for (int m = 0; m < R; ++m) {
+    float2 v = s[pt ^ swz((uint32_t)m * nthr)];
+    if (scale.x != 1.f || scale.y != 0.f) v = cmul(v, scale);
+    g[gt | scatter_bits((uint32_t)m * nthr, ka.L.runs, ka.L.n_runs)] = v;
+  }
 }
 
 template <int K, bool ADJ>
@@ -492,7 +593,6 @@ constexpr int sweep_max_threads() { return ADJ ? (1 << (13 - K)) : 512; }
 template <int K, bool ADJ>
 __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(const __grid_constant__ KernelArgs ka) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_E[1 << kMaxRegQubits];
   float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float2* s_lam = s_psi + (ADJ ? (1u << ka.T) : 0u);
   constexpr int R = 1 << K;
@@ -504,6 +604,7 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
   float2* psi_u = ka.psi ? ka.psi + ((size_t)u << ka.n) : nullptr;
   float2* lam_u = ka.lam ? ka.lam + ((size_t)u << ka.n) : nullptr;
   const uint32_t flags = ka.L.flags;
+  const float2 one = make_float2(1.f, 0.f);
 
   bool active = true;
   if (flags & LF_INIT_BASIS) {
@@ -524,22 +625,23 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
 
   if (active) {
     for (int p = ka.L.pass_a_begin; p < ka.L.pass_a_end; ++p)
-      run_pass<K, false>(ka, ka.passes + p, s_psi, s_lam, s_E, goff, u);
+      run_pass<K, false>(ka, ka.passes + p, s_psi, s_lam, goff, u);
   }
   if (flags & LF_WRITE_STATE) {
     __syncthreads();
-    store_tile<K>(s_psi, ka.state_out + ((size_t)u << ka.n), goff, ka);
+    const float2 phase = ka.phase_coef >= 0 ? ldg2(ka.coef + ka.phase_coef) : one;
+    store_tile<K>(s_psi, ka.state_out + ((size_t)u << ka.n), goff, ka, phase);
   }
   if (flags & LF_EXPECT) expect_phase<K, ADJ>(ka, s_psi, s_lam, goff, u, psi_u);
   if constexpr (ADJ) {
     for (int p = ka.L.pass_b_begin; p < ka.L.pass_b_end; ++p)
-      run_pass<K, true>(ka, ka.passes + p, s_psi, s_lam, s_E, goff, u);
+      run_pass<K, true>(ka, ka.passes + p, s_psi, s_lam, goff, u);
   }
   if (flags & (LF_STORE_PSI | LF_STORE_LAM)) {
     __syncthreads();
-    if (flags & LF_STORE_PSI) store_tile<K>(s_psi, psi_u, goff, ka);
+    if (flags & LF_STORE_PSI) store_tile<K>(s_psi, psi_u, goff, ka, one);
     if constexpr (ADJ) {
-      if (flags & LF_STORE_LAM) store_tile<K>(s_lam, lam_u, goff, ka);
+      if (flags & LF_STORE_LAM) store_tile<K>(s_lam, lam_u, goff, ka, one);
     }
   }
 }
@@ -625,15 +727,19 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __res
     } break;
     case PJ_GRAD1:
     case PJ_GRAD2:
-    case PJ_GDIAG: {
+    case PJ_GDIAG:
+    case PJ_KAPPA: {
       const qhbm_gate_t g = gates[list[0]];
       const int dim = gate_matrix_of(g, symbols, m);
       gate_derivative(g, symbols, job.c, mode, t);
       dagger(m, dim, w);
       matmul(t, w, dim, m);  // M = dG G^dagger
-      if (dim == 4 && job.b) { swap_qubits(m, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
+      if (dim == 4 && job.b && job.kind != PJ_KAPPA) { swap_qubits(m, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
       if (job.kind == PJ_GDIAG) {
         for (int k = 0; k < 4; ++k) write_c(out, k, k < dim ? m[k * dim + k] : mk(0, 0));
+      } else if (job.kind == PJ_KAPPA) {
+        // M = i c0 I - i (kappa/2) A:  X: M01 = -i kappa/2;  Y: M01 = -kappa/2
+        out[0] = (float)(job.b == 0 ? -2.0 * m[1].im : -2.0 * m[1].re);
       } else {
         for (int k = 0; k < dim * dim; ++k) write_c(out, k, m[k]);
       }
@@ -645,6 +751,23 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __res
         cd v = k < dim ? m[k * dim + k] : mk(1, 0);
         write_c(out, k, job.a ? conj(v) : v);
       }
+    } break;
+    case PJ_ROT: {
+      double p[3];
+      gate_param_values(gates[list[0]], symbols, p);
+      const cd e = expipi(0.5 * p[0]);
+      out[0] = (float)e.re;
+      out[1] = (float)(job.a ? -e.im : e.im);
+    } break;
+    case PJ_PHASE: {
+      cd acc = mk(1, 0);
+      for (int i = 0; i < job.list_len; ++i) {
+        const qhbm_gate_t g = gates[list[i]];
+        double p[3];
+        gate_param_values(g, symbols, p);
+        acc = acc * expipi(p[0] * ((double)g.gshift + 0.5));
+      }
+      write_c(out, 0, acc);
     } break;
     default: break;
   }

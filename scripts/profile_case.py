@@ -1,0 +1,30 @@
+"""One invocation of the hot path for ncu: python scripts/profile_case.py n layers U T K grad [ham]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "qhbm-library_b200"), os.path.join(ROOT, "tests")):
+  sys.path.insert(0, p)
+import numpy as np
+import torch
+from oracle import qhbm_oracle as orc
+from qhbmlib import engine
+
+n, layers, u, T, K, grad = (int(x) for x in sys.argv[1:7])
+ham = sys.argv[7] if len(sys.argv) > 7 else "xxz"
+reps = int(sys.argv[8]) if len(sys.argv) > 8 else 1
+gates, names = orc.hea_circuit(n, layers)
+ops = [orc.xxz_ring(n) if ham == "xxz" else orc.tfim_ring(n)]
+terms, offs = engine.terms_from_pauli_sums(ops, n)
+plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, bool(grad), T, K)
+rng = np.random.default_rng(0)
+phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+basis = torch.tensor(rng.choice(1 << n, u, replace=False).astype(np.int64), device="cuda")
+dg = torch.tensor(rng.uniform(0, 1, (u, 1)).astype(np.float32), device="cuda")
+for _ in range(reps):
+  if grad:
+    plan.forward_adjoint(basis, phi, dg)
+  else:
+    plan.forward(basis, phi)
+torch.cuda.synchronize()
+print(plan.info)

@@ -48,14 +48,32 @@ static void prep(const HostPlan& hp, const float* symbols, int mode, std::vector
         if (job.a) { dagger(m, 4, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
         for (int k = 0; k < 16; ++k) wr(job.out, k, m[k]);
       } break;
-      case PJ_GRAD1: case PJ_GRAD2: case PJ_GDIAG: {
+      case PJ_ROT: {
+        double pv[3];
+        gate_param_values(hp.gates[list[0]], symbols, pv);
+        const cd e = expipi(0.5 * pv[0]);
+        coef[job.out] = (float)e.re;
+        coef[job.out + 1] = (float)(job.a ? -e.im : e.im);
+      } break;
+      case PJ_PHASE: {
+        cd acc = mk(1, 0);
+        for (int i = 0; i < job.list_len; ++i) {
+          const qhbm_gate_t g = hp.gates[list[i]];
+          double pv[3];
+          gate_param_values(g, symbols, pv);
+          acc = acc * expipi(pv[0] * ((double)g.gshift + 0.5));
+        }
+        wr(job.out, 0, acc);
+      } break;
+      case PJ_GRAD1: case PJ_GRAD2: case PJ_GDIAG: case PJ_KAPPA: {
         const qhbm_gate_t g = hp.gates[list[0]];
         const int dim = gate_matrix_of(g, symbols, m);
         gate_derivative(g, symbols, job.c, mode, t);
         dagger(m, dim, w);
         matmul(t, w, dim, m);
-        if (dim == 4 && job.b) { swap_qubits(m, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
+        if (dim == 4 && job.b && job.kind != PJ_KAPPA) { swap_qubits(m, t); for (int k = 0; k < 16; ++k) m[k] = t[k]; }
         if (job.kind == PJ_GDIAG) for (int k = 0; k < 4; ++k) wr(job.out, k, k < dim ? m[k * dim + k] : mk(0, 0));
+        else if (job.kind == PJ_KAPPA) coef[job.out] = (float)(job.b == 0 ? -2.0 * m[1].im : -2.0 * m[1].re);
         else for (int k = 0; k < dim * dim; ++k) wr(job.out, k, m[k]);
       } break;
       case PJ_DPAIR: {
@@ -127,6 +145,30 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
       const DevOp& op = hp.ops[oi];
       switch (op.type) {
         case OP_MAT1: mat1(a, op.p0, op.coef); if (both) mat1(b, op.p0, op.coef); break;
+        case OP_XROT: case OP_YROT: {
+          const double cc = c.coef[op.coef], ss = c.coef[op.coef + 1];
+          const cplx m01 = op.type == OP_XROT ? cplx(0, -ss) : cplx(-ss, 0);
+          const cplx m10 = op.type == OP_XROT ? cplx(0, -ss) : cplx(ss, 0);
+          for (int which = 0; which < (both ? 2 : 1); ++which) {
+            std::vector<cplx>& v = which ? b : a;
+            for (int r = 0; r < R; ++r) if (!(r & (1 << op.p0))) {
+              cplx x0 = v[r], x1 = v[r | (1 << op.p0)];
+              v[r] = cc * x0 + m01 * x1;
+              v[r | (1 << op.p0)] = m10 * x0 + cc * x1;
+            }
+          }
+        } break;
+        case OP_GRAD_X: case OP_GRAD_Y: {
+          double sacc = 0;
+          for (int r = 0; r < R; ++r) if (!(r & (1 << op.p0))) {
+            const int q = r | (1 << op.p0);
+            cplx y0, y1;  // (A a) on the pair
+            if (op.type == OP_GRAD_X) { y0 = a[q]; y1 = a[r]; }
+            else { y0 = cplx(0, -1) * a[q]; y1 = cplx(0, 1) * a[r]; }
+            sacc += (std::conj(b[r]) * y0 + std::conj(b[q]) * y1).imag();
+          }
+          gsum[op.gslot] += c.coef[op.coef] * sacc;
+        } break;
         case OP_MAT2: mat2(a, op.p0 ? 2 : 0, op.coef, nullptr, nullptr); if (both) mat2(b, op.p0 ? 2 : 0, op.coef, nullptr, nullptr); break;
         case OP_DCONST_TAB: F *= cf(c, op.coef, (gbase >> op.aux0) & op.aux1); break;
         case OP_DCONST_PAIR: { int sel = (gbase >> op.aux0) & 1; if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1); F *= cf(c, op.coef, sel); } break;
@@ -190,7 +232,7 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
           const DevTermGroup& G = hp.groups[g];
           for (int l = 0; l < tsz; ++l) {
             const uint32_t gi = goff | scatter(l, L.runs, L.n_runs);
-            cplx k = 0;
+            cplx k(G.k0r, G.k0i);
             for (int t = G.term_begin; t < G.term_end; ++t) {
               const DevTerm& T = hp.terms[t];
               const double sg = (__builtin_popcount(gi & T.z) & 1) ? -1.0 : 1.0;
@@ -240,11 +282,15 @@ int verify_run(const qhbm_gate_t* gates, int n_gates, int n, int P, const qhbm_p
         // single launch: capture the forward state by running the forward part alone first
         LaunchDesc F = L; F.flags &= ~(uint32_t)LF_EXPECT; F.pass_b_begin = F.pass_b_end = 0;
         Ctx tmp = ctx; run_launch(tmp, F, (uint32_t)basis, false);
-        for (size_t i = 0; i < tmp.psi.size(); ++i) { state_out[2 * i] = tmp.psi[i].real(); state_out[2 * i + 1] = tmp.psi[i].imag(); }
+        const cplx gph = hp.phase_coef >= 0 ? cplx(ctx.coef[hp.phase_coef], ctx.coef[hp.phase_coef + 1]) : cplx(1, 0);
+        for (size_t i = 0; i < tmp.psi.size(); ++i) { const cplx v = tmp.psi[i] * gph; state_out[2 * i] = v.real(); state_out[2 * i + 1] = v.imag(); }
       }
       run_launch(ctx, L, (uint32_t)basis, with_grad != 0);
       if (hp.tiles() > 1 && state_out && (int)li == hp.n_fwd_launches - 1)
-        for (size_t i = 0; i < ctx.psi.size(); ++i) { state_out[2 * i] = ctx.psi[i].real(); state_out[2 * i + 1] = ctx.psi[i].imag(); }
+      {
+        const cplx gph = hp.phase_coef >= 0 ? cplx(ctx.coef[hp.phase_coef], ctx.coef[hp.phase_coef + 1]) : cplx(1, 0);
+        for (size_t i = 0; i < ctx.psi.size(); ++i) { const cplx v = ctx.psi[i] * gph; state_out[2 * i] = v.real(); state_out[2 * i + 1] = v.imag(); }
+      }
     }
     for (int j = 0; j < O; ++j) e_out[j] = ctx.eacc[j];
     if (with_grad) for (int s = 0; s < P; ++s) g_out[s] = ctx.gacc[s];

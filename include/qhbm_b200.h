@@ -193,8 +193,8 @@ int qhbm_energy_rows(const qhbm_energy_desc_t* e, const uint64_t* d_keys, int64_
  *   d_logits  f32[hi-lo] = -E(row)        (may be NULL)
  *   d_stats   f64[3]: max logit m, s = sum exp(l-m), t = sum exp(l-m)*l
  *             => logZ = m + log s, entropy = logZ - t/s.  Partial stats of several
- *             ranks are merged with qhbm_merge_stats (or one allreduce of the triple
- *             after rebasing to a common max). */
+ *             ranks merge by rebasing to the common max: s = sum_r s_r e^{m_r - m}
+ *             (one all-gather of the triples, or allreduce-max then allreduce-sum). */
 int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float* d_logits,
                    double* d_stats, void* stream);
 

@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(256) cat_max_kernel(const float* __restrict__ 
     m = fmaxf(m, logits[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (m == 0.f) m = 0.f;  // -0.0 would order below every negative float in the int trick
   if ((threadIdx.x & 31) == 0) {
     // float atomic max via int ordering trick
     int* a = reinterpret_cast<int*>(gmax);

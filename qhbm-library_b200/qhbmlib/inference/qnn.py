@@ -53,6 +53,8 @@ class QuantumInference(torch.nn.Module, abc.ABC):
     super().__init__()
     self.name = name
     input_circuit.build([])
+    if torch.cuda.is_available():
+      input_circuit.to("cuda")  # the engine has no CPU path; parameters live next to the kernels
     self._circuit = input_circuit
 
   @property

@@ -87,6 +87,9 @@ class QuantumCircuit(torch.nn.Module):
     if not pieces:
       dev = next(self.parameters()).device if list(self.parameters()) else "cpu"
       return torch.zeros((0,), dtype=torch.float32, device=dev)
+    devices = [p.device for p in pieces if p.is_cuda]
+    if devices:  # summed circuits may mix parameter devices; the engine wants them on the GPU
+      pieces = [p.to(devices[0]) for p in pieces]
     return torch.cat(pieces, 0)
 
   @property

@@ -75,7 +75,7 @@ def test_qnn_expectation_xpow_closed_form(grad_mode, gtol):
   states = 5 * list(itertools.product([0, 1], repeat=num_bits))
   initial_states = _bits(states)
   qnn = inference.AnalyticQuantumInference(p_qnn, grad_mode=grad_mode)
-  p = float(p_qnn.symbol_values[0])
+  p = float(p_qnn.symbol_values[0].detach())
   sin_p, cos_p = math.sin(math.pi * p), math.cos(math.pi * p)
   expected = {
       "X": ([[0.0] * 3 for _ in states], [[0.0] * 3 for _ in states]),
@@ -390,19 +390,22 @@ def test_vqt_loss_x_rot_closed_form(num_qubits):
 
 
 def test_self_vqt_and_self_qmhl_optimum():
-  """tests/inference/vqt_loss_test.py:46-83 and qmhl_loss_test.py:48-80: against its own modular
-  Hamiltonian the VQT loss is -log Z and QMHL is the entropy; the energy-parameter gradients vanish."""
+  """tests/inference/vqt_loss_test.py:46-83 and qmhl_loss_test.py:48-80: a model against a data QHBM
+  with identical weights: the VQT loss is -log Z and QMHL is the entropy; gradients vanish."""
   n, num_samples = 3, 2_000_000
-  _, qhbm = _random_qhbm(n, 1, 21, num_samples, ebm_seed=[5, 6])
-  model_h = qhbm.modular_hamiltonian
-  loss = inference.vqt(qhbm, model_h, torch.tensor(1.0, device=DEV))
-  np.testing.assert_allclose(float(loss), -float(qhbm.e_inference.log_partition()), rtol=2e-2, atol=3e-3)
+  _, data_qhbm = _random_qhbm(n, 1, 21, num_samples, ebm_seed=[5, 6])
+  _, model_qhbm = _random_qhbm(n, 1, 22, num_samples, ebm_seed=[5, 6])
+  data_h, model_h = data_qhbm.modular_hamiltonian, model_qhbm.modular_hamiltonian
+  with torch.no_grad():
+    for pd, pm in zip(data_h.trainable_variables, model_h.trainable_variables):
+      pd.copy_(pm)
+  loss = inference.vqt(model_qhbm, data_h, torch.tensor(1.0, device=DEV))
+  np.testing.assert_allclose(float(loss), -float(data_qhbm.e_inference.log_partition()), rtol=2e-2, atol=3e-3)
   grads = torch.autograd.grad(loss, model_h.trainable_variables, allow_unused=True)
   for g in grads:
     assert g is None or float(g.abs().max()) < 2e-2
-  qdata = data.QHBMData(qhbm)
-  loss = inference.qmhl(qdata, qhbm)
-  np.testing.assert_allclose(float(loss), float(qhbm.e_inference.entropy()), rtol=2e-2, atol=3e-3)
+  loss = inference.qmhl(data.QHBMData(data_qhbm), model_qhbm)
+  np.testing.assert_allclose(float(loss), float(model_qhbm.e_inference.entropy()), rtol=2e-2, atol=3e-3)
   grads = torch.autograd.grad(loss, model_h.trainable_variables, allow_unused=True)
   for g in grads:
     assert g is None or float(g.abs().max()) < 2e-2

@@ -176,15 +176,15 @@ def run_reference(args, cfg):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  from oracle import tfq_cpu
-  threads = tfq_cpu.max_threads()
-  rate0, _, _ = cpu_reference_rate(cfg, min(16, cfg["unique"]))
+  # every host thread the box offers (torchrun pins OMP_NUM_THREADS=1, so ask explicitly)
+  threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+  rate0, _, _ = cpu_reference_rate(cfg, min(2 * threads, cfg["unique"]), threads)
   sample = int(max(8, min(cfg["unique"], rate0 * 4.0)))  # ~4 s of CPU work per step
   for _ in range(args.warmup if args.warmup < 2 else 1):
-    cpu_reference_rate(cfg, sample)
+    cpu_reference_rate(cfg, sample, threads)
   times = []
   for _ in range(args.steps):
-    _, dt, _ = cpu_reference_rate(cfg, sample)
+    _, dt, _ = cpu_reference_rate(cfg, sample, threads)
     times.append(dt)
   ms = 1e3 * float(np.mean(times))
   value = sample / (ms / 1e3)
@@ -339,9 +339,10 @@ def run_gpu(args, cfg):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-      rate0, _, threads = cpu_reference_rate(cfg, min(16, u))
+      nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+      rate0, _, threads = cpu_reference_rate(cfg, min(2 * nthreads, u), nthreads)
       sample = int(max(8, min(u, rate0 * 10.0)))
-      rate, dt, threads = cpu_reference_rate(cfg, sample)
+      rate, dt, threads = cpu_reference_rate(cfg, sample, nthreads)
       out["cpu_baseline"] = {
           "value": rate, "unit": "bitstrings/s", "cores": threads, "kind": "port",
           "sample": f"{sample} of {u} unique bitstrings, {dt:.1f} s; forward op + adjoint op; CPU restatement "

@@ -67,6 +67,7 @@ struct DiagRun {
   std::vector<std::vector<int32_t>> grp_list;
   std::vector<DevOp> pair_ops, cross_ops, gd_ops;
   bool any = false, any_const = false;
+  uint32_t bits = 0;  // state-index bits some pending diagonal gate acts on
 };
 
 DevOp make_op(int type) {
@@ -319,7 +320,31 @@ class Compiler {
           if (!ok) { blk.block(a); continue; }
           if (a.diag) emit_diag(a, backward, regpos, ps, run);
           else {
-            flush_diag(run, backward);
+            // a non-diagonal block commutes with every pending diagonal gate on OTHER qubits, so the
+            // pending run stays open (and keeps growing into one table op) unless it touches this block
+            uint32_t abits = 0;
+            for (int i = 0; i < a.nq; ++i) abits |= 1u << a.bit[i];
+            if (run.bits & abits) {
+              // before closing the run, pull in every later diagonal gate that commutes with all the
+              // blocks still ahead of it (e.g. the Z^-s of the other qubits of this layer)
+              Block b2 = blk;
+              for (size_t aj = ai; aj < atoms.size(); ++aj) {
+                if (done[aj]) continue;
+                const Atom& x = atoms[aj];
+                if (!x.diag || !b2.ready(x)) { b2.block(x); continue; }
+                int ng = 0;
+                if (backward) {
+                  const qhbm_gate_t& g = hp_.gates[x.gates[0]];
+                  for (int k = 0; k < g.nparams; ++k) ng += g.sym[k] >= 0;
+                }
+                if (ps.ngrad + ng > max_slots) { b2.block(x); continue; }
+                emit_diag(x, backward, regpos, ps, run);
+                done[aj] = 1;
+                --remaining;
+                ++executed;
+              }
+              flush_diag(run, backward);
+            }
             emit_nondiag(a, backward, regpos, ps);
           }
           done[ai] = 1;
@@ -351,23 +376,19 @@ class Compiler {
       const int gi = a.gates[0];
       const qhbm_gate_t& g = hp_.gates[gi];
       const bool is_y = g.type == QHBM_GATE_YPOW;
+      DevOp o = make_op(is_y ? OP_YROT : OP_XROT);
+      o.p0 = p;
+      o.coef = alloc_coef(4);  // (c, s, kappa, -)
+      add_job(PJ_ROT, o.coef, backward ? 1 : 0, 0, 0, 0, {gi});
       if (backward) {
-        if (g.sym[0] >= 0) {
-          DevOp o = make_op(is_y ? OP_GRAD_Y : OP_GRAD_X);
-          o.p0 = p;
-          o.coef = alloc_coef(4);
+        if (g.sym[0] >= 0) {  // gradient inner product fused into the un-rotation (gslot >= 0)
           o.gslot = ps.ngrad++;
           hp_.gsym.push_back(g.sym[0]);
-          add_job(PJ_KAPPA, o.coef, 0, is_y ? 1 : 0, 0, 0, {gi});
-          hp_.ops.push_back(o);
+          add_job(PJ_KAPPA, o.coef + 2, 0, is_y ? 1 : 0, 0, 0, {gi});
         }
       } else {
         phase_gates_.push_back(gi);
       }
-      DevOp o = make_op(is_y ? OP_YROT : OP_XROT);
-      o.p0 = p;
-      o.coef = alloc_coef(4);
-      add_job(PJ_ROT, o.coef, backward ? 1 : 0, 0, 0, 0, {gi});
       hp_.ops.push_back(o);
     } else if (a.nq == 1) {
       const int p = regpos[a.bit[0]];
@@ -418,6 +439,7 @@ class Compiler {
 
   void emit_diag(const Atom& a, bool backward, const std::vector<int>& regpos, DevPass& ps, DiagRun& run) {
     run.any = true;
+    for (int i = 0; i < a.nq; ++i) run.bits |= 1u << a.bit[i];
     const int dag = backward ? 1 : 0;
     const int pa = regpos[a.bit[0]];
     const int pb = a.nq == 2 ? regpos[a.bit[1]] : -1;

@@ -362,17 +362,23 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
     if (oi + step < op_end) nxt = load_op(ka.ops + oi + step);  // prefetch the next descriptor
     switch (op.type) {
       case OP_XROT: {
-        const float2 cs = ldg2(cf);
+        const float4 cs = ldg4(cf);  // (c, s, kappa, -)
         dispatch_pos<K>(op.p0, [&](auto pc) {
           constexpr int P = decltype(pc)::value;
+          if constexpr (BOTH) {
+            if (op.gslot >= 0) scratch[op.gslot * nthr + tid] = cs.z * im_bxa<K, P>(a, b);
+          }
           xrot<K, P>(a, cs.x, cs.y);
           if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
         });
       } break;
       case OP_YROT: {
-        const float2 cs = ldg2(cf);
+        const float4 cs = ldg4(cf);
         dispatch_pos<K>(op.p0, [&](auto pc) {
           constexpr int P = decltype(pc)::value;
+          if constexpr (BOTH) {
+            if (op.gslot >= 0) scratch[op.gslot * nthr + tid] = cs.z * im_bya<K, P>(a, b);
+          }
           yrot<K, P>(a, cs.x, cs.y);
           if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
         });
@@ -405,10 +411,15 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
       } break;
       case OP_DREG_TAB: {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float2 c = cmul(F, ldg2(cf + 2 * r));
-          a[r] = cmul(a[r], c);
-          if constexpr (BOTH) b[r] = cmul(b[r], c);
+        for (int r = 0; r < R; r += 2) {
+          const float4 t = ldg4(cf + 2 * r);
+          const float2 c0 = cmul(F, make_float2(t.x, t.y)), c1 = cmul(F, make_float2(t.z, t.w));
+          a[r] = cmul(a[r], c0);
+          a[r + 1] = cmul(a[r + 1], c1);
+          if constexpr (BOTH) {
+            b[r] = cmul(b[r], c0);
+            b[r + 1] = cmul(b[r + 1], c1);
+          }
         }
         F = make_float2(1.f, 0.f);
       } break;
@@ -435,15 +446,13 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
       } break;
       default:
         if constexpr (BOTH) {
-          if (op.type == OP_GRAD_X) {
+          if (op.type == OP_GRAD_X || op.type == OP_GRAD_Y) {
             const float kappa = __ldg(cf);
             float v = 0.f;
-            dispatch_pos<K>(op.p0, [&](auto pc) { v = im_bxa<K, decltype(pc)::value>(a, b); });
-            scratch[op.gslot * nthr + tid] = kappa * v;
-          } else if (op.type == OP_GRAD_Y) {
-            const float kappa = __ldg(cf);
-            float v = 0.f;
-            dispatch_pos<K>(op.p0, [&](auto pc) { v = im_bya<K, decltype(pc)::value>(a, b); });
+            const bool isx = op.type == OP_GRAD_X;
+            dispatch_pos<K>(op.p0, [&](auto pc) {
+              v = isx ? im_bxa<K, decltype(pc)::value>(a, b) : im_bya<K, decltype(pc)::value>(a, b);
+            });
             scratch[op.gslot * nthr + tid] = kappa * v;
           } else if (op.type == OP_GRAD_MAT1) {
             const float4 m0 = ldg4(cf), m1 = ldg4(cf + 4);
@@ -488,6 +497,57 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
 // The thread's amplitudes are i_m = m * nthreads + tid; parity(i_m & z) splits into a per-thread
 // bit and a per-m bit that the host precomputed (DevTerm::mword).
 // ---------------------------------------------------------------------------------
+// One x-group of one observable for MC of the thread's amplitudes.  SRC: 0 diagonal (partner = own
+// amplitude), 1 partner inside the tile (smem), 2 partner in another tile (global / L2).
+template <int MC, bool ADJ, bool CPLX, int SRC>
+__device__ __forceinline__ float expect_group(const KernelArgs& ka, const float2* s_psi, const float2* __restrict__ psi_u,
+                                              const float2 (&a)[MC], float2 (&lam)[ADJ ? MC : 1], const uint32_t (&ph)[MC],
+                                              const uint32_t gi_tid, const uint32_t nthr, const int m0, const uint32_t x,
+                                              const int xl, const int t0, const int t1, const float k0r, const float k0i,
+                                              const float gj) {
+  float cr[MC];
+  float ci[CPLX ? MC : 1];
+#pragma unroll
+  for (int m = 0; m < MC; ++m) {
+    cr[m] = k0r;
+    if constexpr (CPLX) ci[m] = k0i;
+  }
+  for (int t = t0; t < t1; ++t) {
+    const float4 tv = __ldg(reinterpret_cast<const float4*>(ka.terms + t));
+    const uint32_t tp = (uint32_t)(__popc(gi_tid & __float_as_uint(tv.z)) & 1) << 31;
+    const uint32_t word = __float_as_uint(tv.w) >> m0;
+#pragma unroll
+    for (int m = 0; m < MC; ++m) {
+      const uint32_t sgn = tp ^ ((word >> m) << 31);
+      cr[m] += __uint_as_float(__float_as_uint(tv.x) ^ sgn);
+      if constexpr (CPLX) ci[m] += __uint_as_float(__float_as_uint(tv.y) ^ sgn);
+    }
+  }
+  const uint32_t pxor = SRC == 1 ? swz((uint32_t)xl) : 0u;
+  float ej = 0.f;
+#pragma unroll
+  for (int m = 0; m < MC; ++m) {
+    float2 p;
+    if constexpr (SRC == 0) p = a[m];
+    else if constexpr (SRC == 1) p = s_psi[ph[m] ^ pxor];
+    else p = psi_u[(gi_tid | scatter_bits((uint32_t)(m0 + m) * nthr, ka.L.runs, ka.L.n_runs)) ^ x];
+    float hr = cr[m] * p.x, hi = cr[m] * p.y;
+    if constexpr (CPLX) { hr = fmaf(-ci[m], p.y, hr); hi = fmaf(ci[m], p.x, hi); }
+    ej = fmaf(a[m].x, hr, fmaf(a[m].y, hi, ej));
+    if constexpr (ADJ) {
+      lam[m].x = fmaf(gj, hr, lam[m].x);
+      lam[m].y = fmaf(gj, hi, lam[m].y);
+    }
+  }
+  return ej;
+}
+
+// ---------------------------------------------------------------------------------
+// Expectation phase: E_j = Re <psi|H_j|psi>, and (adjoint) lambda = sum_j g_j H_j psi.
+// H psi[i] = sum_groups c_g(i) psi[i ^ x_g]; c_g(i) = k0 + sum_t k_t (-1)^{parity(i & z_t)}.
+// The thread's amplitudes are i_m = m * nthreads + tid; parity(i_m & z) splits into a per-thread
+// bit and a per-m bit that the host precomputed (DevTerm::mword).
+// ---------------------------------------------------------------------------------
 template <int K, bool ADJ>
 __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi, float2* s_lam, uint32_t goff,
                                              uint32_t u, const float2* __restrict__ psi_u) {
@@ -518,36 +578,18 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
         const uint32_t x = (uint32_t)gh.x;
         const int xl = gh.y;
         const float k0r = __int_as_float(gk.x), k0i = __int_as_float(gk.y);
-        const bool cplx = gk.z != 0;
-        float cr[MC], ci[MC];
-#pragma unroll
-        for (int m = 0; m < MC; ++m) { cr[m] = k0r; ci[m] = k0i; }
-        for (int t = gh.z; t < gh.w; ++t) {
-          const float4 tv = __ldg(reinterpret_cast<const float4*>(ka.terms + t));
-          const uint32_t tp = (uint32_t)(__popc(gi_tid & __float_as_uint(tv.z)) & 1) << 31;
-          const uint32_t word = __float_as_uint(tv.w) >> m0;
-#pragma unroll
-          for (int m = 0; m < MC; ++m) {
-            const uint32_t sgn = tp ^ ((word >> m) << 31);
-            cr[m] += __uint_as_float(__float_as_uint(tv.x) ^ sgn);
-            if (cplx) ci[m] += __uint_as_float(__float_as_uint(tv.y) ^ sgn);
-          }
+#define QHBM_EG(CPLX, SRC) \
+  expect_group<MC, ADJ, CPLX, SRC>(ka, s_psi, psi_u, a, lam, ph, gi_tid, nthr, m0, x, xl, gh.z, gh.w, k0r, k0i, gj)
+        if (gk.z == 0) {
+          if (x == 0) ej += QHBM_EG(false, 0);
+          else if (xl >= 0) ej += QHBM_EG(false, 1);
+          else ej += QHBM_EG(false, 2);
+        } else {
+          if (x == 0) ej += QHBM_EG(true, 0);
+          else if (xl >= 0) ej += QHBM_EG(true, 1);
+          else ej += QHBM_EG(true, 2);
         }
-        const uint32_t pxor = xl >= 0 ? swz((uint32_t)xl) : 0u;
-#pragma unroll
-        for (int m = 0; m < MC; ++m) {
-          float2 p;
-          if (x == 0) p = a[m];
-          else if (xl >= 0) p = s_psi[ph[m] ^ pxor];
-          else p = psi_u[(gi_tid | scatter_bits((uint32_t)(m0 + m) * nthr, ka.L.runs, ka.L.n_runs)) ^ x];
-          float hr = cr[m] * p.x, hi = cr[m] * p.y;
-          if (cplx) { hr = fmaf(-ci[m], p.y, hr); hi = fmaf(ci[m], p.x, hi); }
-          ej = fmaf(a[m].x, hr, fmaf(a[m].y, hi, ej));
-          if constexpr (ADJ) {
-            lam[m].x = fmaf(gj, hr, lam[m].x);
-            lam[m].y = fmaf(gj, hi, lam[m].y);
-          }
-        }
+#undef QHBM_EG
       }
       ej = warp_sum(ej);
       if ((tid & 31) == 0) atomicAdd(&ka.eacc[(size_t)u * ka.O + j], (double)ej);

@@ -149,6 +149,17 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
           const double cc = c.coef[op.coef], ss = c.coef[op.coef + 1];
           const cplx m01 = op.type == OP_XROT ? cplx(0, -ss) : cplx(-ss, 0);
           const cplx m10 = op.type == OP_XROT ? cplx(0, -ss) : cplx(ss, 0);
+          if (both && op.gslot >= 0) {
+            double sacc = 0;
+            for (int r = 0; r < R; ++r) if (!(r & (1 << op.p0))) {
+              const int q = r | (1 << op.p0);
+              cplx y0, y1;
+              if (op.type == OP_XROT) { y0 = a[q]; y1 = a[r]; }
+              else { y0 = cplx(0, -1) * a[q]; y1 = cplx(0, 1) * a[r]; }
+              sacc += (std::conj(b[r]) * y0 + std::conj(b[q]) * y1).imag();
+            }
+            gsum[op.gslot] += c.coef[op.coef + 2] * sacc;
+          }
           for (int which = 0; which < (both ? 2 : 1); ++which) {
             std::vector<cplx>& v = which ? b : a;
             for (int r = 0; r < R; ++r) if (!(r & (1 << op.p0))) {
@@ -301,4 +312,38 @@ int verify_run(const qhbm_gate_t* gates, int n_gates, int n, int P, const qhbm_p
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
+}
+
+#include <cstdio>
+extern "C" int verify_dump(const qhbm_gate_t* gates, int n_gates, int n, int P, const qhbm_pauli_term_t* terms,
+                           const int32_t* offs, int O, int with_grad, int T, int K) {
+  try {
+    CircuitIR c; c.n_qubits = n; c.n_symbols = P; c.gates.assign(gates, gates + n_gates);
+    OpsIR o; o.n_qubits = n; o.offsets.assign(offs, offs + O + 1); o.terms.assign(terms, terms + offs[O]);
+    HostPlan hp = compile_plan(c, o, with_grad != 0, T, K);
+    static const char* names[] = {"NOP", "MAT1", "MAT2", "DCONST_TAB", "DCONST_PAIR", "DREG_TAB", "DAPPLY", "DCROSS",
+                                  "XROT", "YROT", "GRAD_MAT1", "GRAD_MAT2", "GRAD_X", "GRAD_Y", "GD_BEGIN", "GD_CONST",
+                                  "GD_REG1", "GD_REG2", "GD_MIX"};
+    printf("n_eff=%d T=%d K=%d ncoef=%d jobs=%zu terms=%zu groups=%zu\n", hp.n_eff, hp.T, hp.K, hp.ncoef, hp.jobs.size(),
+           hp.terms.size(), hp.groups.size());
+    for (size_t li = 0; li < hp.launches.size(); ++li) {
+      const LaunchDesc& L = hp.launches[li];
+      printf("launch %zu flags=0x%x tile_mask=0x%x passA=[%d,%d) passB=[%d,%d)\n", li, L.flags, L.tile_mask,
+             L.pass_a_begin, L.pass_a_end, L.pass_b_begin, L.pass_b_end);
+      for (int pass = 0; pass < 2; ++pass) {
+        int b = pass ? L.pass_b_begin : L.pass_a_begin, e = pass ? L.pass_b_end : L.pass_a_end;
+        for (int p = b; p < e; ++p) {
+          const DevPass& ps = hp.passes[p];
+          int hist[19] = {0};
+          for (int oi = ps.op_begin; oi < ps.op_end; ++oi) hist[hp.ops[oi].type]++;
+          printf("   pass %d regbits=[", p);
+          for (int j = 0; j < hp.K; ++j) printf("%d ", ps.regbit[j]);
+          printf("] ngrad=%d ops:", ps.ngrad);
+          for (int t = 0; t < 19; ++t) if (hist[t]) printf(" %s=%d", names[t], hist[t]);
+          printf("\n");
+        }
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }

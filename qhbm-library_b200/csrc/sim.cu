@@ -104,10 +104,16 @@ int default_chunk(const qhbm_plan* p) {
   }
   const int tiles = hp.tiles();
   if (tiles == 1) return 1 << 20;  // single launch, no workspace
-  // keep the in-flight states L2-resident (126 MB) and the grid a multiple of the SM count
+  // Multi-tile states round-trip through global memory between sweeps.  The sweeps are compute
+  // bound (DRAM traffic is a few % of peak), so L2 residency does not matter; what matters is that
+  // each launch is many waves deep.  Workspace budget: 4 GiB (of 180 GB).
   const size_t state_bytes = (size_t)8 << hp.n_eff;
   const size_t per_state = state_bytes * (hp.grad ? 2 : 1);
-  const size_t budget = (size_t)80 << 20;
+  size_t budget = (size_t)4 << 30;
+  if (const char* e = std::getenv("QHBM_WORKSPACE_MB")) {
+    long v = std::atol(e);
+    if (v > 0) budget = (size_t)v << 20;
+  }
   int c = (int)std::max<size_t>(1, budget / per_state);
   const int waves = std::max(1, (c * tiles) / p->sm_count);
   c = std::max(1, (waves * p->sm_count) / tiles);

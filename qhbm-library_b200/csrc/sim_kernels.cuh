@@ -276,10 +276,12 @@ __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const f
                                               const DevOp* __restrict__ ops, int count, bool pairs,
                                               const float* __restrict__ coef, float* scratch, uint32_t gbase,
                                               uint32_t tid, uint32_t nthr) {
+  OpRec nxt = load_op(ops);  // issued before the marginals so that its latency is covered
   Marginals<K> mg;
   compute_marginals<K>(a, b, mg, pairs);
   for (int i = 0; i < count; ++i) {
-    const OpRec op = load_op(ops + i);
+    const OpRec op = nxt;
+    if (i + 1 < count) nxt = load_op(ops + i + 1);
     const float* e = coef + op.coef;
     float val;
     if (op.type == OP_GD_CONST) {
@@ -497,16 +499,11 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
 // The thread's amplitudes are i_m = m * nthreads + tid; parity(i_m & z) splits into a per-thread
 // bit and a per-m bit that the host precomputed (DevTerm::mword).
 // ---------------------------------------------------------------------------------
-// One x-group of one observable for MC of the thread's amplitudes.  SRC: 0 diagonal (partner = own
-// amplitude), 1 partner inside the tile (smem), 2 partner in another tile (global / L2).
-template <int MC, bool ADJ, bool CPLX, int SRC>
-__device__ __forceinline__ float expect_group(const KernelArgs& ka, const float2* s_psi, const float2* __restrict__ psi_u,
-                                              const float2 (&a)[MC], float2 (&lam)[ADJ ? MC : 1], const uint32_t (&ph)[MC],
-                                              const uint32_t gi_tid, const uint32_t nthr, const int m0, const uint32_t x,
-                                              const int xl, const int t0, const int t1, const float k0r, const float k0i,
-                                              const float gj) {
-  float cr[MC];
-  float ci[CPLX ? MC : 1];
+// Coefficients c(i_m) = k0 + sum_t k_t (-1)^{parity(i_m & z_t)} of one x-group for MC amplitudes.
+template <int MC, bool CPLX>
+__device__ __forceinline__ void group_coefficients(const KernelArgs& ka, float (&cr)[MC], float (&ci)[CPLX ? MC : 1],
+                                                   const uint32_t gi_tid, const int m0, const int t0, const int t1,
+                                                   const float k0r, const float k0i) {
 #pragma unroll
   for (int m = 0; m < MC; ++m) {
     cr[m] = k0r;
@@ -523,36 +520,45 @@ __device__ __forceinline__ float expect_group(const KernelArgs& ka, const float2
       if constexpr (CPLX) ci[m] += __uint_as_float(__float_as_uint(tv.y) ^ sgn);
     }
   }
-  const uint32_t pxor = SRC == 1 ? swz((uint32_t)xl) : 0u;
-  float ej = 0.f;
+}
+
+// h[m] += c(i_m) * psi[i_m ^ x] for one off-diagonal x-group.  GLOBAL: the partner lives in
+// another tile (read through L2), else inside this tile's shared memory.
+template <int MC, bool CPLX, bool GLOBAL>
+__device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const float2* s_psi, const float2* __restrict__ psi_u,
+                                              float2 (&h)[MC], const uint32_t gi_tid, const uint32_t ph_tid,
+                                              const uint32_t nthr, const int m0, const uint32_t x, const int xl,
+                                              const int t0, const int t1, const float k0r, const float k0i) {
+  float cr[MC];
+  float ci[CPLX ? MC : 1];
+  group_coefficients<MC, CPLX>(ka, cr, ci, gi_tid, m0, t0, t1, k0r, k0i);
+  const uint32_t pxor = GLOBAL ? 0u : swz((uint32_t)xl);
 #pragma unroll
   for (int m = 0; m < MC; ++m) {
     float2 p;
-    if constexpr (SRC == 0) p = a[m];
-    else if constexpr (SRC == 1) p = s_psi[ph[m] ^ pxor];
-    else p = psi_u[(gi_tid | scatter_bits((uint32_t)(m0 + m) * nthr, ka.L.runs, ka.L.n_runs)) ^ x];
-    float hr = cr[m] * p.x, hi = cr[m] * p.y;
-    if constexpr (CPLX) { hr = fmaf(-ci[m], p.y, hr); hi = fmaf(ci[m], p.x, hi); }
-    ej = fmaf(a[m].x, hr, fmaf(a[m].y, hi, ej));
-    if constexpr (ADJ) {
-      lam[m].x = fmaf(gj, hr, lam[m].x);
-      lam[m].y = fmaf(gj, hi, lam[m].y);
+    if constexpr (GLOBAL) p = psi_u[(gi_tid | scatter_bits((uint32_t)(m0 + m) * nthr, ka.L.runs, ka.L.n_runs)) ^ x];
+    else p = s_psi[ph_tid ^ swz((uint32_t)(m0 + m) * nthr) ^ pxor];
+    h[m].x = fmaf(cr[m], p.x, h[m].x);
+    h[m].y = fmaf(cr[m], p.y, h[m].y);
+    if constexpr (CPLX) {
+      h[m].x = fmaf(-ci[m], p.y, h[m].x);
+      h[m].y = fmaf(ci[m], p.x, h[m].y);
     }
   }
-  return ej;
 }
 
 // ---------------------------------------------------------------------------------
 // Expectation phase: E_j = Re <psi|H_j|psi>, and (adjoint) lambda = sum_j g_j H_j psi.
-// H psi[i] = sum_groups c_g(i) psi[i ^ x_g]; c_g(i) = k0 + sum_t k_t (-1)^{parity(i & z_t)}.
+// H psi[i] = sum_groups c_g(i) psi[i ^ x_g]; all terms of a group share the x-mask.
 // The thread's amplitudes are i_m = m * nthreads + tid; parity(i_m & z) splits into a per-thread
-// bit and a per-m bit that the host precomputed (DevTerm::mword).
+// bit and a per-m bit that the host precomputed (DevTerm::mword).  Diagonal groups (x = 0) only
+// need |psi_i|^2 and a real per-amplitude factor D_i = sum_j g_j c_j(i), applied once at the end.
 // ---------------------------------------------------------------------------------
 template <int K, bool ADJ>
 __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi, float2* s_lam, uint32_t goff,
                                              uint32_t u, const float2* __restrict__ psi_u) {
   constexpr int R = 1 << K;
-  constexpr int MC = R < 16 ? R : 16;  // amplitudes per thread handled at a time
+  constexpr int MC = ADJ ? (R < 8 ? R : 8) : (R < 16 ? R : 16);  // amplitudes per thread handled at a time
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
   const bool want_lam = ADJ && ka.dgrad != nullptr;
   const uint32_t gi_tid = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
@@ -560,43 +566,82 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
   __syncthreads();
   for (int m0 = 0; m0 < R; m0 += MC) {
     float2 a[MC];
+    float p2[MC];
     float2 lam[ADJ ? MC : 1];
-    uint32_t ph[MC];
+    float dg[ADJ ? MC : 1];
 #pragma unroll
     for (int m = 0; m < MC; ++m) {
-      ph[m] = ph_tid ^ swz((uint32_t)(m0 + m) * nthr);
-      a[m] = s_psi[ph[m]];
-      if constexpr (ADJ) lam[m] = make_float2(0.f, 0.f);
+      a[m] = s_psi[ph_tid ^ swz((uint32_t)(m0 + m) * nthr)];
+      p2[m] = a[m].x * a[m].x + a[m].y * a[m].y;
+      if constexpr (ADJ) {
+        lam[m] = make_float2(0.f, 0.f);
+        dg[m] = 0.f;
+      }
     }
     for (int j = 0; j < ka.O; ++j) {
       const float gj = want_lam ? __ldg(&ka.dgrad[(size_t)u * ka.O + j]) : 0.f;
       float ej = 0.f;
+      float2 h[MC];
+      bool offdiag = false;
       const int g_end = __ldg(&ka.opranges[j].group_end);
-      for (int g = __ldg(&ka.opranges[j].group_begin); g < g_end; ++g) {
-        const int4 gh = __ldg(reinterpret_cast<const int4*>(ka.groups + g));
-        const int4 gk = __ldg(reinterpret_cast<const int4*>(ka.groups + g) + 1);
-        const uint32_t x = (uint32_t)gh.x;
-        const int xl = gh.y;
-        const float k0r = __int_as_float(gk.x), k0i = __int_as_float(gk.y);
-#define QHBM_EG(CPLX, SRC) \
-  expect_group<MC, ADJ, CPLX, SRC>(ka, s_psi, psi_u, a, lam, ph, gi_tid, nthr, m0, x, xl, gh.z, gh.w, k0r, k0i, gj)
-        if (gk.z == 0) {
-          if (x == 0) ej += QHBM_EG(false, 0);
-          else if (xl >= 0) ej += QHBM_EG(false, 1);
-          else ej += QHBM_EG(false, 2);
-        } else {
-          if (x == 0) ej += QHBM_EG(true, 0);
-          else if (xl >= 0) ej += QHBM_EG(true, 1);
-          else ej += QHBM_EG(true, 2);
+      int g = __ldg(&ka.opranges[j].group_begin);
+      int4 gh, gk;
+      if (g < g_end) {
+        gh = __ldg(reinterpret_cast<const int4*>(ka.groups + g));
+        gk = __ldg(reinterpret_cast<const int4*>(ka.groups + g) + 1);
+      }
+      for (; g < g_end; ++g) {
+        const int4 ch = gh, ck = gk;
+        if (g + 1 < g_end) {  // prefetch the next group header
+          gh = __ldg(reinterpret_cast<const int4*>(ka.groups + g + 1));
+          gk = __ldg(reinterpret_cast<const int4*>(ka.groups + g + 1) + 1);
         }
-#undef QHBM_EG
+        const uint32_t x = (uint32_t)ch.x;
+        const int xl = ch.y;
+        const float k0r = __int_as_float(ck.x), k0i = __int_as_float(ck.y);
+        if (x == 0) {
+          float cr[MC], ci[1];
+          group_coefficients<MC, false>(ka, cr, ci, gi_tid, m0, ch.z, ch.w, k0r, 0.f);
+#pragma unroll
+          for (int m = 0; m < MC; ++m) {
+            ej = fmaf(cr[m], p2[m], ej);
+            if constexpr (ADJ) dg[m] = fmaf(gj, cr[m], dg[m]);
+          }
+          continue;
+        }
+        if (!offdiag) {
+          offdiag = true;
+#pragma unroll
+          for (int m = 0; m < MC; ++m) h[m] = make_float2(0.f, 0.f);
+        }
+        if (ck.z == 0) {
+          if (xl >= 0) group_offdiag<MC, false, false>(ka, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          else group_offdiag<MC, false, true>(ka, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+        } else {
+          if (xl >= 0) group_offdiag<MC, true, false>(ka, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          else group_offdiag<MC, true, true>(ka, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+        }
+      }
+      if (offdiag) {
+#pragma unroll
+        for (int m = 0; m < MC; ++m) {
+          ej = fmaf(a[m].x, h[m].x, fmaf(a[m].y, h[m].y, ej));
+          if constexpr (ADJ) {
+            lam[m].x = fmaf(gj, h[m].x, lam[m].x);
+            lam[m].y = fmaf(gj, h[m].y, lam[m].y);
+          }
+        }
       }
       ej = warp_sum(ej);
       if ((tid & 31) == 0) atomicAdd(&ka.eacc[(size_t)u * ka.O + j], (double)ej);
     }
     if constexpr (ADJ) {
 #pragma unroll
-      for (int m = 0; m < MC; ++m) s_lam[ph[m]] = lam[m];
+      for (int m = 0; m < MC; ++m) {
+        lam[m].x = fmaf(dg[m], a[m].x, lam[m].x);
+        lam[m].y = fmaf(dg[m], a[m].y, lam[m].y);
+        s_lam[ph_tid ^ swz((uint32_t)(m0 + m) * nthr)] = lam[m];
+      }
     }
   }
 }

@@ -21,10 +21,16 @@ rng = np.random.default_rng(0)
 phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
 basis = torch.tensor(rng.choice(1 << n, u, replace=False).astype(np.int64), device="cuda")
 dg = torch.tensor(rng.uniform(0, 1, (u, 1)).astype(np.float32), device="cuda")
+best = None
 for _ in range(reps):
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
   if grad:
     plan.forward_adjoint(basis, phi, dg)
   else:
     plan.forward(basis, phi)
-torch.cuda.synchronize()
-print(plan.info)
+  b.record()
+  torch.cuda.synchronize()
+  t = a.elapsed_time(b)
+  best = t if best is None else min(best, t)
+print(plan.info, f"best {best:.2f} ms {u / best * 1e3:.0f} bitstrings/s")

@@ -239,7 +239,7 @@ class Compiler {
     const int n = hp_.n_eff, K = hp_.K;
     std::vector<char> done(atoms.size(), 0);
     size_t remaining = atoms.size();
-    const int max_slots = 4 * (1 << K);  // gradient scratch = the two dead smem tiles
+    const int max_slots = std::min(4 * (1 << K), 255);  // gradient scratch = the two dead smem tiles
     while (remaining > 0) {
       SweepOut sw;
       sw.tile_bits = choose_tile(atoms, done);
@@ -353,6 +353,7 @@ class Compiler {
         }
         flush_diag(run, backward);
         if (executed == 0) break;  // nothing runnable with this tile: next sweep
+        merge_rotations(ps);
         ps.op_end = (int)hp_.ops.size();
         hp_.passes.push_back(ps);
         executed_in_sweep += executed;
@@ -366,6 +367,45 @@ class Compiler {
         throw std::runtime_error("internal: scheduler made no progress");
       sweeps.push_back(sw);
     }
+  }
+
+  // Peephole: consecutive X (or Y) rotations on distinct register positions become ONE op whose
+  // handler is straight-line code over the positions (no per-gate dispatch).
+  void merge_rotations(const DevPass& ps) {
+    std::vector<DevOp> out;
+    const int K = hp_.K;
+    size_t i = (size_t)ps.op_begin;
+    const size_t end = hp_.ops.size();
+    while (i < end) {
+      const DevOp& o = hp_.ops[i];
+      if (o.type != OP_XROT && o.type != OP_YROT) { out.push_back(o); ++i; continue; }
+      size_t j = i;
+      int mask = 0;
+      while (j < end && hp_.ops[j].type == o.type && !(mask & (1 << hp_.ops[j].p0))) { mask |= 1 << hp_.ops[j].p0; ++j; }
+      DevOp m = make_op(o.type == OP_XROT ? OP_XROTM : OP_YROTM);
+      m.p0 = mask;
+      m.aux0 = 0;
+      m.coef = alloc_coef(4 * K);
+      // per-position gradient slots, 8 bits each: positions 0..3 in aux1, position 4 in p1
+      m.aux1 = 0;
+      m.p1 = 0;
+      for (size_t q = i; q < j; ++q) {
+        const DevOp& r = hp_.ops[q];
+        for (auto& job : hp_.jobs) {  // retarget the coefficient jobs of this rotation
+          if ((job.kind == PJ_ROT && job.out == r.coef) || (job.kind == PJ_KAPPA && job.out == r.coef + 2))
+            job.out = m.coef + 4 * r.p0 + (job.kind == PJ_KAPPA ? 2 : 0);
+        }
+        if (r.gslot >= 0) {
+          m.aux0 |= 1 << r.p0;
+          if (r.p0 < 4) m.aux1 |= (r.gslot & 0xff) << (8 * r.p0);
+          else m.p1 = r.gslot;
+        }
+      }
+      out.push_back(m);
+      i = j;
+    }
+    hp_.ops.resize(ps.op_begin);
+    hp_.ops.insert(hp_.ops.end(), out.begin(), out.end());
   }
 
   void emit_nondiag(const Atom& a, bool backward, const std::vector<int>& regpos, DevPass& ps) {
@@ -511,10 +551,18 @@ class Compiler {
     if (!run.any) return;
     const int dag = backward ? 1 : 0;
     if (!run.gd_ops.empty()) {
+      auto rank = [](const DevOp& o) { return o.type == OP_GD_CONST ? 0 : (o.type == OP_GD_REG2 ? 2 : 1); };
+      std::stable_sort(run.gd_ops.begin(), run.gd_ops.end(),
+                       [&](const DevOp& x, const DevOp& y) { return rank(x) < rank(y); });
       DevOp b = make_op(OP_GD_BEGIN);
       b.aux0 = (int)run.gd_ops.size();
       b.aux1 = 0;
-      for (auto& o : run.gd_ops) if (o.type == OP_GD_REG2) b.aux1 = 1;
+      b.p0 = b.p1 = 0;
+      for (auto& o : run.gd_ops) {
+        if (o.type == OP_GD_REG2) b.aux1 = 1;
+        if (rank(o) == 0) ++b.p0;
+        if (rank(o) == 1) ++b.p1;
+      }
       hp_.ops.push_back(b);
       for (auto& o : run.gd_ops) hp_.ops.push_back(o);
     }

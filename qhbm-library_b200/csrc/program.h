@@ -37,9 +37,14 @@ enum OpType : int32_t {
   // gradient ops (adjoint sweeps only); value lands in scratch slot gslot
   OP_GRAD_MAT1,   // 2 Re <lam| M |psi>, M 2x2 at coef, position p0
   OP_GRAD_MAT2,   // same for 4x4, p0 as in OP_MAT2
+  OP_XROTM,       // several OP_XROT in one op: p0 = mask of register positions, coef -> K x (c, s, kappa, -),
+                  //     aux0 = mask of positions with a gradient; slot of position P: byte P of aux1
+                  //     (P < 4) or p1 (P = 4)
+  OP_YROTM,       // same for OP_YROT
   OP_GRAD_X,      // kappa * Im <lam| X_p0 |psi>; coef -> kappa   (two-level X-type gate)
   OP_GRAD_Y,      // kappa * Im <lam| Y_p0 |psi>; coef -> kappa
-  OP_GD_BEGIN,    // starts a run of aux0 diagonal-gradient ops (they share conj(lam)*psi);
+  OP_GD_BEGIN,    // starts a run of aux0 diagonal-gradient ops (they share conj(lam)*psi), sorted by kind:
+                  //     p0 OP_GD_CONST, then p1 OP_GD_REG1 / OP_GD_MIX, then the OP_GD_REG2;
                   //     aux1 != 0: pair marginals are needed (some OP_GD_REG2 in the run)
   OP_GD_CONST,    // entries M[sel] at coef (complex); sel = 2*bit(aux0)+bit(aux1) (aux1<0: bit(aux0))
   OP_GD_REG1,     // sel = register bit p0; coef -> 2 complex

@@ -39,6 +39,7 @@ struct KernelArgs {
   int32_t grow0;          // accumulator row of this chunk's first state (per-state gradients)
   int32_t per_state;
   int32_t phase_coef;     // coef offset of the dropped global phase (debug state output), or -1
+  int32_t sync_ops;       // experiment: CTA barrier every sync_ops ops keeps the warps on the same code
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t x) {
@@ -98,6 +99,15 @@ __device__ __forceinline__ void dispatch_pos(int p, F&& f) {
     default:
       if constexpr (K > 4) f(IntC<4>{});
       break;
+  }
+}
+
+// Calls f(IntC<0>{}), ..., f(IntC<K-1>{}) in order (compile-time loop over register positions).
+template <int K, int P = 0, class F>
+__device__ __forceinline__ void for_each_pos(F&& f) {
+  if constexpr (P < K) {
+    f(IntC<P>{});
+    for_each_pos<K, P + 1>(f);
   }
 }
 
@@ -273,38 +283,45 @@ __device__ __forceinline__ void compute_marginals(const float2 (&a)[1 << K], con
 
 template <int K>
 __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
-                                              const DevOp* __restrict__ ops, int count, bool pairs,
-                                              const float* __restrict__ coef, float* scratch, uint32_t gbase,
-                                              uint32_t tid, uint32_t nthr) {
+                                              const DevOp* __restrict__ ops, const int n_const, const int n_reg1,
+                                              const int count, const bool pairs, const float* __restrict__ coef,
+                                              float* scratch, uint32_t gbase, uint32_t tid, uint32_t nthr) {
   OpRec nxt = load_op(ops);  // issued before the marginals so that its latency is covered
   Marginals<K> mg;
   compute_marginals<K>(a, b, mg, pairs);
-  for (int i = 0; i < count; ++i) {
+  int i = 0;
+  // gates whose qubits are all thread-constant: one selected entry times the thread totals
+  for (; i < n_const; ++i) {
+    const OpRec op = nxt;
+    if (i + 1 < count) nxt = load_op(ops + i + 1);
+    int sel = (gbase >> op.aux0) & 1;
+    if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1);
+    const float2 m = ldg2(coef + op.coef + 2 * sel);
+    scratch[op.gslot * nthr + tid] = 2.f * (m.x * mg.U - m.y * mg.V);
+  }
+  // one register bit (plus, for OP_GD_MIX, one thread-constant bit)
+  for (; i < n_const + n_reg1; ++i) {
+    const OpRec op = nxt;
+    if (i + 1 < count) nxt = load_op(ops + i + 1);
+    const int cb = op.type == OP_GD_MIX ? ((gbase >> op.aux0) & 1) : 0;
+    const float U1 = pick<K>(mg.Up, op.p0), V1 = pick<K>(mg.Vp, op.p0);
+    const float4 m = ldg4(coef + op.coef + 4 * cb);
+    scratch[op.gslot * nthr + tid] = 2.f * (m.x * (mg.U - U1) - m.y * (mg.V - V1) + m.z * U1 - m.w * V1);
+  }
+  // two register bits, p0 > p1
+  for (; i < count; ++i) {
     const OpRec op = nxt;
     if (i + 1 < count) nxt = load_op(ops + i + 1);
     const float* e = coef + op.coef;
-    float val;
-    if (op.type == OP_GD_CONST) {
-      int sel = (gbase >> op.aux0) & 1;
-      if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1);
-      const float2 m = ldg2(e + 2 * sel);
-      val = m.x * mg.U - m.y * mg.V;
-    } else if (op.type == OP_GD_REG1 || op.type == OP_GD_MIX) {
-      const int cb = op.type == OP_GD_MIX ? ((gbase >> op.aux0) & 1) : 0;
-      const float U1 = pick<K>(mg.Up, op.p0), V1 = pick<K>(mg.Vp, op.p0);
-      const float4 m = ldg4(e + 4 * cb);
-      val = m.x * (mg.U - U1) - m.y * (mg.V - V1) + m.z * U1 - m.w * V1;
-    } else {  // OP_GD_REG2, p0 > p1
-      const float Uh = pick<K>(mg.Up, op.p0), Vh = pick<K>(mg.Vp, op.p0);
-      const float Ul = pick<K>(mg.Up, op.p1), Vl = pick<K>(mg.Vp, op.p1);
-      const int pi = op.p0 * (op.p0 - 1) / 2 + op.p1;
-      const float U11 = pick<Marginals<K>::NP>(mg.Upp, pi), V11 = pick<Marginals<K>::NP>(mg.Vpp, pi);
-      const float4 m01 = ldg4(e), m23 = ldg4(e + 4);
-      val = m01.x * (mg.U - Uh - Ul + U11) - m01.y * (mg.V - Vh - Vl + V11)  // sel 0
-            + m01.z * (Ul - U11) - m01.w * (Vl - V11)                         // sel 1: lo bit only
-            + m23.x * (Uh - U11) - m23.y * (Vh - V11)                         // sel 2: hi bit only
-            + m23.z * U11 - m23.w * V11;                                      // sel 3
-    }
+    const float Uh = pick<K>(mg.Up, op.p0), Vh = pick<K>(mg.Vp, op.p0);
+    const float Ul = pick<K>(mg.Up, op.p1), Vl = pick<K>(mg.Vp, op.p1);
+    const int pi = op.p0 * (op.p0 - 1) / 2 + op.p1;
+    const float U11 = pick<Marginals<K>::NP>(mg.Upp, pi), V11 = pick<Marginals<K>::NP>(mg.Vpp, pi);
+    const float4 m01 = ldg4(e), m23 = ldg4(e + 4);
+    const float val = m01.x * (mg.U - Uh - Ul + U11) - m01.y * (mg.V - Vh - Vl + V11)  // sel 0
+                      + m01.z * (Ul - U11) - m01.w * (Vl - V11)                         // sel 1: lo bit only
+                      + m23.x * (Uh - U11) - m23.y * (Vh - V11)                         // sel 2: hi bit only
+                      + m23.z * U11 - m23.w * V11;                                      // sel 3
     scratch[op.gslot * nthr + tid] = 2.f * val;
   }
 }
@@ -356,9 +373,14 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   int oi = __ldg(&ps->op_begin);
   OpRec nxt;
   if (oi < op_end) nxt = load_op(ka.ops + oi);
+  int since_sync = 0;
   while (oi < op_end) {
     const OpRec op = nxt;
     const float* cf = ka.coef + op.coef;
+    if (ka.sync_ops > 0 && ++since_sync >= ka.sync_ops) {
+      since_sync = 0;
+      __syncthreads();
+    }
     int step = 1;
     if (op.type == OP_GD_BEGIN) step += op.aux0;
     if (oi + step < op_end) nxt = load_op(ka.ops + oi + step);  // prefetch the next descriptor
@@ -383,6 +405,29 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
           }
           yrot<K, P>(a, cs.x, cs.y);
           if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
+        });
+      } break;
+      case OP_XROTM:
+      case OP_YROTM: {
+        const bool isx = op.type == OP_XROTM;
+        for_each_pos<K>([&](auto pc) {
+          constexpr int P = decltype(pc)::value;
+          if (op.p0 & (1 << P)) {
+            const float4 cs = ldg4(cf + 4 * P);  // (c, s, kappa, -)
+            if constexpr (BOTH) {
+              if (op.aux0 & (1 << P)) {
+                const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1;
+                scratch[slot * nthr + tid] = cs.z * (isx ? im_bxa<K, P>(a, b) : im_bya<K, P>(a, b));
+              }
+            }
+            if (isx) {
+              xrot<K, P>(a, cs.x, cs.y);
+              if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
+            } else {
+              yrot<K, P>(a, cs.x, cs.y);
+              if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
+            }
+          }
         });
       } break;
       case OP_MAT1: {
@@ -465,7 +510,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
             const float g = op.p0 == 0 ? mat2<K, 0, true>(a, b, cf) : mat2<K, 2, true>(a, b, cf);
             scratch[op.gslot * nthr + tid] = g;
           } else if (op.type == OP_GD_BEGIN) {
-            grad_diag_run<K>(a, b, ka.ops + oi + 1, op.aux0, op.aux1 != 0, ka.coef, scratch, gbase, tid, nthr);
+            grad_diag_run<K>(a, b, ka.ops + oi + 1, op.p0, op.p1, op.aux0, op.aux1 != 0, ka.coef, scratch, gbase, tid, nthr);
           }
         }
         break;

@@ -169,6 +169,32 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
             }
           }
         } break;
+        case OP_XROTM: case OP_YROTM: {
+          for (int P = 0; P < K; ++P) if (op.p0 & (1 << P)) {
+            const double cc = c.coef[op.coef + 4 * P], ss = c.coef[op.coef + 4 * P + 1], kap = c.coef[op.coef + 4 * P + 2];
+            const bool isx = op.type == OP_XROTM;
+            const cplx m01 = isx ? cplx(0, -ss) : cplx(-ss, 0);
+            const cplx m10 = isx ? cplx(0, -ss) : cplx(ss, 0);
+            if (both && (op.aux0 & (1 << P))) {
+              double sacc = 0;
+              for (int r = 0; r < R; ++r) if (!(r & (1 << P))) {
+                const int q = r | (1 << P);
+                cplx y0, y1;
+                if (isx) { y0 = a[q]; y1 = a[r]; } else { y0 = cplx(0, -1) * a[q]; y1 = cplx(0, 1) * a[r]; }
+                sacc += (std::conj(b[r]) * y0 + std::conj(b[q]) * y1).imag();
+              }
+              gsum[P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1] += kap * sacc;
+            }
+            for (int which = 0; which < (both ? 2 : 1); ++which) {
+              std::vector<cplx>& v = which ? b : a;
+              for (int r = 0; r < R; ++r) if (!(r & (1 << P))) {
+                cplx x0 = v[r], x1 = v[r | (1 << P)];
+                v[r] = cc * x0 + m01 * x1;
+                v[r | (1 << P)] = m10 * x0 + cc * x1;
+              }
+            }
+          }
+        } break;
         case OP_GRAD_X: case OP_GRAD_Y: {
           double sacc = 0;
           for (int r = 0; r < R; ++r) if (!(r & (1 << op.p0))) {
@@ -322,8 +348,8 @@ extern "C" int verify_dump(const qhbm_gate_t* gates, int n_gates, int n, int P, 
     OpsIR o; o.n_qubits = n; o.offsets.assign(offs, offs + O + 1); o.terms.assign(terms, terms + offs[O]);
     HostPlan hp = compile_plan(c, o, with_grad != 0, T, K);
     static const char* names[] = {"NOP", "MAT1", "MAT2", "DCONST_TAB", "DCONST_PAIR", "DREG_TAB", "DAPPLY", "DCROSS",
-                                  "XROT", "YROT", "GRAD_MAT1", "GRAD_MAT2", "GRAD_X", "GRAD_Y", "GD_BEGIN", "GD_CONST",
-                                  "GD_REG1", "GD_REG2", "GD_MIX"};
+                                  "XROT", "YROT", "GRAD_MAT1", "GRAD_MAT2", "XROTM", "YROTM", "GRAD_X", "GRAD_Y", "GD_BEGIN",
+                                  "GD_CONST", "GD_REG1", "GD_REG2", "GD_MIX"};
     printf("n_eff=%d T=%d K=%d ncoef=%d jobs=%zu terms=%zu groups=%zu\n", hp.n_eff, hp.T, hp.K, hp.ncoef, hp.jobs.size(),
            hp.terms.size(), hp.groups.size());
     for (size_t li = 0; li < hp.launches.size(); ++li) {
@@ -334,12 +360,12 @@ extern "C" int verify_dump(const qhbm_gate_t* gates, int n_gates, int n, int P, 
         int b = pass ? L.pass_b_begin : L.pass_a_begin, e = pass ? L.pass_b_end : L.pass_a_end;
         for (int p = b; p < e; ++p) {
           const DevPass& ps = hp.passes[p];
-          int hist[19] = {0};
+          int hist[21] = {0};
           for (int oi = ps.op_begin; oi < ps.op_end; ++oi) hist[hp.ops[oi].type]++;
           printf("   pass %d regbits=[", p);
           for (int j = 0; j < hp.K; ++j) printf("%d ", ps.regbit[j]);
           printf("] ngrad=%d ops:", ps.ngrad);
-          for (int t = 0; t < 19; ++t) if (hist[t]) printf(" %s=%d", names[t], hist[t]);
+          for (int t = 0; t < 21; ++t) if (hist[t]) printf(" %s=%d", names[t], hist[t]);
           printf("\n");
         }
       }

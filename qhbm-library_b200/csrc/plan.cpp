@@ -615,6 +615,17 @@ class Compiler {
     for (int b = 0; b < n; ++b) if (!in[b]) obits.push_back(b);
     build(tile_bits, L.runs, L.n_runs);
     build(obits, L.oruns, L.n_oruns);
+    const int mshift = (int)tile_bits.size() - hp_.K;
+    for (int m = 0; m < (1 << kMaxRegQubits); ++m) {
+      L.moff[m] = 0;
+      L.soff[m] = 0;
+      if (m >= (1 << hp_.K) || mshift < 0) continue;
+      const uint32_t l = (uint32_t)m << mshift;
+      uint32_t g = 0;
+      for (size_t j = 0; j < tile_bits.size(); ++j) if ((l >> j) & 1) g |= 1u << tile_bits[j];
+      L.moff[m] = g;
+      L.soff[m] = (uint16_t)((l & ~15u) | ((l ^ (l >> 4) ^ (l >> 8) ^ (l >> 12)) & 15u));
+    }
   }
 
   void build_terms(const OpsIR& o) {

@@ -96,6 +96,9 @@ struct LaunchDesc {
   BitRun oruns[kMaxRuns];            // tile-id bits -> state bits (the out-of-tile bits)
   uint32_t tile_mask;                // state-index bits covered by the tile
   int32_t group_set;                 // which term-group table to use for LF_EXPECT
+  // the thread's m-th tile element is local index (m << (T-K)) | tid:
+  uint32_t moff[1 << kMaxRegQubits]; // its state-index contribution scatter(m << (T-K))
+  uint16_t soff[1 << kMaxRegQubits]; // its swizzled smem contribution swz(m << (T-K))
 };
 
 // Pauli-sum tables for the expectation phase.

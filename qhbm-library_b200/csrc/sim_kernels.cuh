@@ -47,12 +47,14 @@ __device__ __forceinline__ uint32_t swz(uint32_t x) {
 }
 __device__ __forceinline__ uint32_t scatter_bits(uint32_t l, const BitRun* runs, int nr) {
   uint32_t g = 0;
+#pragma unroll 1
   for (int i = 0; i < nr; ++i)
     g |= ((l >> runs[i].local_start) & ((1u << runs[i].len) - 1u)) << runs[i].global_start;
   return g;
 }
 __device__ __forceinline__ uint32_t gather_bits(uint32_t g, const BitRun* runs, int nr) {
   uint32_t l = 0;
+#pragma unroll 1
   for (int i = 0; i < nr; ++i)
     l |= ((g >> runs[i].global_start) & ((1u << runs[i].len) - 1u)) << runs[i].local_start;
   return l;
@@ -407,9 +409,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
           if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
         });
       } break;
-      case OP_XROTM:
-      case OP_YROTM: {
-        const bool isx = op.type == OP_XROTM;
+      case OP_XROTM: {
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
           if (op.p0 & (1 << P)) {
@@ -417,16 +417,27 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
             if constexpr (BOTH) {
               if (op.aux0 & (1 << P)) {
                 const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1;
-                scratch[slot * nthr + tid] = cs.z * (isx ? im_bxa<K, P>(a, b) : im_bya<K, P>(a, b));
+                scratch[slot * nthr + tid] = cs.z * im_bxa<K, P>(a, b);
               }
             }
-            if (isx) {
-              xrot<K, P>(a, cs.x, cs.y);
-              if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
-            } else {
-              yrot<K, P>(a, cs.x, cs.y);
-              if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
+            xrot<K, P>(a, cs.x, cs.y);
+            if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
+          }
+        });
+      } break;
+      case OP_YROTM: {
+        for_each_pos<K>([&](auto pc) {
+          constexpr int P = decltype(pc)::value;
+          if (op.p0 & (1 << P)) {
+            const float4 cs = ldg4(cf + 4 * P);
+            if constexpr (BOTH) {
+              if (op.aux0 & (1 << P)) {
+                const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1;
+                scratch[slot * nthr + tid] = cs.z * im_bya<K, P>(a, b);
+              }
             }
+            yrot<K, P>(a, cs.x, cs.y);
+            if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
           }
         });
       } break;
@@ -581,8 +592,8 @@ __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const float2
 #pragma unroll
   for (int m = 0; m < MC; ++m) {
     float2 p;
-    if constexpr (GLOBAL) p = psi_u[(gi_tid | scatter_bits((uint32_t)(m0 + m) * nthr, ka.L.runs, ka.L.n_runs)) ^ x];
-    else p = s_psi[ph_tid ^ swz((uint32_t)(m0 + m) * nthr) ^ pxor];
+    if constexpr (GLOBAL) p = psi_u[(gi_tid | ka.L.moff[m0 + m]) ^ x];
+    else p = s_psi[ph_tid ^ ka.L.soff[m0 + m] ^ pxor];
     h[m].x = fmaf(cr[m], p.x, h[m].x);
     h[m].y = fmaf(cr[m], p.y, h[m].y);
     if constexpr (CPLX) {
@@ -616,7 +627,7 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
     float dg[ADJ ? MC : 1];
 #pragma unroll
     for (int m = 0; m < MC; ++m) {
-      a[m] = s_psi[ph_tid ^ swz((uint32_t)(m0 + m) * nthr)];
+      a[m] = s_psi[ph_tid ^ ka.L.soff[m0 + m]];
       p2[m] = a[m].x * a[m].x + a[m].y * a[m].y;
       if constexpr (ADJ) {
         lam[m] = make_float2(0.f, 0.f);
@@ -685,7 +696,7 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
       for (int m = 0; m < MC; ++m) {
         lam[m].x = fmaf(dg[m], a[m].x, lam[m].x);
         lam[m].y = fmaf(dg[m], a[m].y, lam[m].y);
-        s_lam[ph_tid ^ swz((uint32_t)(m0 + m) * nthr)] = lam[m];
+        s_lam[ph_tid ^ ka.L.soff[m0 + m]] = lam[m];
       }
     }
   }
@@ -694,27 +705,28 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
 template <int K>
 __device__ __forceinline__ void load_tile(float2* s, const float2* __restrict__ g, uint32_t goff, const KernelArgs& ka) {
   constexpr int R = 1 << K;
-  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  const uint32_t tid = threadIdx.x;
   const uint32_t gt = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
   const uint32_t pt = swz(tid);
   float2 v[R];
 #pragma unroll
-  for (int m = 0; m < R; ++m) v[m] = g[gt | scatter_bits((uint32_t)m * nthr, ka.L.runs, ka.L.n_runs)];
+  for (int m = 0; m < R; ++m) v[m] = g[gt | ka.L.moff[m]];
 #pragma unroll
-  for (int m = 0; m < R; ++m) s[pt ^ swz((uint32_t)m * nthr)] = v[m];
+  for (int m = 0; m < R; ++m) s[pt ^ ka.L.soff[m]] = v[m];
 }
 template <int K>
 __device__ __forceinline__ void store_tile(const float2* s, float2* __restrict__ g, uint32_t goff, const KernelArgs& ka,
                                            const float2 scale) {
   constexpr int R = 1 << K;
-  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  const uint32_t tid = threadIdx.x;
   const uint32_t gt = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
   const uint32_t pt = swz(tid);
+  const bool scaled = scale.x != 1.f || scale.y != 0.f;
 #pragma unroll
   for (int m = 0; m < R; ++m) {
-    float2 v = s[pt ^ swz((uint32_t)m * nthr)];
-    if (scale.x != 1.f || scale.y != 0.f) v = cmul(v, scale);
-    g[gt | scatter_bits((uint32_t)m * nthr, ka.L.runs, ka.L.n_runs)] = v;
+    float2 v = s[pt ^ ka.L.soff[m]];
+    if (scaled) v = cmul(v, scale);
+    g[gt | ka.L.moff[m]] = v;
   }
 }
 
@@ -744,9 +756,10 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
     active = (basis & ~ka.L.tile_mask) == goff;
     const uint32_t lb = gather_bits(basis, ka.L.runs, ka.L.n_runs);
 #pragma unroll
+    const uint32_t pt = swz(tid);
     for (int m = 0; m < R; ++m) {
       const uint32_t l = (uint32_t)m * nthr | tid;
-      s_psi[swz(l)] = make_float2((active && l == lb) ? 1.f : 0.f, 0.f);
+      s_psi[pt ^ ka.L.soff[m]] = make_float2((active && l == lb) ? 1.f : 0.f, 0.f);
     }
   } else if (flags & LF_LOAD_PSI) {
     load_tile<K>(s_psi, psi_u, goff, ka);

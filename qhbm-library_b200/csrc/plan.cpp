@@ -758,13 +758,17 @@ HostPlan compile_plan(const CircuitIR& c, const OpsIR& o, bool with_gradient, in
   hp.grad = with_gradient;
   hp.K = reg_qubits > 0 ? reg_qubits : (with_gradient ? 4 : 5);
   if (hp.K < 2 || hp.K > kMaxRegQubits) throw std::runtime_error("reg_qubits must be in [2, 5]");
-  int T = tile_qubits > 0 ? tile_qubits : 13;
+  hp.n_eff = std::max(hp.n, hp.K + 5);
+  // Defaults from measurement on B200 (profiles/): a state that fits one tile stays in shared memory
+  // for the whole computation; larger states use 2^12-amplitude tiles for the adjoint (psi + lambda =
+  // 64 KiB, two CTAs per SM) and 2^13 for forward-only sweeps (64 KiB, three CTAs per SM).
   const int t_max = with_gradient ? 13 : 14;  // 2 tiles (psi, lambda) of 8*2^T bytes must fit 227 KB
+  int T = tile_qubits;
+  if (T <= 0) T = hp.n_eff <= std::min(t_max, hp.K + 9) ? hp.n_eff : (with_gradient ? 12 : 13);
   if (T > t_max) throw std::runtime_error("tile_qubits too large for shared memory");
   if (T < hp.K + 5) throw std::runtime_error("tile_qubits must be >= reg_qubits + 5");
   if (T - hp.K > 9) throw std::runtime_error("tile_qubits - reg_qubits must be <= 9 (512 threads per CTA)");
   if (hp.K != 4 && hp.K != 5) throw std::runtime_error("reg_qubits must be 4 or 5");
-  hp.n_eff = std::max(hp.n, hp.K + 5);
   hp.T = std::min(T, hp.n_eff);
   hp.gates = c.gates;
   Compiler comp(hp);

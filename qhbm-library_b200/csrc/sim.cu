@@ -114,10 +114,7 @@ int default_chunk(const qhbm_plan* p) {
     long v = std::atol(e);
     if (v > 0) budget = (size_t)v << 20;
   }
-  int c = (int)std::max<size_t>(1, budget / per_state);
-  const int waves = std::max(1, (c * tiles) / p->sm_count);
-  c = std::max(1, (waves * p->sm_count) / tiles);
-  return c;
+  return (int)std::max<size_t>(1, budget / per_state);
 }
 
 void fill_common(const qhbm_plan* p, KernelArgs& ka) {
@@ -164,7 +161,9 @@ void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const flo
   }
   p->d_eacc.reserve((size_t)U * hp.O);
   if (grows) p->d_gacc.reserve((size_t)std::max<int64_t>(1, grows * hp.P));
-  const int chunk = (int)std::min<int64_t>(p->chunk, U);
+  // equal chunks no larger than the workspace allows (one chunk when everything fits)
+  const int64_t n_chunks = (U + p->chunk - 1) / p->chunk;
+  const int chunk = (int)((U + n_chunks - 1) / n_chunks);
   if (multi) {
     p->d_psi.reserve((size_t)chunk << hp.n_eff);
     if (adjoint) p->d_lam.reserve((size_t)chunk << hp.n_eff);

@@ -32,7 +32,8 @@ def test_hea_tfim_xxz(n, layers, T, K):
   gates, names = orc.hea_circuit(n, layers)
   ops = [orc.tfim_ring(n), orc.xxz_ring(n)] + orc.kobe_shards(n, 2)[:5]
   info = _check(gates, n, len(names), ops, rng, T, K)
-  assert info[4] == (T or min(13, max(n, K + 5)))
+  n_eff = max(n, K + 5)
+  assert info[4] == (min(T, n_eff) if T else (n_eff if n_eff <= 13 else 12))
 
 
 @pytest.mark.parametrize("seed", range(8))

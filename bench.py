@@ -34,6 +34,9 @@ CONFIGS = {
                label="16-qubit Heisenberg XXZ ring, HEA L=2, 4096 unique bitstrings, fwd+adjoint (config 3)"),
     "c3l7": dict(n=16, layers=7, unique=4096, ham="xxz", grad=True,
                  label="16-qubit XXZ ring, HEA L=7, 4096 unique bitstrings, fwd+adjoint"),
+    "c3q": dict(n=16, layers=2, unique=4096, ham="kobe2", grad=True,
+                label="16-qubit QMHL term: data HEA L=2 + model HEA L=2 inverse, 136 KOBE-2 Z-shards, 4096 unique "
+                      "bitstrings, fwd+adjoint"),
     "c4": dict(n=20, layers=2, unique=8192, ham="tfim", grad=False,
                label="20-qubit TFIM ring, HEA L=2, 8192 unique bitstrings per GPU, forward (config 4 shard)"),
 }
@@ -50,10 +53,20 @@ def synth_workload(cfg, rank):
   qubits = cq.GridQubit.rect(1, n)
   circuit = arch.get_hardware_efficient_model_unitary(qubits, layers, "q")
   names = sorted(cq.circuit_symbols(circuit))
+  if cfg["ham"] == "kobe2":
+    # QMHL: <K_model> on data states = data circuit followed by the inverse model circuit, measured on
+    # the model energy's Z-string shards (qnn.py:69-72, hamiltonian.py:48-51)
+    model = arch.get_hardware_efficient_model_unitary(qubits, layers, "m")
+    mnames = sorted(cq.circuit_symbols(model))
+    circuit = circuit + model**-1
+    names = names + mnames
+    shards = models.KOBE(list(range(n)), 2).operator_shards(qubits)
+    terms, offs = cq.convert_to_tensor(shards).tables(qubits)
+  else:
+    ham = arch.xxz_ring(qubits) if cfg["ham"] == "xxz" else arch.tfim_ring(qubits)
+    terms, offs = cq.convert_to_tensor([ham]).tables(qubits)
   gates = cq.gate_table(circuit, qubits, names)
   phi = np.random.default_rng(11).uniform(-1, 1, len(names)).astype(np.float32)
-  ham = arch.xxz_ring(qubits) if cfg["ham"] == "xxz" else arch.tfim_ring(qubits)
-  terms, offs = cq.convert_to_tensor([ham]).tables(qubits)
   rng = np.random.default_rng(3 + rank)
   u = min(u, 1 << n)
   basis = rng.choice(1 << n, size=u, replace=False).astype(np.int64)
@@ -92,7 +105,7 @@ def oracle_ops(terms, offs, n):
 
 def algorithmic_bytes_per_bitstring(cfg):
   """F = L(n-1) fused <=2-qubit blocks; fwd (2F+1) S, fwd+adjoint (6F+2) S."""
-  f = cfg["layers"] * (cfg["n"] - 1)
+  f = cfg["layers"] * (cfg["n"] - 1) * (2 if cfg["ham"] == "kobe2" else 1)
   s = 8 * (1 << cfg["n"])
   return ((6 * f + 2) if cfg["grad"] else (2 * f + 1)) * s
 
@@ -160,7 +173,9 @@ def cpu_reference_rate(cfg, sample, threads=0, with_forward_op=True):
   gates, names, phi, (terms, offs), basis, counts = synth_workload(cfg, 0)
   prob = tfq_cpu.Problem(gates.astype(orc.GATE_DTYPE), cfg["n"], phi, oracle_ops(terms, offs, cfg["n"]), "tfq_fd")
   b = basis[:sample]
-  dg = (counts[:sample] / counts.sum()).astype(np.float32)[:, None]
+  n_ops = len(offs) - 1
+  w = np.random.default_rng(17).normal(0, 0.1, n_ops).astype(np.float32) if n_ops > 1 else np.ones(1, np.float32)
+  dg = ((counts[:sample] / counts.sum()).astype(np.float32)[:, None] * w[None, :]).astype(np.float32)
   t0 = time.perf_counter()
   if cfg["grad"]:
     if with_forward_op:
@@ -217,7 +232,8 @@ def run_gpu(args, cfg):
   gates, names, phi, (terms, offs), basis, counts = synth_workload(cfg, rank)
   n, u, grad = cfg["n"], len(basis), cfg["grad"]
   plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, grad, args.tile_qubits, args.reg_qubits)
-  n_ops, n_sym = 1, len(names)
+  n_ops, n_sym = len(offs) - 1, len(names)
+  op_weights = np.random.default_rng(17).normal(0, 0.1, n_ops).astype(np.float32) if n_ops > 1 else np.ones(1, np.float32)
 
   total_counts = torch.tensor([float(counts.sum())], dtype=torch.float64, device=dev)
   if world > 1:
@@ -225,7 +241,8 @@ def run_gpu(args, cfg):
   d_basis = torch.tensor(basis, device=dev)
   d_counts = torch.tensor(counts, device=dev)
   d_phi = torch.tensor(phi, device=dev)
-  dgrad_np = (counts / float(total_counts.item())).astype(np.float32)[:, None]
+  # upstream gradient of every expectation: count weight x (for shards) the energy parameter theta_j
+  dgrad_np = ((counts / float(total_counts.item())).astype(np.float32)[:, None] * op_weights[None, :]).astype(np.float32)
   d_dgrad = torch.tensor(dgrad_np, device=dev)
   packed = torch.zeros(n_ops + 1 + n_sym, dtype=torch.float64, device=dev)
 

@@ -632,6 +632,11 @@ class Compiler {
     // k = coeff * (-i)^{ny}; sign from parity(i & z) of the OUTPUT index i (derivation in DESIGN.md).
     const uint32_t tile_mask = hp_.n_eff <= hp_.T ? 0xffffffffu : ((1u << hp_.T) - 1u);
     const int mshift = hp_.T - hp_.K;  // the thread's m-th amplitude has tile-local index m << mshift | tid
+    // Many diagonal terms (e.g. the K Z-string shards of a modular Hamiltonian, hamiltonian.py:48-51):
+    // evaluate them all at once from one Walsh-Hadamard transform of |psi|^2 per tile.
+    int n_diag = 0;
+    for (const auto& t : o.terms) n_diag += t.xmask == 0;
+    const bool use_wht = n_diag >= kWhtMinTerms;
     for (int j = 0; j < o.n_ops(); ++j) {
       DevOpRange r;
       r.group_begin = (int32_t)hp_.groups.size();
@@ -641,6 +646,18 @@ class Compiler {
       size_t i = 0;
       while (i < idx.size()) {
         const uint32_t x = o.terms[idx[i]].xmask;
+        if (x == 0 && use_wht) {
+          while (i < idx.size() && o.terms[idx[i]].xmask == 0) {
+            DevDiagTerm d;
+            d.coeff = o.terms[idx[i]].coeff;
+            d.z = o.terms[idx[i]].zmask;
+            d.op = j;
+            d.pad = 0;
+            hp_.dterms.push_back(d);
+            ++i;
+          }
+          continue;
+        }
         DevTermGroup g;
         std::memset(&g, 0, sizeof(g));
         g.x = x;

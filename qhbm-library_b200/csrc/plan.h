@@ -47,6 +47,7 @@ struct HostPlan {
   std::vector<DevTerm> terms;
   std::vector<DevTermGroup> groups;
   std::vector<DevOpRange> opranges;
+  std::vector<DevDiagTerm> dterms;        // diagonal terms routed through the WHT path (may be empty)
 
   int tiles() const { return 1 << (n_eff - T); }
 };

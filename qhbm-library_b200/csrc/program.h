@@ -119,6 +119,14 @@ struct DevTermGroup {  // terms sharing one x-mask: H psi[i] += coefficient(i) *
 struct DevOpRange {
   int32_t group_begin, group_end;
 };
+// Diagonal (Z-string) term evaluated through a Walsh-Hadamard transform of |psi|^2 (many-shard case)
+struct DevDiagTerm {
+  float coeff;
+  uint32_t z;
+  int32_t op;
+  int32_t pad;
+};
+constexpr int kWhtMinTerms = 32;  // below this the direct evaluation is cheaper
 
 // Coefficient-preparation jobs (run on the device once per call, from the symbols).
 enum PrepKind : int32_t {

@@ -57,6 +57,7 @@ struct qhbm_plan {
   DevBuf<DevTerm> d_terms;
   DevBuf<DevTermGroup> d_groups;
   DevBuf<DevOpRange> d_opranges;
+  DevBuf<DevDiagTerm> d_dterms;
   DevBuf<float> d_coef;
   // workspace (grown on demand)
   DevBuf<float2> d_psi, d_lam;
@@ -85,7 +86,8 @@ void launch_sweep(const KernelArgs& ka, int n_states, int tiles, int threads, si
 void launch_any(const qhbm_plan* p, bool adj, const KernelArgs& ka, int n_states, cudaStream_t s) {
   const HostPlan& hp = p->hp;
   const int threads = 1 << (hp.T - hp.K);
-  const size_t smem = (size_t)(adj ? 2 : 1) * 8u * (1u << hp.T);
+  // psi tile (+ lambda tile for the adjoint kernel; forward-only WHT needs a float scratch tile)
+  const size_t smem = (size_t)(adj ? 2 : 1) * 8u * (1u << hp.T) + ((!adj && !hp.dterms.empty()) ? 4u * (1u << hp.T) : 0u);
   const int tiles = hp.tiles();
   if (hp.K == 4) {
     if (adj) launch_sweep<4, true>(ka, n_states, tiles, threads, smem, s);
@@ -127,6 +129,8 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
   ka.terms = p->d_terms.p;
   ka.groups = p->d_groups.p;
   ka.opranges = p->d_opranges.p;
+  ka.dterms = p->d_dterms.p;
+  ka.n_dterms = (int)hp.dterms.size();
   ka.n = hp.n_eff;
   ka.T = hp.T;
   ka.O = hp.O;
@@ -279,6 +283,7 @@ int qhbm_plan_create(const qhbm_circuit_t* c, const qhbm_ops_t* o, int32_t with_
       p->d_terms.upload(hp.terms);
       p->d_groups.upload(hp.groups);
       p->d_opranges.upload(hp.opranges);
+      p->d_dterms.upload(hp.dterms);
       p->d_coef.reserve(std::max(hp.ncoef, 4));
       int dev = 0;
       QHBM_CUDA(cudaGetDevice(&dev));

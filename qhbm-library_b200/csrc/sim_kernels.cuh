@@ -28,6 +28,8 @@ struct KernelArgs {
   const DevTerm* terms;
   const DevTermGroup* groups;
   const DevOpRange* opranges;
+  const DevDiagTerm* dterms;  // diagonal terms evaluated through the WHT path
+  int32_t n_dterms;
   float2* psi;            // [chunk][2^n] workspace (multi-tile only)
   float2* lam;            // [chunk][2^n] workspace (multi-tile adjoint only)
   const uint64_t* basis;  // [chunk]
@@ -555,6 +557,81 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
 // The thread's amplitudes are i_m = m * nthreads + tid; parity(i_m & z) splits into a per-thread
 // bit and a per-m bit that the host precomputed (DevTerm::mword).
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t wsw(uint32_t i) { return i ^ ((i >> 5) & 31u); }  // float scratch swizzle
+
+// In-place Walsh-Hadamard transform of w[2^T] (swizzled with wsw) by the whole CTA, K bits per pass.
+template <int K>
+__device__ __forceinline__ void wht_inplace(float* w, const int T, const uint32_t tid, const uint32_t nthr) {
+  for (int lo = 0; lo < T; lo += K) {
+    const int kb = (T - lo) < K ? (T - lo) : K;
+    const uint32_t ngroups = 1u << (T - kb);
+    for (uint32_t g = tid; g < ngroups; g += nthr) {
+      const uint32_t base = ((g >> lo) << (lo + kb)) | (g & ((1u << lo) - 1u));
+      float v[1 << K];
+#pragma unroll
+      for (int r = 0; r < (1 << K); ++r)
+        if (r < (1 << kb)) v[r] = w[wsw(base | ((uint32_t)r << lo))];
+#pragma unroll
+      for (int st = 0; st < K; ++st) {
+        if (st < kb) {
+#pragma unroll
+          for (int r = 0; r < (1 << K); ++r) {
+            if (!(r & (1 << st)) && (r | (1 << st)) < (1 << kb)) {
+              const float x = v[r], y = v[r | (1 << st)];
+              v[r] = x + y;
+              v[r | (1 << st)] = x - y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < (1 << K); ++r)
+        if (r < (1 << kb)) w[wsw(base | ((uint32_t)r << lo))] = v[r];
+    }
+    __syncthreads();
+  }
+}
+
+// All diagonal (Z-string) terms at once: W = WHT(|psi|^2) gives sum_i (-1)^{parity(i & z)} |psi_i|^2 for
+// every in-tile mask z; the adjoint factor D_i = sum_terms g c (-1)^{parity(i & z)} is the WHT of the
+// sparse vector V[z] = g c.  Out-of-tile bits of z only contribute a per-tile sign.
+template <int K, bool ADJ>
+__device__ __forceinline__ void wht_diag(const KernelArgs& ka, const float2* s_psi, float* W, float* V,
+                                         float (&dgall)[ADJ ? (1 << K) : 1], const uint32_t goff, const uint32_t u,
+                                         const bool want_lam) {
+  constexpr int R = 1 << K;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  const uint32_t ph_tid = swz(tid);
+  const uint32_t tmask = (1u << ka.T) - 1u;
+#pragma unroll
+  for (int m = 0; m < R; ++m) {
+    const float2 a = s_psi[ph_tid ^ ka.L.soff[m]];
+    const uint32_t i = wsw((uint32_t)m * nthr | tid);
+    W[i] = a.x * a.x + a.y * a.y;
+    if constexpr (ADJ) V[i] = 0.f;
+  }
+  __syncthreads();
+  wht_inplace<K>(W, ka.T, tid, nthr);
+  for (int t = (int)tid; t < ka.n_dterms; t += (int)nthr) {
+    const int4 d = __ldg(reinterpret_cast<const int4*>(ka.dterms + t));
+    const uint32_t z = (uint32_t)d.y;
+    float val = __int_as_float(d.x);
+    if (__popc(goff & z) & 1) val = -val;
+    const uint32_t zi = wsw(z & tmask);
+    atomicAdd(&ka.eacc[(size_t)u * ka.O + d.z], (double)(val * W[zi]));
+    if constexpr (ADJ) {
+      if (want_lam) atomicAdd(&V[zi], __ldg(&ka.dgrad[(size_t)u * ka.O + d.z]) * val);
+    }
+  }
+  __syncthreads();
+  if constexpr (ADJ) {
+    wht_inplace<K>(V, ka.T, tid, nthr);
+#pragma unroll
+    for (int m = 0; m < R; ++m) dgall[m] = V[wsw((uint32_t)m * nthr | tid)];
+    __syncthreads();  // V is about to be overwritten by the lambda tile
+  }
+}
+
 // Coefficients c(i_m) = k0 + sum_t k_t (-1)^{parity(i_m & z_t)} of one x-group for MC amplitudes.
 template <int MC, bool CPLX>
 __device__ __forceinline__ void group_coefficients(const KernelArgs& ka, float (&cr)[MC], float (&ci)[CPLX ? MC : 1],
@@ -620,6 +697,14 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
   const uint32_t gi_tid = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
   const uint32_t ph_tid = swz(tid);
   __syncthreads();
+  float dgall[ADJ ? R : 1];
+  const bool wht = ka.n_dterms > 0;
+  if (wht) {
+    // float scratch: the (not yet written) lambda tile, or the extra tile of the forward-only kernel
+    float* W = reinterpret_cast<float*>(s_psi + (1u << ka.T));
+    wht_diag<K, ADJ>(ka, s_psi, W, W + (1u << ka.T), dgall, goff, u, want_lam);
+  }
+#pragma unroll
   for (int m0 = 0; m0 < R; m0 += MC) {
     float2 a[MC];
     float p2[MC];
@@ -631,7 +716,7 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
       p2[m] = a[m].x * a[m].x + a[m].y * a[m].y;
       if constexpr (ADJ) {
         lam[m] = make_float2(0.f, 0.f);
-        dg[m] = 0.f;
+        dg[m] = wht ? dgall[m0 + m] : 0.f;  // m0 is a constant after unrolling the chunk loop
       }
     }
     for (int j = 0; j < ka.O; ++j) {

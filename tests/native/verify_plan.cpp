@@ -262,6 +262,15 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
     if (L.flags & LF_LOAD_LAM) for (int l = 0; l < tsz; ++l) tl[l] = c.lam[goff | scatter(l, L.runs, L.n_runs)];
     if (active) for (int p = L.pass_a_begin; p < L.pass_a_end; ++p) run_pass(c, L, hp.passes[p], tp, tl, goff, false);
     if (L.flags & LF_EXPECT) {
+      for (const DevDiagTerm& d : hp.dterms) {  // WHT-path terms: same mathematics, evaluated directly here
+        const double gj = (adjoint && c.dgrad) ? c.dgrad[d.op] : 0.0;
+        for (int l = 0; l < tsz; ++l) {
+          const uint32_t gi = goff | scatter(l, L.runs, L.n_runs);
+          const double sg = (__builtin_popcount(gi & d.z) & 1) ? -1.0 : 1.0;
+          c.eacc[d.op] += sg * d.coeff * std::norm(tp[l]);
+          tl[l] += gj * sg * d.coeff * tp[l];
+        }
+      }
       for (int j = 0; j < hp.O; ++j) {
         const double gj = (adjoint && c.dgrad) ? c.dgrad[j] : 0.0;
         double ej = 0;

@@ -80,6 +80,34 @@ def test_tfq_fd_mode(n, T, K):
   _compare(gates, n, 5, ops, rng, 3, T, K, mode="tfq_fd")
 
 
+@pytest.mark.parametrize("n,T,K,grad", [(12, 0, 0, True), (12, 0, 5, True), (14, 12, 4, True), (13, 9, 4, True),
+                                          (12, 0, 0, False), (15, 13, 5, False)])
+def test_many_diagonal_shards_walsh_hadamard_path(n, T, K, grad):
+  """>= 32 diagonal terms switch the expectation phase to the WHT evaluation: KOBE-2 Z-shards (the
+  modular-Hamiltonian observables of hamiltonian.py:48-51) mixed with TFIM / XXZ sums."""
+  rng = np.random.default_rng(40 + n)
+  gates, names = orc.hea_circuit(n, 2)
+  ops = orc.kobe_shards(n, 2) + [orc.tfim_ring(n), orc.xxz_ring(n), [(0.7, {}), (1.1, {0: "Z", n - 1: "Z", 3: "Z"})]]
+  phi = rng.uniform(-1, 1, len(names)).astype(np.float32)
+  basis = rng.choice(1 << n, 4, replace=False).astype(np.int64)
+  plan = _plan(gates, n, len(names), ops, grad, T, K)
+  d_phi, d_basis = torch.tensor(phi, device="cuda"), torch.tensor(basis, device="cuda")
+  scale = _scale(ops).max()
+  if not grad:
+    e = plan.forward(d_basis, d_phi).cpu().numpy()
+    e_ref = orc.expectations(gates, n, phi, basis, ops)
+    np.testing.assert_allclose(e, e_ref, rtol=RTOL, atol=RTOL * scale)
+    return
+  dg = rng.uniform(-1, 1, (len(basis), len(ops))).astype(np.float32)
+  e_ref, g_ref = orc.batch_expectation_and_gradient(gates, n, phi, basis, ops, dg)
+  e, g = plan.forward_adjoint(d_basis, d_phi, torch.tensor(dg, device="cuda"), grad_mode="exact")
+  np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=RTOL, atol=RTOL * scale)
+  gs = g_ref.sum(0)
+  np.testing.assert_allclose(g.cpu().numpy(), gs, rtol=RTOL, atol=RTOL * np.abs(g_ref).sum(0).max())
+  e2 = plan.forward(d_basis, d_phi).cpu().numpy()   # forward-only call on an adjoint plan
+  np.testing.assert_allclose(e2, e_ref, rtol=RTOL, atol=RTOL * scale)
+
+
 def test_config1_4q_tfim_bernoulli_samples():
   """BASELINE config 1: 4-qubit TFIM, 2-layer HEA, 1k Bernoulli samples -> unique -> weighted mean."""
   rng = np.random.default_rng(5)

@@ -54,6 +54,15 @@ def test_tfq_fd_mode(n, T, K):
   _check(gates, n, 5, ops, rng, T, K, mode="tfq_fd")
 
 
+@pytest.mark.parametrize("n,T,K", [(5, 0, 4), (11, 9, 4)])
+def test_many_diagonal_terms_table(n, T, K):
+  """>= 32 diagonal terms are routed to the WHT term table (checked here through the interpreter)."""
+  rng = np.random.default_rng(21)
+  gates, names = orc.hea_circuit(n, 1)
+  ops = orc.kobe_shards(n, 3)[:40] + [orc.tfim_ring(n), [(0.7, {}), (1.1, {0: "Z", n - 1: "Z"})]]
+  _check(gates, n, len(names), ops, rng, T, K)
+
+
 def test_empty_circuit_and_identity_terms():
   rng = np.random.default_rng(3)
   for n, T, K in [(3, 0, 4), (11, 9, 4)]:

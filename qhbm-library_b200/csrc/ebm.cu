@@ -404,6 +404,127 @@ __global__ void __launch_bounds__(kEnergyThreads) ebm_sweep_kernel(const __grid_
     if (threadIdx.x == 0) partial[blockIdx.x] = v;
   }
 }
+// ------------------------------------------------------------------ dense-stack sweep, register tiled
+// The dense stack over 2^n rows is a chain of small GEMMs ([rows x in] x [in x out], widths <= 64) that must
+// stay in fp32 FMA (energies feed exp()).  One CTA pushes tiles of kMlpRows rows through all layers with
+// the activations feature-major in shared memory ([feature][row]); each thread owns an 8-row x 4-output
+// micro-tile, so one LDS.128 of weights and two of activations feed 32 FMAs.
+constexpr int kMlpRows = 128;
+constexpr int kMlpThreads = 256;
+
+__device__ __forceinline__ float fast_tanh(float x) {
+  x = fminf(fmaxf(x, -9.f), 9.f);
+  const float e = __expf(2.f * x);
+  return __fdividef(e - 1.f, e + 1.f);
+}
+
+__global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid_constant__ EnergyArgs ea, uint64_t lo,
+                                                                    uint64_t hi, float* __restrict__ logits,
+                                                                    Stat* __restrict__ partial) {
+  extern __shared__ __align__(16) float s_f[];
+  __shared__ Stat s_st[kMlpThreads / 32];
+  const qhbm_energy_desc_t& d = ea.d;
+  stage_energy(ea, s_f);  // weights [in][out4] + bias[out4] per layer, as in the per-row kernel
+  int wfloats = 0;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const int out4 = (d.widths[l + 1] + 3) & ~3;
+    wfloats += d.widths[l] * out4 + out4;
+  }
+  float* bufA = s_f + ((wfloats + 3) & ~3);
+  float* bufB = bufA + kMaxWidth * kMlpRows;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // rows tx*8.., outputs ty*4..
+  const int n = d.n_bits;
+  const uint64_t rows = hi - lo;
+  const uint64_t ntiles = (rows + kMlpRows - 1) / kMlpRows;
+  Stat acc_st;
+  acc_st.m = 0.0; acc_st.s = 0.0; acc_st.t = 0.0;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t row0 = lo + tile * kMlpRows;
+    __syncthreads();  // previous tile fully consumed
+    for (int i = tid; i < n * kMlpRows; i += kMlpThreads) {
+      const int k = i / kMlpRows, r = i - k * kMlpRows;
+      bufA[i] = (float)(((row0 + r) >> (n - 1 - k)) & 1ull);
+    }
+    __syncthreads();
+    float* src = bufA;
+    float* dst = bufB;
+    int off = 0;
+    for (int l = 0; l + 1 < d.n_layers; ++l) {
+      const int in = d.widths[l], out = d.widths[l + 1];
+      const int out4 = (out + 3) & ~3;
+      const float* W = s_f + off;
+      const float* Bv = W + in * out4;
+      if (ty * 4 < out4) {
+        float acc[8][4];
+        const float4 b4 = *reinterpret_cast<const float4*>(Bv + ty * 4);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { acc[r][0] = b4.x; acc[r][1] = b4.y; acc[r][2] = b4.z; acc[r][3] = b4.w; }
+#pragma unroll 4
+        for (int k = 0; k < in; ++k) {
+          const float4 x0 = *reinterpret_cast<const float4*>(src + k * kMlpRows + tx * 8);
+          const float4 x1 = *reinterpret_cast<const float4*>(src + k * kMlpRows + tx * 8 + 4);
+          const float4 w = *reinterpret_cast<const float4*>(W + k * out4 + ty * 4);
+          const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            acc[r][0] = fmaf(xs[r], w.x, acc[r][0]);
+            acc[r][1] = fmaf(xs[r], w.y, acc[r][1]);
+            acc[r][2] = fmaf(xs[r], w.z, acc[r][2]);
+            acc[r][3] = fmaf(xs[r], w.w, acc[r][3]);
+          }
+        }
+        const int act = d.act[l];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            float y = acc[r][j];
+            if (act == 1) y = fast_tanh(y);
+            else if (act == 2) y = fmaxf(y, 0.f);
+            v[r] = y;
+          }
+          float* o = dst + (ty * 4 + j) * kMlpRows + tx * 8;
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+      off += in * out4 + out4;
+      __syncthreads();
+      float* t = src; src = dst; dst = t;
+    }
+    // last layer: one output per row
+    {
+      const int l = d.n_layers - 1;
+      const int in = d.widths[l];
+      const int out4 = (d.widths[l + 1] + 3) & ~3;
+      const float* W = s_f + off;
+      if (tid < kMlpRows && row0 + tid < hi) {
+        float e = W[in * out4];
+        for (int k = 0; k < in; ++k) e = fmaf(src[k * kMlpRows + tid], W[k * out4], e);
+        if (d.act[l] == 1) e = fast_tanh(e);
+        else if (d.act[l] == 2) e = fmaxf(e, 0.f);
+        const float lg = -e;
+        if (logits) logits[row0 + tid - lo] = lg;
+        Stat one;
+        one.m = (double)lg; one.s = 1.0; one.t = (double)lg;
+        acc_st = stat_merge(acc_st, one);
+      }
+    }
+  }
+  acc_st = stat_warp(acc_st);
+  if ((tid & 31) == 0) s_st[tid >> 5] = acc_st;
+  __syncthreads();
+  if (tid < 32) {
+    Stat v;
+    v.m = 0.0; v.s = 0.0; v.t = 0.0;
+    if (tid < kMlpThreads / 32) v = s_st[tid];
+    v = stat_warp(v);
+    if (tid == 0) partial[blockIdx.x] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) stat_final_kernel(const Stat* __restrict__ partial, int n, double* __restrict__ out) {
   __shared__ Stat s_st[8];
   Stat acc;
@@ -693,8 +814,16 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
       QHBM_CUDA(cudaMalloc(&g_sweep_partial, sizeof(Stat) * 148 * 8));
       g_sweep_partial_cap = 148 * 8;
     }
-    QHBM_CUDA(cudaFuncSetAttribute(ebm_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    ebm_sweep_kernel<<<blocks, kEnergyThreads, smem, s>>>(ea, lo, hi, d_logits, (Stat*)g_sweep_partial);
+    if (e->kind == QHBM_ENERGY_MLP && e->n_layers >= 2 && rows >= 4096) {
+      // register-tiled dense-stack kernel: weights + two [64][128] activation buffers in shared memory
+      const size_t msmem = ((smem + 15) & ~(size_t)15) + 2 * sizeof(float) * kMaxWidth * kMlpRows;
+      QHBM_CUDA(cudaFuncSetAttribute(ebm_mlp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+      blocks = (int)std::min<uint64_t>((rows + kMlpRows - 1) / kMlpRows, 148 * 2);
+      ebm_mlp_sweep_kernel<<<blocks, kMlpThreads, msmem, s>>>(ea, lo, hi, d_logits, (Stat*)g_sweep_partial);
+    } else {
+      QHBM_CUDA(cudaFuncSetAttribute(ebm_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      ebm_sweep_kernel<<<blocks, kEnergyThreads, smem, s>>>(ea, lo, hi, d_logits, (Stat*)g_sweep_partial);
+    }
     stat_final_kernel<<<1, 256, 0, s>>>((const Stat*)g_sweep_partial, blocks, d_stats);
     QHBM_CUDA(cudaGetLastError());
   });

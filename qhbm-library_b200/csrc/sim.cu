@@ -136,8 +136,6 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
   ka.O = hp.O;
   ka.P = hp.P;
   ka.phase_coef = hp.phase_coef;
-  ka.sync_ops = 0;
-  if (const char* e = std::getenv("QHBM_SYNC_OPS")) ka.sync_ops = std::atoi(e);
 }
 
 void run_prep(qhbm_plan* p, const float* d_symbols, int mode, cudaStream_t s) {

@@ -41,7 +41,6 @@ struct KernelArgs {
   int32_t grow0;          // accumulator row of this chunk's first state (per-state gradients)
   int32_t per_state;
   int32_t phase_coef;     // coef offset of the dropped global phase (debug state output), or -1
-  int32_t sync_ops;       // experiment: CTA barrier every sync_ops ops keeps the warps on the same code
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t x) {
@@ -377,40 +376,13 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   int oi = __ldg(&ps->op_begin);
   OpRec nxt;
   if (oi < op_end) nxt = load_op(ka.ops + oi);
-  int since_sync = 0;
   while (oi < op_end) {
     const OpRec op = nxt;
     const float* cf = ka.coef + op.coef;
-    if (ka.sync_ops > 0 && ++since_sync >= ka.sync_ops) {
-      since_sync = 0;
-      __syncthreads();
-    }
     int step = 1;
     if (op.type == OP_GD_BEGIN) step += op.aux0;
     if (oi + step < op_end) nxt = load_op(ka.ops + oi + step);  // prefetch the next descriptor
     switch (op.type) {
-      case OP_XROT: {
-        const float4 cs = ldg4(cf);  // (c, s, kappa, -)
-        dispatch_pos<K>(op.p0, [&](auto pc) {
-          constexpr int P = decltype(pc)::value;
-          if constexpr (BOTH) {
-            if (op.gslot >= 0) scratch[op.gslot * nthr + tid] = cs.z * im_bxa<K, P>(a, b);
-          }
-          xrot<K, P>(a, cs.x, cs.y);
-          if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
-        });
-      } break;
-      case OP_YROT: {
-        const float4 cs = ldg4(cf);
-        dispatch_pos<K>(op.p0, [&](auto pc) {
-          constexpr int P = decltype(pc)::value;
-          if constexpr (BOTH) {
-            if (op.gslot >= 0) scratch[op.gslot * nthr + tid] = cs.z * im_bya<K, P>(a, b);
-          }
-          yrot<K, P>(a, cs.x, cs.y);
-          if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
-        });
-      } break;
       case OP_XROTM: {
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
@@ -506,15 +478,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
       } break;
       default:
         if constexpr (BOTH) {
-          if (op.type == OP_GRAD_X || op.type == OP_GRAD_Y) {
-            const float kappa = __ldg(cf);
-            float v = 0.f;
-            const bool isx = op.type == OP_GRAD_X;
-            dispatch_pos<K>(op.p0, [&](auto pc) {
-              v = isx ? im_bxa<K, decltype(pc)::value>(a, b) : im_bya<K, decltype(pc)::value>(a, b);
-            });
-            scratch[op.gslot * nthr + tid] = kappa * v;
-          } else if (op.type == OP_GRAD_MAT1) {
+          if (op.type == OP_GRAD_MAT1) {
             const float4 m0 = ldg4(cf), m1 = ldg4(cf + 4);
             float v = 0.f;
             dispatch_pos<K>(op.p0, [&](auto pc) { v = grad_mat1<K, decltype(pc)::value>(a, b, m0, m1); });

@@ -166,6 +166,35 @@ def test_config3_full_size_properties():
   assert float(g0.abs().max()) < 2e-3 * 1e-2 * u
 
 
+def test_config4_20q_tfim_forward_sample_and_properties():
+  """BASELINE config 4: 20-qubit TFIM expectation (forward).  Oracle on two bitstrings; for a larger batch
+  the identity observable must give 1 and sharding the batch must not change any value."""
+  rng = np.random.default_rng(4)
+  n = 20
+  gates, names = orc.hea_circuit(n, 2)
+  ops = [orc.tfim_ring(n), [(1.0, {})]]
+  plan = _plan(gates, n, len(names), ops, grad=False)
+  assert plan.info["sweeps_fwd"] >= 2 and plan.info["tile_qubits"] == 13
+  phi = rng.uniform(-1, 1, len(names)).astype(np.float32)
+  d_phi = torch.tensor(phi, device="cuda")
+  basis = rng.choice(1 << n, 64, replace=False).astype(np.int64)
+  e = plan.forward(torch.tensor(basis, device="cuda"), d_phi).cpu().numpy()
+  e_ref = orc.expectations(gates, n, phi, basis[:2], ops)
+  np.testing.assert_allclose(e[:2], e_ref, rtol=RTOL, atol=RTOL * 2 * n)
+  np.testing.assert_allclose(e[:, 1], 1.0, atol=3e-6)
+  e_a = plan.forward(torch.tensor(basis[:23], device="cuda"), d_phi).cpu().numpy()
+  e_b = plan.forward(torch.tensor(basis[23:], device="cuda"), d_phi).cpu().numpy()
+  np.testing.assert_allclose(np.concatenate([e_a, e_b]), e, rtol=0, atol=1e-6)   # rows are independent
+
+
+def test_18q_adjoint_sample_against_oracle():
+  """Multi-tile adjoint with 64 tiles per state (n = 18, tile 2^12)."""
+  rng = np.random.default_rng(18)
+  n = 18
+  gates, names = orc.hea_circuit(n, 2)
+  _compare(gates, n, len(names), [orc.xxz_ring(n), orc.tfim_ring(n)], rng, 2, check_state=False)
+
+
 def test_trace_property_all_basis_states():
   """sum over ALL basis states of <x|U^dag H U|x> = Tr H = 0 for a traceless H (n=12, 4096 rows)."""
   n = 12

@@ -515,12 +515,6 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   }
 }
 
-// ---------------------------------------------------------------------------------
-// Expectation phase: E_j = Re <psi|H_j|psi>, and (adjoint) lambda = sum_j g_j H_j psi.
-// H psi[i] = sum_groups c_g(i) psi[i ^ x_g]; c_g(i) = k0 + sum_t k_t (-1)^{parity(i & z_t)}.
-// The thread's amplitudes are i_m = m * nthreads + tid; parity(i_m & z) splits into a per-thread
-// bit and a per-m bit that the host precomputed (DevTerm::mword).
-// ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t wsw(uint32_t i) { return i ^ ((i >> 5) & 31u); }  // float scratch swizzle
 
 // In-place Walsh-Hadamard transform of w[2^T] (swizzled with wsw) by the whole CTA, K bits per pass.

@@ -401,6 +401,11 @@ class Compiler {
           else m.p1 = r.gslot;
         }
       }
+      if (m.type == OP_XROTM && __builtin_popcount(mask) >= K - 1) {
+        m.type = OP_XROTF;
+        for (int P = 0; P < K; ++P)
+          if (!(mask & (1 << P))) add_job(PJ_ROT, m.coef + 4 * P, 0, 0, 0, 0, {});  // identity rotation
+      }
       out.push_back(m);
       i = j;
     }

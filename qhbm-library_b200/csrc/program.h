@@ -41,6 +41,8 @@ enum OpType : int32_t {
                   //     aux0 = mask of positions with a gradient; slot of position P: byte P of aux1
                   //     (P < 4) or p1 (P = 4)
   OP_YROTM,       // same for OP_YROT
+  OP_XROTF,       // OP_XROTM applied to ALL K positions without tests (inactive ones hold the identity
+                  //     rotation): no branches, no register reconciliation at merge points
   OP_GRAD_X,      // kappa * Im <lam| X_p0 |psi>; coef -> kappa   (two-level X-type gate)
   OP_GRAD_Y,      // kappa * Im <lam| Y_p0 |psi>; coef -> kappa
   OP_GD_BEGIN,    // starts a run of aux0 diagonal-gradient ops (they share conj(lam)*psi), sorted by kind:

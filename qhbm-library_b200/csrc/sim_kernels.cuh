@@ -399,6 +399,20 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
           }
         });
       } break;
+      case OP_XROTF: {
+        for_each_pos<K>([&](auto pc) {
+          constexpr int P = decltype(pc)::value;
+          const float4 cs = ldg4(cf + 4 * P);  // identity (1, 0, 0, -) at inactive positions
+          if constexpr (BOTH) {
+            if (op.aux0 & (1 << P)) {
+              const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1;
+              scratch[slot * nthr + tid] = cs.z * im_bxa<K, P>(a, b);
+            }
+          }
+          xrot<K, P>(a, cs.x, cs.y);
+          if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
+        });
+      } break;
       case OP_YROTM: {
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
@@ -941,6 +955,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __res
       }
     } break;
     case PJ_ROT: {
+      if (job.list_len == 0) {  // identity rotation filling an unused position of OP_XROTF
+        out[0] = 1.f; out[1] = 0.f; out[2] = 0.f; out[3] = 0.f;
+        break;
+      }
       double p[3];
       gate_param_values(gates[list[0]], symbols, p);
       const cd e = expipi(0.5 * p[0]);

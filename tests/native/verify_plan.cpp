@@ -49,6 +49,7 @@ static void prep(const HostPlan& hp, const float* symbols, int mode, std::vector
         for (int k = 0; k < 16; ++k) wr(job.out, k, m[k]);
       } break;
       case PJ_ROT: {
+        if (job.list_len == 0) { coef[job.out] = 1.f; coef[job.out + 1] = 0.f; coef[job.out + 2] = 0.f; break; }
         double pv[3];
         gate_param_values(hp.gates[list[0]], symbols, pv);
         const cd e = expipi(0.5 * pv[0]);
@@ -169,10 +170,10 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
             }
           }
         } break;
-        case OP_XROTM: case OP_YROTM: {
-          for (int P = 0; P < K; ++P) if (op.p0 & (1 << P)) {
+        case OP_XROTM: case OP_YROTM: case OP_XROTF: {
+          for (int P = 0; P < K; ++P) if ((op.p0 & (1 << P)) || op.type == OP_XROTF) {
             const double cc = c.coef[op.coef + 4 * P], ss = c.coef[op.coef + 4 * P + 1], kap = c.coef[op.coef + 4 * P + 2];
-            const bool isx = op.type == OP_XROTM;
+            const bool isx = op.type != OP_YROTM;
             const cplx m01 = isx ? cplx(0, -ss) : cplx(-ss, 0);
             const cplx m10 = isx ? cplx(0, -ss) : cplx(ss, 0);
             if (both && (op.aux0 & (1 << P))) {
@@ -357,7 +358,7 @@ extern "C" int verify_dump(const qhbm_gate_t* gates, int n_gates, int n, int P, 
     OpsIR o; o.n_qubits = n; o.offsets.assign(offs, offs + O + 1); o.terms.assign(terms, terms + offs[O]);
     HostPlan hp = compile_plan(c, o, with_grad != 0, T, K);
     static const char* names[] = {"NOP", "MAT1", "MAT2", "DCONST_TAB", "DCONST_PAIR", "DREG_TAB", "DAPPLY", "DCROSS",
-                                  "XROT", "YROT", "GRAD_MAT1", "GRAD_MAT2", "XROTM", "YROTM", "GRAD_X", "GRAD_Y", "GD_BEGIN",
+                                  "XROT", "YROT", "GRAD_MAT1", "GRAD_MAT2", "XROTM", "YROTM", "XROTF", "GRAD_X", "GRAD_Y", "GD_BEGIN",
                                   "GD_CONST", "GD_REG1", "GD_REG2", "GD_MIX"};
     printf("n_eff=%d T=%d K=%d ncoef=%d jobs=%zu terms=%zu groups=%zu\n", hp.n_eff, hp.T, hp.K, hp.ncoef, hp.jobs.size(),
            hp.terms.size(), hp.groups.size());
@@ -369,12 +370,12 @@ extern "C" int verify_dump(const qhbm_gate_t* gates, int n_gates, int n, int P, 
         int b = pass ? L.pass_b_begin : L.pass_a_begin, e = pass ? L.pass_b_end : L.pass_a_end;
         for (int p = b; p < e; ++p) {
           const DevPass& ps = hp.passes[p];
-          int hist[21] = {0};
+          int hist[22] = {0};
           for (int oi = ps.op_begin; oi < ps.op_end; ++oi) hist[hp.ops[oi].type]++;
           printf("   pass %d regbits=[", p);
           for (int j = 0; j < hp.K; ++j) printf("%d ", ps.regbit[j]);
           printf("] ngrad=%d ops:", ps.ngrad);
-          for (int t = 0; t < 21; ++t) if (hist[t]) printf(" %s=%d", names[t], hist[t]);
+          for (int t = 0; t < 22; ++t) if (hist[t]) printf(" %s=%d", names[t], hist[t]);
           printf("\n");
         }
       }

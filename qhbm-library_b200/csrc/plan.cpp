@@ -402,9 +402,20 @@ class Compiler {
         }
       }
       if (m.type == OP_XROTM && __builtin_popcount(mask) >= K - 1) {
+        // one job computes all K rotations of the op together (it needs the product of the cosines)
         m.type = OP_XROTF;
-        for (int P = 0; P < K; ++P)
-          if (!(mask & (1 << P))) add_job(PJ_ROT, m.coef + 4 * P, 0, 0, 0, 0, {});  // identity rotation
+        std::vector<int32_t> per_pos(K, -1);
+        int dag = 0;
+        for (auto& job : hp_.jobs) {
+          if (job.kind == PJ_ROT && job.out >= m.coef && job.out < m.coef + 4 * K) {
+            per_pos[(job.out - m.coef) / 4] = hp_.lists[job.list_off];
+            dag = job.a;
+            job.kind = PJ_NONE;
+          } else if (job.kind == PJ_KAPPA && job.out >= m.coef && job.out < m.coef + 4 * K) {
+            job.kind = PJ_NONE;
+          }
+        }
+        add_job(PJ_ROTF, m.coef, dag, m.aux0, 0, K, per_pos);
       }
       out.push_back(m);
       i = j;

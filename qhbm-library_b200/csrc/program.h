@@ -42,7 +42,9 @@ enum OpType : int32_t {
                   //     (P < 4) or p1 (P = 4)
   OP_YROTM,       // same for OP_YROT
   OP_XROTF,       // OP_XROTM applied to ALL K positions without tests (inactive ones hold the identity
-                  //     rotation): no branches, no register reconciliation at merge points
+                  //     rotation): no branches, no register reconciliation at merge points.  When the 4th
+                  //     coefficient of position 0 is non-zero, positions 0..K-2 hold tan(theta) and are applied
+                  //     as 1-FMA-per-component unnormalised rotations; position K-1 restores the scale
   OP_GRAD_X,      // kappa * Im <lam| X_p0 |psi>; coef -> kappa   (two-level X-type gate)
   OP_GRAD_Y,      // kappa * Im <lam| Y_p0 |psi>; coef -> kappa
   OP_GD_BEGIN,    // starts a run of aux0 diagonal-gradient ops (they share conj(lam)*psi), sorted by kind:
@@ -144,6 +146,11 @@ enum PrepKind : int32_t {
   PJ_KAPPA,      // kappa of a two-level X/Y-type gate (b: 0 = X, 1 = Y) for param c:
                  //   dG G^dagger = i(c0 I - kappa/2 A)  =>  d<H>/ds = kappa Im<lam|A|psi>
   PJ_PHASE,      // product of the dropped global phases e^{i pi t (g + 1/2)} of the list gates
+  PJ_ROTF,       // all K rotations of one OP_XROTF: list = gate per register position (-1: identity);
+                 //   a: dagger; b: mask of positions with a gradient.  Positions 0..K-2 are stored in the
+                 //   unnormalised form (tan, -, kappa', 1) and the last one absorbs the product of their
+                 //   cosines, unless some cosine is too small (then the plain (c, s, kappa, 0) form)
+  PJ_NONE,       // removed job
 };
 struct PrepJob {  // 32 bytes
   int32_t kind;

@@ -139,6 +139,19 @@ __device__ __forceinline__ void xrot(float2 (&a)[1 << K], const float c, const f
     a[r | (1 << P)].y = fmaf(-s, x0.x, c * x1.y);
   }
 }
+// unnormalised (I - i t X), t = tan: one FMA per component; the missing factor cos is restored later
+template <int K, int P>
+__device__ __forceinline__ void xrot_fast(float2 (&a)[1 << K], const float t) {
+#pragma unroll
+  for (int r = 0; r < (1 << K); ++r) {
+    if (r & (1 << P)) continue;
+    const float2 x0 = a[r], x1 = a[r | (1 << P)];
+    a[r].x = fmaf(t, x1.y, x0.x);
+    a[r].y = fmaf(-t, x1.x, x0.y);
+    a[r | (1 << P)].x = fmaf(t, x0.y, x1.x);
+    a[r | (1 << P)].y = fmaf(-t, x0.x, x1.y);
+  }
+}
 // (c I - i s Y) = [[c, -s], [s, c]]
 template <int K, int P>
 __device__ __forceinline__ void yrot(float2 (&a)[1 << K], const float c, const float s) {
@@ -400,17 +413,23 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
         });
       } break;
       case OP_XROTF: {
+        const bool fast = __ldg(cf + 3) != 0.f;
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
-          const float4 cs = ldg4(cf + 4 * P);  // identity (1, 0, 0, -) at inactive positions
+          const float4 cs = ldg4(cf + 4 * P);  // identity at inactive positions
           if constexpr (BOTH) {
             if (op.aux0 & (1 << P)) {
               const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1;
               scratch[slot * nthr + tid] = cs.z * im_bxa<K, P>(a, b);
             }
           }
-          xrot<K, P>(a, cs.x, cs.y);
-          if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
+          if (P < K - 1 && fast) {
+            xrot_fast<K, P>(a, cs.x);
+            if constexpr (BOTH) xrot_fast<K, P>(b, cs.x);
+          } else {
+            xrot<K, P>(a, cs.x, cs.y);
+            if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
+          }
         });
       } break;
       case OP_YROTM: {
@@ -964,6 +983,47 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __res
       const cd e = expipi(0.5 * p[0]);
       out[0] = (float)e.re;
       out[1] = (float)(job.a ? -e.im : e.im);
+    } break;
+    case PJ_ROTF: {
+      const int K = job.d;
+      double c[kMaxRegQubits], sn[kMaxRegQubits], kap[kMaxRegQubits];
+      bool fast = true;
+      for (int P = 0; P < K; ++P) {
+        c[P] = 1.0; sn[P] = 0.0; kap[P] = 0.0;
+        if (list[P] < 0) continue;
+        const qhbm_gate_t g = gates[list[P]];
+        double pv[3];
+        gate_param_values(g, symbols, pv);
+        const cd e = expipi(0.5 * pv[0]);
+        c[P] = e.re;
+        sn[P] = job.a ? -e.im : e.im;
+        if (job.b & (1 << P)) {
+          const int dim = gate_matrix_of(g, symbols, m);
+          gate_derivative(g, symbols, 0, mode, t);
+          dagger(m, dim, w);
+          matmul(t, w, dim, m);  // M = dG G^dagger = i c0 I - i (kappa/2) X
+          kap[P] = -2.0 * m[1].im;
+        }
+        if (P < K - 1 && fabs(c[P]) < 0.05) fast = false;
+      }
+      double scale = 1.0;  // product of the cosines of the unnormalised positions so far
+      for (int P = 0; P < K; ++P) {
+        if (fast && P < K - 1) {
+          out[4 * P + 0] = (float)(sn[P] / c[P]);
+          out[4 * P + 1] = 0.f;
+          out[4 * P + 2] = (float)(kap[P] * scale * scale);
+          scale *= c[P];
+        } else if (fast) {
+          out[4 * P + 0] = (float)(c[P] * scale);
+          out[4 * P + 1] = (float)(sn[P] * scale);
+          out[4 * P + 2] = (float)(kap[P] * scale * scale);
+        } else {
+          out[4 * P + 0] = (float)c[P];
+          out[4 * P + 1] = (float)sn[P];
+          out[4 * P + 2] = (float)kap[P];
+        }
+        out[4 * P + 3] = fast ? 1.f : 0.f;
+      }
     } break;
     case PJ_PHASE: {
       cd acc = mk(1, 0);

@@ -56,6 +56,37 @@ static void prep(const HostPlan& hp, const float* symbols, int mode, std::vector
         coef[job.out] = (float)e.re;
         coef[job.out + 1] = (float)(job.a ? -e.im : e.im);
       } break;
+      case PJ_NONE: break;
+      case PJ_ROTF: {
+        const int K = job.d;
+        double c[8], sn[8], kap[8];
+        bool fast = true;
+        for (int P = 0; P < K; ++P) {
+          c[P] = 1.0; sn[P] = 0.0; kap[P] = 0.0;
+          if (list[P] < 0) continue;
+          const qhbm_gate_t g = hp.gates[list[P]];
+          double pv[3];
+          gate_param_values(g, symbols, pv);
+          const cd e = expipi(0.5 * pv[0]);
+          c[P] = e.re; sn[P] = job.a ? -e.im : e.im;
+          if (job.b & (1 << P)) {
+            const int dim = gate_matrix_of(g, symbols, m);
+            gate_derivative(g, symbols, 0, mode, t);
+            dagger(m, dim, w);
+            matmul(t, w, dim, m);
+            kap[P] = -2.0 * m[1].im;
+          }
+          if (P < K - 1 && fabs(c[P]) < 0.05) fast = false;
+        }
+        double scale = 1.0;
+        for (int P = 0; P < K; ++P) {
+          float* o = &coef[job.out + 4 * P];
+          if (fast && P < K - 1) { o[0] = (float)(sn[P] / c[P]); o[1] = 0.f; o[2] = (float)(kap[P] * scale * scale); scale *= c[P]; }
+          else if (fast) { o[0] = (float)(c[P] * scale); o[1] = (float)(sn[P] * scale); o[2] = (float)(kap[P] * scale * scale); }
+          else { o[0] = (float)c[P]; o[1] = (float)sn[P]; o[2] = (float)kap[P]; }
+          o[3] = fast ? 1.f : 0.f;
+        }
+      } break;
       case PJ_PHASE: {
         cd acc = mk(1, 0);
         for (int i = 0; i < job.list_len; ++i) {
@@ -172,7 +203,9 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
         } break;
         case OP_XROTM: case OP_YROTM: case OP_XROTF: {
           for (int P = 0; P < K; ++P) if ((op.p0 & (1 << P)) || op.type == OP_XROTF) {
-            const double cc = c.coef[op.coef + 4 * P], ss = c.coef[op.coef + 4 * P + 1], kap = c.coef[op.coef + 4 * P + 2];
+            double cc = c.coef[op.coef + 4 * P], ss = c.coef[op.coef + 4 * P + 1];
+            const double kap = c.coef[op.coef + 4 * P + 2];
+            if (op.type == OP_XROTF && c.coef[op.coef + 3] != 0.f && P < K - 1) { ss = cc; cc = 1.0; }  // (I - i t X)
             const bool isx = op.type != OP_YROTM;
             const cplx m01 = isx ? cplx(0, -ss) : cplx(-ss, 0);
             const cplx m10 = isx ? cplx(0, -ss) : cplx(ss, 0);

@@ -187,6 +187,39 @@ def test_config4_20q_tfim_forward_sample_and_properties():
   np.testing.assert_allclose(np.concatenate([e_a, e_b]), e, rtol=0, atol=1e-6)   # rows are independent
 
 
+def test_24q_forward_is_schedule_independent():
+  """Size-independent check at n = 24 (128 MiB per state, 2048+ tiles): two different tilings of the
+  same circuit must agree, the identity observable must give 1, and <Z_0> must lie in [-1, 1]."""
+  rng = np.random.default_rng(24)
+  n = 24
+  gates, names = orc.hea_circuit(n, 2)
+  ops = [orc.tfim_ring(n), [(1.0, {})], [(1.0, {0: "Z"})]]
+  phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+  basis = torch.tensor(rng.choice(1 << n, 3, replace=False).astype(np.int64), device="cuda")
+  e1 = _plan(gates, n, len(names), ops, False, 13, 5).forward(basis, phi).cpu().numpy()
+  e2 = _plan(gates, n, len(names), ops, False, 12, 4).forward(basis, phi).cpu().numpy()
+  np.testing.assert_allclose(e1, e2, rtol=1e-5, atol=1e-5 * 2 * n)
+  np.testing.assert_allclose(e1[:, 1], 1.0, atol=5e-6)
+  assert np.all(np.abs(e1[:, 2]) <= 1.0 + 1e-5)
+
+
+def test_adjoint_is_schedule_independent_16q():
+  """Same for the gradient at n = 16: tile 2^12/K=4, 2^13/K=4 and 2^13/K=5 give the same numbers."""
+  rng = np.random.default_rng(16)
+  n = 16
+  gates, names = orc.hea_circuit(n, 3)
+  ops = [orc.xxz_ring(n)] + orc.kobe_shards(n, 2)[:3]
+  phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+  basis = torch.tensor(rng.choice(1 << n, 37, replace=False).astype(np.int64), device="cuda")
+  dg = torch.tensor(rng.uniform(-1, 1, (37, len(ops))).astype(np.float32), device="cuda")
+  outs = [_plan(gates, n, len(names), ops, True, T, K).forward_adjoint(basis, phi, dg) for T, K in
+          [(12, 4), (13, 4), (13, 5)]]
+  for e, g in outs[1:]:
+    np.testing.assert_allclose(e.cpu().numpy(), outs[0][0].cpu().numpy(), rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(g.cpu().numpy(), outs[0][1].cpu().numpy(), rtol=1e-5,
+                               atol=1e-5 * float(outs[0][1].abs().max()))
+
+
 def test_18q_adjoint_sample_against_oracle():
   """Multi-tile adjoint with 64 tiles per state (n = 18, tile 2^12)."""
   rng = np.random.default_rng(18)

@@ -292,6 +292,7 @@ class Compiler {
         ps.op_begin = (int)hp_.ops.size();
         ps.gsym_off = (int)hp_.gsym.size();
         ps.ngrad = 0;
+        ps.coef_begin = hp_.ncoef;
         std::vector<int> regpos(n, -1);  // state bit -> register position
         for (int j = 0; j < K; ++j) regpos[sw.tile_bits[ra.pos_bit[j]]] = j;
 
@@ -355,6 +356,7 @@ class Compiler {
         if (executed == 0) break;  // nothing runnable with this tile: next sweep
         merge_rotations(ps);
         ps.op_end = (int)hp_.ops.size();
+        ps.coef_end = hp_.ncoef;
         hp_.passes.push_back(ps);
         executed_in_sweep += executed;
         if (!have_nondiag && remaining > 0) {

@@ -21,6 +21,8 @@ constexpr int kMaxTileQubits = 14;
 constexpr int kMaxQubits = 30;
 constexpr int kConstGroupBits = 7;  // width of one "thread-constant" phase table
 constexpr int kMaxRuns = 16;
+constexpr int kStageOps = 96;      // ops of one pass staged in shared memory (else read from global)
+constexpr int kStageCoef = 1792;   // floats of one pass's coefficients staged in shared memory
 
 enum OpType : int32_t {
   OP_NOP = 0,
@@ -71,7 +73,7 @@ struct DevPass {  // 128 bytes
   int32_t sorted[kMaxRegQubits];     // the same bits in ascending order
   int32_t op_begin, op_end;
   int32_t ngrad, gsym_off;           // gradient slots of this pass -> symbols gsym[gsym_off..]
-  int32_t pad[2];
+  int32_t coef_begin, coef_end;      // float range of the coefficient buffer this pass reads
   uint16_t eoff[1 << kMaxRegQubits]; // swizzled smem offset of register amplitude r (XOR with the thread base)
 };
 

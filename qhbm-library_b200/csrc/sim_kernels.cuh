@@ -68,15 +68,17 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+// Program data (ops, coefficients) is read through generic pointers: it lives in shared memory when the
+// pass was staged there, in global memory otherwise.
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 ldg2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
 struct OpRec {
   int type, p0, p1, coef, gslot, aux0, aux1;
 };
 __device__ __forceinline__ OpRec load_op(const DevOp* op) {
-  const int4 a = __ldg(reinterpret_cast<const int4*>(op));
-  const int4 b = __ldg(reinterpret_cast<const int4*>(op) + 1);
+  const int4 a = *reinterpret_cast<const int4*>(op);
+  const int4 b = reinterpret_cast<const int4*>(op)[1];
   OpRec r;
   r.type = a.x; r.p0 = a.y; r.p1 = a.z; r.coef = a.w;
   r.gslot = b.x; r.aux0 = b.y; r.aux1 = b.z;
@@ -348,9 +350,27 @@ __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const f
 // ---------------------------------------------------------------------------------
 template <int K, bool BOTH>
 __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __restrict__ ps, float2* s_psi,
-                                         float2* s_lam, uint32_t goff, uint32_t u) {
+                                         float2* s_lam, float4* s_stage, uint32_t goff, uint32_t u) {
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  // Stage this pass's op descriptors and coefficients in shared memory: every later access is then an
+  // LDS broadcast with a short fixed latency instead of a dependent global load per op.
+  const int op_begin = __ldg(&ps->op_begin), op_end = __ldg(&ps->op_end);
+  const int cb = __ldg(&ps->coef_begin), ce = __ldg(&ps->coef_end);
+  const bool staged = (op_end - op_begin) <= kStageOps && (ce - cb) <= kStageCoef;
+  const DevOp* ops_base = ka.ops;       // indexed by absolute op number
+  const float* coef_base = ka.coef;     // indexed by absolute float offset
+  __syncthreads();  // the previous pass (its tile stores and its staged program) is finished everywhere
+  if (staged) {
+    float4* s_ops = s_stage;                       // kStageOps * 2 float4
+    float4* s_cf = s_stage + 2 * kStageOps;        // kStageCoef / 4 float4
+    const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
+    for (int i = (int)tid; i < 2 * (op_end - op_begin); i += (int)nthr) s_ops[i] = __ldg(g_ops + i);
+    const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);  // coefficient slots are 16-byte aligned
+    for (int i = (int)tid; i < (ce - cb + 3) / 4; i += (int)nthr) s_cf[i] = __ldg(g_cf + i);
+    ops_base = reinterpret_cast<const DevOp*>(s_ops) - op_begin;
+    coef_base = reinterpret_cast<const float*>(s_cf) - cb;
+  }
   uint32_t base = tid;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
@@ -371,7 +391,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
       eo[8 * i + 6] = w.w & 0xffffu; eo[8 * i + 7] = w.w >> 16;
     }
   }
-  __syncthreads();  // tile complete in smem
+  __syncthreads();  // staged program visible
 
   float2 a[R];
   float2 b[BOTH ? R : 1];
@@ -385,16 +405,15 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   if (ngrad > 0) __syncthreads();  // every amplitude is in registers: the tiles become scratch
 
   float2 F = make_float2(1.f, 0.f);
-  const int op_end = __ldg(&ps->op_end);
-  int oi = __ldg(&ps->op_begin);
+  int oi = op_begin;
   OpRec nxt;
-  if (oi < op_end) nxt = load_op(ka.ops + oi);
+  if (oi < op_end) nxt = load_op(ops_base + oi);
   while (oi < op_end) {
     const OpRec op = nxt;
-    const float* cf = ka.coef + op.coef;
+    const float* cf = coef_base + op.coef;
     int step = 1;
     if (op.type == OP_GD_BEGIN) step += op.aux0;
-    if (oi + step < op_end) nxt = load_op(ka.ops + oi + step);  // prefetch the next descriptor
+    if (oi + step < op_end) nxt = load_op(ops_base + oi + step);  // prefetch the next descriptor
     switch (op.type) {
       case OP_XROTM: {
         for_each_pos<K>([&](auto pc) {
@@ -413,7 +432,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
         });
       } break;
       case OP_XROTF: {
-        const bool fast = __ldg(cf + 3) != 0.f;
+        const bool fast = cf[3] != 0.f;
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
           const float4 cs = ldg4(cf + 4 * P);  // identity at inactive positions
@@ -520,7 +539,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
             const float g = op.p0 == 0 ? mat2<K, 0, true>(a, b, cf) : mat2<K, 2, true>(a, b, cf);
             scratch[op.gslot * nthr + tid] = g;
           } else if (op.type == OP_GD_BEGIN) {
-            grad_diag_run<K>(a, b, ka.ops + oi + 1, op.p0, op.p1, op.aux0, op.aux1 != 0, ka.coef, scratch, gbase, tid, nthr);
+            grad_diag_run<K>(a, b, ops_base + oi + 1, op.p0, op.p1, op.aux0, op.aux1 != 0, coef_base, scratch, gbase, tid, nthr);
           }
         }
         break;
@@ -813,6 +832,7 @@ constexpr int sweep_max_threads() { return ADJ ? (1 << (13 - K)) : 512; }
 template <int K, bool ADJ>
 __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(const __grid_constant__ KernelArgs ka) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float4 s_stage[2 * kStageOps + kStageCoef / 4];
   float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float2* s_lam = s_psi + (ADJ ? (1u << ka.T) : 0u);
   constexpr int R = 1 << K;
@@ -846,7 +866,7 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
 
   if (active) {
     for (int p = ka.L.pass_a_begin; p < ka.L.pass_a_end; ++p)
-      run_pass<K, false>(ka, ka.passes + p, s_psi, s_lam, goff, u);
+      run_pass<K, false>(ka, ka.passes + p, s_psi, s_lam, s_stage, goff, u);
   }
   if (flags & LF_WRITE_STATE) {
     __syncthreads();
@@ -856,7 +876,7 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
   if (flags & LF_EXPECT) expect_phase<K, ADJ>(ka, s_psi, s_lam, goff, u, psi_u);
   if constexpr (ADJ) {
     for (int p = ka.L.pass_b_begin; p < ka.L.pass_b_end; ++p)
-      run_pass<K, true>(ka, ka.passes + p, s_psi, s_lam, goff, u);
+      run_pass<K, true>(ka, ka.passes + p, s_psi, s_lam, s_stage, goff, u);
   }
   if (flags & (LF_STORE_PSI | LF_STORE_LAM)) {
     __syncthreads();

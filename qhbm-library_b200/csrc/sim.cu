@@ -131,6 +131,8 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
   ka.opranges = p->d_opranges.p;
   ka.dterms = p->d_dterms.p;
   ka.n_dterms = (int)hp.dterms.size();
+  ka.n_groups = (int)hp.groups.size();
+  ka.n_terms = (int)hp.terms.size();
   ka.n = hp.n_eff;
   ka.T = hp.T;
   ka.O = hp.O;

@@ -30,6 +30,7 @@ struct KernelArgs {
   const DevOpRange* opranges;
   const DevDiagTerm* dterms;  // diagonal terms evaluated through the WHT path
   int32_t n_dterms;
+  int32_t n_groups, n_terms;  // sizes of the group / term tables (for staging them in shared memory)
   float2* psi;            // [chunk][2^n] workspace (multi-tile only)
   float2* lam;            // [chunk][2^n] workspace (multi-tile adjoint only)
   const uint64_t* basis;  // [chunk]
@@ -644,7 +645,7 @@ __device__ __forceinline__ void wht_diag(const KernelArgs& ka, const float2* s_p
 
 // Coefficients c(i_m) = k0 + sum_t k_t (-1)^{parity(i_m & z_t)} of one x-group for MC amplitudes.
 template <int MC, bool CPLX>
-__device__ __forceinline__ void group_coefficients(const KernelArgs& ka, float (&cr)[MC], float (&ci)[CPLX ? MC : 1],
+__device__ __forceinline__ void group_coefficients(const DevTerm* terms, float (&cr)[MC], float (&ci)[CPLX ? MC : 1],
                                                    const uint32_t gi_tid, const int m0, const int t0, const int t1,
                                                    const float k0r, const float k0i) {
 #pragma unroll
@@ -653,7 +654,7 @@ __device__ __forceinline__ void group_coefficients(const KernelArgs& ka, float (
     if constexpr (CPLX) ci[m] = k0i;
   }
   for (int t = t0; t < t1; ++t) {
-    const float4 tv = __ldg(reinterpret_cast<const float4*>(ka.terms + t));
+    const float4 tv = *reinterpret_cast<const float4*>(terms + t);
     const uint32_t tp = (uint32_t)(__popc(gi_tid & __float_as_uint(tv.z)) & 1) << 31;
     const uint32_t word = __float_as_uint(tv.w) >> m0;
 #pragma unroll
@@ -668,13 +669,14 @@ __device__ __forceinline__ void group_coefficients(const KernelArgs& ka, float (
 // h[m] += c(i_m) * psi[i_m ^ x] for one off-diagonal x-group.  GLOBAL: the partner lives in
 // another tile (read through L2), else inside this tile's shared memory.
 template <int MC, bool CPLX, bool GLOBAL>
-__device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const float2* s_psi, const float2* __restrict__ psi_u,
-                                              float2 (&h)[MC], const uint32_t gi_tid, const uint32_t ph_tid,
+__device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const DevTerm* terms, const float2* s_psi,
+                                              const float2* __restrict__ psi_u, float2 (&h)[MC],
+                                              const uint32_t gi_tid, const uint32_t ph_tid,
                                               const uint32_t nthr, const int m0, const uint32_t x, const int xl,
                                               const int t0, const int t1, const float k0r, const float k0i) {
   float cr[MC];
   float ci[CPLX ? MC : 1];
-  group_coefficients<MC, CPLX>(ka, cr, ci, gi_tid, m0, t0, t1, k0r, k0i);
+  group_coefficients<MC, CPLX>(terms, cr, ci, gi_tid, m0, t0, t1, k0r, k0i);
   const uint32_t pxor = GLOBAL ? 0u : swz((uint32_t)xl);
 #pragma unroll
   for (int m = 0; m < MC; ++m) {
@@ -698,8 +700,8 @@ __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const float2
 // need |psi_i|^2 and a real per-amplitude factor D_i = sum_j g_j c_j(i), applied once at the end.
 // ---------------------------------------------------------------------------------
 template <int K, bool ADJ>
-__device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi, float2* s_lam, uint32_t goff,
-                                             uint32_t u, const float2* __restrict__ psi_u) {
+__device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi, float2* s_lam, float4* s_stage,
+                                             uint32_t goff, uint32_t u, const float2* __restrict__ psi_u) {
   constexpr int R = 1 << K;
   constexpr int MC = ADJ ? (R < 8 ? R : 8) : (R < 16 ? R : 16);  // amplitudes per thread handled at a time
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
@@ -707,6 +709,18 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
   const uint32_t gi_tid = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
   const uint32_t ph_tid = swz(tid);
   __syncthreads();
+  // stage the Pauli tables (group headers: 2 float4 each, terms: 1 float4 each) next to the program
+  const DevTermGroup* groups = ka.groups;
+  const DevTerm* terms = ka.terms;
+  if (2 * ka.n_groups + ka.n_terms <= 2 * kStageOps + kStageCoef / 4) {
+    const float4* gg = reinterpret_cast<const float4*>(ka.groups);
+    const float4* gt = reinterpret_cast<const float4*>(ka.terms);
+    for (int i = (int)tid; i < 2 * ka.n_groups; i += (int)nthr) s_stage[i] = __ldg(gg + i);
+    for (int i = (int)tid; i < ka.n_terms; i += (int)nthr) s_stage[2 * ka.n_groups + i] = __ldg(gt + i);
+    groups = reinterpret_cast<const DevTermGroup*>(s_stage);
+    terms = reinterpret_cast<const DevTerm*>(s_stage + 2 * ka.n_groups);
+    __syncthreads();
+  }
   float dgall[ADJ ? R : 1];
   const bool wht = ka.n_dterms > 0;
   if (wht) {
@@ -738,21 +752,21 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
       int g = __ldg(&ka.opranges[j].group_begin);
       int4 gh, gk;
       if (g < g_end) {
-        gh = __ldg(reinterpret_cast<const int4*>(ka.groups + g));
-        gk = __ldg(reinterpret_cast<const int4*>(ka.groups + g) + 1);
+        gh = reinterpret_cast<const int4*>(groups + g)[0];
+        gk = reinterpret_cast<const int4*>(groups + g)[1];
       }
       for (; g < g_end; ++g) {
         const int4 ch = gh, ck = gk;
         if (g + 1 < g_end) {  // prefetch the next group header
-          gh = __ldg(reinterpret_cast<const int4*>(ka.groups + g + 1));
-          gk = __ldg(reinterpret_cast<const int4*>(ka.groups + g + 1) + 1);
+          gh = reinterpret_cast<const int4*>(groups + g + 1)[0];
+          gk = reinterpret_cast<const int4*>(groups + g + 1)[1];
         }
         const uint32_t x = (uint32_t)ch.x;
         const int xl = ch.y;
         const float k0r = __int_as_float(ck.x), k0i = __int_as_float(ck.y);
         if (x == 0) {
           float cr[MC], ci[1];
-          group_coefficients<MC, false>(ka, cr, ci, gi_tid, m0, ch.z, ch.w, k0r, 0.f);
+          group_coefficients<MC, false>(terms, cr, ci, gi_tid, m0, ch.z, ch.w, k0r, 0.f);
 #pragma unroll
           for (int m = 0; m < MC; ++m) {
             ej = fmaf(cr[m], p2[m], ej);
@@ -766,11 +780,11 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
           for (int m = 0; m < MC; ++m) h[m] = make_float2(0.f, 0.f);
         }
         if (ck.z == 0) {
-          if (xl >= 0) group_offdiag<MC, false, false>(ka, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
-          else group_offdiag<MC, false, true>(ka, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          if (xl >= 0) group_offdiag<MC, false, false>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          else group_offdiag<MC, false, true>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
         } else {
-          if (xl >= 0) group_offdiag<MC, true, false>(ka, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
-          else group_offdiag<MC, true, true>(ka, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          if (xl >= 0) group_offdiag<MC, true, false>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          else group_offdiag<MC, true, true>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
         }
       }
       if (offdiag) {
@@ -873,7 +887,7 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
     const float2 phase = ka.phase_coef >= 0 ? ldg2(ka.coef + ka.phase_coef) : one;
     store_tile<K>(s_psi, ka.state_out + ((size_t)u << ka.n), goff, ka, phase);
   }
-  if (flags & LF_EXPECT) expect_phase<K, ADJ>(ka, s_psi, s_lam, goff, u, psi_u);
+  if (flags & LF_EXPECT) expect_phase<K, ADJ>(ka, s_psi, s_lam, s_stage, goff, u, psi_u);
   if constexpr (ADJ) {
     for (int p = ka.L.pass_b_begin; p < ka.L.pass_b_end; ++p)
       run_pass<K, true>(ka, ka.passes + p, s_psi, s_lam, s_stage, goff, u);

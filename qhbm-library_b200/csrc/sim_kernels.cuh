@@ -657,11 +657,13 @@ __device__ __forceinline__ void group_coefficients(const DevTerm* terms, float (
     const float4 tv = *reinterpret_cast<const float4*>(terms + t);
     const uint32_t tp = (uint32_t)(__popc(gi_tid & __float_as_uint(tv.z)) & 1) << 31;
     const uint32_t word = __float_as_uint(tv.w) >> m0;
+    // thread parity folded into k once per term; the per-amplitude bit then only selects +k or -k
+    const float kx = __uint_as_float(__float_as_uint(tv.x) ^ tp), ky = __uint_as_float(__float_as_uint(tv.y) ^ tp);
 #pragma unroll
     for (int m = 0; m < MC; ++m) {
-      const uint32_t sgn = tp ^ ((word >> m) << 31);
-      cr[m] += __uint_as_float(__float_as_uint(tv.x) ^ sgn);
-      if constexpr (CPLX) ci[m] += __uint_as_float(__float_as_uint(tv.y) ^ sgn);
+      const bool neg = (word >> m) & 1u;
+      cr[m] += neg ? -kx : kx;
+      if constexpr (CPLX) ci[m] += neg ? -ky : ky;
     }
   }
 }

@@ -22,8 +22,7 @@ class _ExpectationOp(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, symbol_values, basis_idx, holder):
-    plan = holder.plan
-    vals = plan.forward(basis_idx, symbol_values.detach().contiguous().float())
+    vals = holder.forward_plan.forward(basis_idx, symbol_values.detach().contiguous().float())
     ctx.holder = holder
     ctx.save_for_backward(symbol_values, basis_idx)
     return vals
@@ -41,9 +40,19 @@ class _ExpectationOp(torch.autograd.Function):
 
 
 class _PlanHolder:
+  """The adjoint plan, plus a forward-only plan (wider register blocking, no lambda tile) compiled
+  lazily for the forward pass of autograd."""
 
-  def __init__(self, plan, grad_mode):
+  def __init__(self, plan, grad_mode, make_forward_plan):
     self.plan, self.grad_mode = plan, grad_mode
+    self._make_forward_plan = make_forward_plan
+    self._forward_plan = None
+
+  @property
+  def forward_plan(self):
+    if self._forward_plan is None:
+      self._forward_plan = self._make_forward_plan()
+    return self._forward_plan
 
 
 class QuantumInference(torch.nn.Module, abc.ABC):
@@ -106,9 +115,10 @@ class AnalyticQuantumInference(QuantumInference):
     hit = self._plans.get(key)
     if hit is None:
       terms, offsets = ops_tensor.tables(circuit.qubits)
-      plan = engine.ExpectationPlan(circuit.gate_table(), len(circuit.qubits), len(circuit.symbol_names), terms,
-                                    offsets, True, self._tile_qubits, self._reg_qubits)
-      hit = (circuit, ops_tensor, _PlanHolder(plan, self.grad_mode))  # keep the keys alive
+      args = (circuit.gate_table(), len(circuit.qubits), len(circuit.symbol_names), terms, offsets)
+      plan = engine.ExpectationPlan(*args, True, self._tile_qubits, self._reg_qubits)
+      make_fwd = lambda: engine.ExpectationPlan(*args, False, 0, 0)
+      hit = (circuit, ops_tensor, _PlanHolder(plan, self.grad_mode, make_fwd))  # keep the keys alive
       self._plans[key] = hit
     hit[2].grad_mode = self.grad_mode
     return hit[2]

@@ -134,6 +134,28 @@ int qhbm_expectation_host(qhbm_plan_t* p, const uint64_t* h_basis_idx, int64_t n
                           const float* h_symbols, const float* h_dgrad, float* h_out,
                           float* h_grad_out, int32_t grad_mode, void* stream);
 
+/* Replaces: tfq.layers.State / tfq.layers.Unitary as used by qnn_utils.py:23-33 (the unitary is the
+ * batch of final states of all 2^n basis inputs) and the simulation half of tfq.layers.Sample
+ * (qnn.py:166, 283-289).
+ *   d_states_out  complex64[U, 2^n] interleaved (re, im), row u = U|basis_u>, index big-endian */
+int qhbm_final_states(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_states,
+                      const float* d_symbols, float* d_states_out, void* stream);
+
+/* Replaces: the measurement half of tfq.layers.Sample (qnn.py:262-292 `_sample`).
+ *   d_states   complex64[U, 2^n] as written by qhbm_final_states
+ *   d_offsets  i64[U+1]  shots of state u are d_out[d_offsets[u] .. d_offsets[u+1])
+ *   d_out      u64[total_samples]  measured basis index (qubit k <-> bit n-1-k)
+ * Philox4x32-10 counter = global shot index: a fixed seed repeats exactly. */
+int qhbm_sample_states(const float* d_states, int64_t n_states, int32_t n_qubits,
+                       const int64_t* d_offsets, int64_t total_samples, uint64_t seed0,
+                       uint64_t seed1, uint64_t* d_out, void* stream);
+
+/* Replaces: the shot noise of tfq.layers.SampledExpectation (qnn.py:255-260), which measures each
+ * Pauli term with its own `shots` repetitions: d_out[i] = (2 Binomial(shots, (1+d_exact[i])/2)
+ * - shots) / shots, drawn exactly (geometric gaps / BTRS rejection). */
+int qhbm_binomial_shots(const float* d_exact, int64_t n, int64_t shots, uint64_t seed0,
+                        uint64_t seed1, float* d_out, void* stream);
+
 /* Debug / parity: final state of one bitstring, complex64[2^n] interleaved. */
 int qhbm_debug_state(qhbm_plan_t* p, uint64_t basis_idx, const float* d_symbols,
                      float* d_state_out, void* stream);

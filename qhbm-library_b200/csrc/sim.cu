@@ -212,6 +212,53 @@ void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const flo
   }
 }
 
+// Final states U|basis_u> as dense complex64 [U, 2^n] rows (global phase restored): the forward
+// sweeps without the expectation phase, then one write-out launch per chunk.
+void run_states(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const float* d_symbols, float2* d_out,
+                cudaStream_t s) {
+  const HostPlan& hp = p->hp;
+  if (U < 0) throw std::runtime_error("n_states must be >= 0");
+  if (U == 0) return;
+  const bool multi = hp.tiles() > 1;
+  const bool padded = hp.n_eff != hp.n;  // small circuits are simulated with idle high qubits
+  const size_t dim_eff = (size_t)1 << hp.n_eff, dim = (size_t)1 << hp.n;
+  int64_t chunk = multi ? p->chunk : (int64_t)1 << 16;
+  if (padded) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, ((int64_t)1 << 28) >> hp.n_eff));
+  chunk = std::min<int64_t>(chunk, U);
+  p->d_eacc.reserve(std::max(hp.O, 1));
+  if (multi) p->d_psi.reserve((size_t)chunk << hp.n_eff);
+  if (padded || (multi && hp.grad)) p->d_lam.reserve((size_t)chunk << hp.n_eff);  // never both
+  run_prep(p, d_symbols, QHBM_GRAD_EXACT, s);
+  KernelArgs ka;
+  fill_common(p, ka);
+  ka.eacc = p->d_eacc.p;
+  ka.psi = multi ? p->d_psi.p : nullptr;
+  ka.lam = (multi && hp.grad) ? p->d_lam.p : nullptr;
+  for (int64_t u0 = 0; u0 < U; u0 += chunk) {
+    const int c = (int)std::min<int64_t>(chunk, U - u0);
+    ka.basis = d_basis + u0;
+    ka.state_out = padded ? p->d_lam.p : d_out + (size_t)u0 * dim;
+    for (int li = 0; li < hp.n_fwd_launches; ++li) {
+      ka.L = hp.launches[li];
+      ka.L.pass_b_begin = ka.L.pass_b_end = 0;
+      ka.L.flags &= ~(uint32_t)(LF_EXPECT | LF_STORE_LAM);
+      if (!multi) ka.L.flags |= LF_WRITE_STATE;
+      launch_any(p, hp.grad, ka, c, s);
+    }
+    if (multi) {
+      // one more launch: load the stored state and write it out with the dropped global phase
+      ka.L = hp.launches[hp.n_fwd_launches];  // the expectation launch has the contiguous tile map
+      ka.L.pass_a_begin = ka.L.pass_a_end = ka.L.pass_b_begin = ka.L.pass_b_end = 0;
+      ka.L.flags = LF_LOAD_PSI | LF_WRITE_STATE;
+      launch_any(p, hp.grad, ka, c, s);
+    }
+    if (padded)
+      QHBM_CUDA(cudaMemcpy2DAsync(d_out + (size_t)u0 * dim, dim * sizeof(float2), p->d_lam.p,
+                                  dim_eff * sizeof(float2), dim * sizeof(float2), (size_t)c,
+                                  cudaMemcpyDeviceToDevice, s));
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -364,44 +411,25 @@ int qhbm_expectation_host(qhbm_plan_t* p, const uint64_t* h_basis_idx, int64_t n
   });
 }
 
+int qhbm_final_states(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_states, const float* d_symbols,
+                      float* d_states_out, void* stream) {
+  return guarded([&] {
+    if (!p) throw std::runtime_error("null plan");
+    std::lock_guard<std::mutex> lk(p->mu);
+    run_states(p, d_basis_idx, n_states, d_symbols, reinterpret_cast<float2*>(d_states_out), (cudaStream_t)stream);
+  });
+}
+
 int qhbm_debug_state(qhbm_plan_t* p, uint64_t basis_idx, const float* d_symbols, float* d_state_out,
                      void* stream) {
   return guarded([&] {
     if (!p) throw std::runtime_error("null plan");
     std::lock_guard<std::mutex> lk(p->mu);
     cudaStream_t s = (cudaStream_t)stream;
-    const HostPlan& hp = p->hp;
-    const bool multi = hp.tiles() > 1;
     p->d_basis.reserve(1);
     QHBM_CUDA(cudaMemcpyAsync(p->d_basis.p, &basis_idx, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     QHBM_CUDA(cudaStreamSynchronize(s));
-    p->d_eacc.reserve(std::max(hp.O, 1));
-    if (multi) {
-      p->d_psi.reserve((size_t)1 << hp.n_eff);
-      if (hp.grad) p->d_lam.reserve((size_t)1 << hp.n_eff);
-    }
-    run_prep(p, d_symbols, QHBM_GRAD_EXACT, s);
-    KernelArgs ka;
-    fill_common(p, ka);
-    ka.basis = p->d_basis.p;
-    ka.eacc = p->d_eacc.p;
-    ka.psi = multi ? p->d_psi.p : nullptr;
-    ka.lam = (multi && hp.grad) ? p->d_lam.p : nullptr;
-    ka.state_out = reinterpret_cast<float2*>(d_state_out);
-    for (int li = 0; li < hp.n_fwd_launches; ++li) {
-      ka.L = hp.launches[li];
-      ka.L.pass_b_begin = ka.L.pass_b_end = 0;
-      ka.L.flags &= ~(uint32_t)(LF_EXPECT | LF_STORE_LAM);
-      if (!multi) ka.L.flags |= LF_WRITE_STATE;
-      launch_any(p, hp.grad, ka, 1, s);
-    }
-    if (multi) {
-      // one more launch: load the stored state and write it out with the dropped global phase
-      ka.L = hp.launches[hp.n_fwd_launches];  // the expectation launch has the contiguous tile map
-      ka.L.pass_a_begin = ka.L.pass_a_end = ka.L.pass_b_begin = ka.L.pass_b_end = 0;
-      ka.L.flags = LF_LOAD_PSI | LF_WRITE_STATE;
-      launch_any(p, hp.grad, ka, 1, s);
-    }
+    run_states(p, p->d_basis.p, 1, d_symbols, reinterpret_cast<float2*>(d_state_out), s);
   });
 }
 

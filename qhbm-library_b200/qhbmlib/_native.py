@@ -56,6 +56,9 @@ SIGNATURES = {
     "qhbm_expectation_adjoint": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, _I32, _VP]),
     "qhbm_expectation_host": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, _VP]),
     "qhbm_debug_state": (ctypes.c_int, [_VP, _U64, _VP, _VP, _VP]),
+    "qhbm_final_states": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP]),
+    "qhbm_sample_states": (ctypes.c_int, [_VP, _I64, _I32, _VP, _I64, _U64, _U64, _VP, _VP]),
+    "qhbm_binomial_shots": (ctypes.c_int, [_VP, _I64, _I64, _U64, _U64, _VP, _VP]),
     "qhbm_pack_bits": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP]),
     "qhbm_unpack_bits": (ctypes.c_int, [_VP, _I64, _I32, _VP, _VP, _VP]),
     "qhbm_unique_workspace_bytes": (_I64, [_I64]),

@@ -135,10 +135,49 @@ class ExpectationPlan:
   def state(self, basis_index, symbols):
     """complex64[2^n] final state U|basis> (debug / parity)."""
     symbols = _require_cuda(symbols, "symbols", torch.float32)
-    out = torch.zeros((1 << self.n_eff, 2), dtype=torch.float32, device=symbols.device)
+    out = torch.zeros((1 << self.n_qubits, 2), dtype=torch.float32, device=symbols.device)
     nat.check(nat.lib().qhbm_debug_state(self._plan, ctypes.c_uint64(int(basis_index)), nat.ptr(symbols),
                                          nat.ptr(out), _stream()))
-    return torch.view_as_complex(out)[:1 << self.n_qubits]
+    return torch.view_as_complex(out)
+
+  def final_states(self, basis_idx, symbols):
+    """complex64[U, 2^n]: row u = U|basis_u>, big-endian amplitudes (tfq.layers.State)."""
+    basis_idx = self._basis(basis_idx)
+    symbols = _require_cuda(symbols, "symbols", torch.float32)
+    u = basis_idx.shape[0]
+    out = torch.zeros((u, 1 << self.n_qubits, 2), dtype=torch.float32, device=basis_idx.device)
+    nat.check(nat.lib().qhbm_final_states(self._plan, nat.ptr(basis_idx), u, nat.ptr(symbols), nat.ptr(out),
+                                          _stream()))
+    return torch.view_as_complex(out)
+
+
+def sample_states(states, counts, seed):
+  """Measurement shots of many states.  states complex64[U, 2^n]; counts int[U] shots per state.
+  Returns (int64[sum counts] basis indices grouped by state, int64[U+1] offsets)."""
+  states = _require_cuda(states, "states", torch.complex64)
+  u, dim = states.shape
+  n = int(dim).bit_length() - 1
+  if (1 << n) != dim:
+    raise ValueError("states must have 2^n columns")
+  counts = counts.to(device=states.device, dtype=torch.int64)
+  offsets = torch.zeros(u + 1, dtype=torch.int64, device=states.device)
+  offsets[1:] = torch.cumsum(counts, 0)
+  total = int(offsets[-1].item())
+  out = torch.empty(total, dtype=torch.int64, device=states.device)
+  flat = torch.view_as_real(states)
+  nat.check(nat.lib().qhbm_sample_states(nat.ptr(flat), u, n, nat.ptr(offsets), total, int(seed[0]), int(seed[1]),
+                                         nat.ptr(out), _stream()))
+  return out, offsets
+
+
+def binomial_shots(exact, shots, seed):
+  """Shot-noise estimate of +-1 valued measurements with exact means `exact` (any shape):
+  (2 Binomial(shots, (1 + exact) / 2) - shots) / shots, element-wise."""
+  exact = _require_cuda(exact, "exact", torch.float32)
+  out = torch.empty_like(exact)
+  nat.check(nat.lib().qhbm_binomial_shots(nat.ptr(exact), exact.numel(), int(shots), int(seed[0]), int(seed[1]),
+                                          nat.ptr(out), _stream()))
+  return out
 
 
 def _shift_array(shifts):

@@ -6,9 +6,13 @@ with the adjoint-gradient kernels wired into torch autograd (the reference wires
 differentiator into TF autodiff, qnn.py:87-139).
 """
 import abc
+import math
+import os
 
+import numpy as np
 import torch
 
+from qhbmlib import _native as nat
 from qhbmlib import circuits as cq
 from qhbmlib import engine
 from qhbmlib import utils
@@ -140,3 +144,260 @@ class AnalyticQuantumInference(QuantumInference):
       values = values.to(circuits.basis_idx.device)
     expectations = _ExpectationOp.apply(values, circuits.basis_idx, holder)
     return post_process(expectations)
+
+
+# ------------------------------------------------------------------------------------------------
+# Shot-based inference (reference qnn.py:142-292)
+
+# gates whose exponent generator has exactly two distinct eigenvalues (gap 1): the two-term
+# parameter-shift rule  d f/d t = (pi/2) [f(t + 1/2) - f(t - 1/2)]  holds for the exponent t
+_TWO_EIGENVALUE_GATES = (1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12)  # X Y Z H CZ CNOT SWAP XX YY ZZ PhasedX (exponent)
+
+
+class _Occurrences:
+  """Gate table in which every shiftable symbolic exponent is its own symbol.
+
+  TFQ's ParameterShift differentiator shifts each gate occurrence of a symbol separately
+  (`get_gradient_circuits`, used at reference qnn.py:192-195).  Here the table keeps the original
+  symbols at [0, P) and appends one symbol per shiftable occurrence whose value is the gate's
+  whole exponent scalar * phi[sym] + const; shifting occurrence g is adding +-1/2 to entry P + g."""
+
+  def __init__(self, gates, n_symbols):
+    self.n_symbols = int(n_symbols)
+    table = np.array(gates, dtype=nat.GATE_DTYPE, copy=True)
+    sym, scalar, const, blocked = [], [], [], []
+    for i in range(len(table)):
+      for k in range(int(table[i]["nparams"])):
+        s = int(table[i]["sym"][k])
+        if s < 0:
+          continue
+        if k == 0 and int(table[i]["type"]) in _TWO_EIGENVALUE_GATES:
+          sym.append(s)
+          scalar.append(float(table[i]["scalar"][k]))
+          const.append(float(table[i]["cnst"][k]))
+          table[i]["sym"][k] = self.n_symbols + len(sym) - 1
+          table[i]["scalar"][k] = 1.0
+          table[i]["cnst"][k] = 0.0
+        else:
+          blocked.append(s)
+    self.table = table
+    self.sym = torch.tensor(sym, dtype=torch.int64)
+    self.scalar = torch.tensor(scalar, dtype=torch.float32)
+    self.const = torch.tensor(const, dtype=torch.float32)
+    self.blocked = sorted(set(blocked))
+    self.total_symbols = self.n_symbols + len(sym)
+
+  def values(self, symbol_values):
+    """phi [P] -> [P + G] values of the occurrence table."""
+    dev = symbol_values.device
+    phi = symbol_values.detach().float()
+    occ = self.scalar.to(dev) * phi[self.sym.to(dev)] + self.const.to(dev)
+    return torch.cat([phi, occ]).contiguous()
+
+
+class _ParameterShiftOp(torch.autograd.Function):
+  """Zero in the forward pass; in the backward pass the parameter-shift estimate of
+  d estimator / d symbol_values contracted with the upstream gradient, every shifted circuit
+  measured with fresh shots (reference qnn.py:188-228)."""
+
+  @staticmethod
+  def forward(ctx, symbol_values, occ, estimator, shape):
+    ctx.occ, ctx.estimator = occ, estimator
+    ctx.save_for_backward(symbol_values)
+    return torch.zeros(shape, dtype=torch.float32, device=symbol_values.device)
+
+  @staticmethod
+  def backward(ctx, grad_out):
+    (symbol_values,) = ctx.saved_tensors
+    occ = ctx.occ
+    if occ.blocked:
+      raise NotImplementedError(
+          "parameter-shift gradients need two-eigenvalue gates; decompose the gates carrying symbol index "
+          f"{occ.blocked} (ISwapPow / FSim / PhasedISwapPow / phase exponents) first")
+    grad = torch.zeros_like(symbol_values, dtype=torch.float32)
+    base = occ.values(symbol_values)
+    with torch.no_grad():
+      for g in range(len(occ.sym)):
+        shifted = base.clone()
+        shifted[occ.n_symbols + g] += 0.5
+        plus = ctx.estimator(shifted)
+        shifted[occ.n_symbols + g] -= 1.0
+        minus = ctx.estimator(shifted)
+        weight = 0.5 * math.pi * float(occ.scalar[g])
+        grad[int(occ.sym[g])] += weight * torch.sum(grad_out * (plus - minus))
+    return grad.to(symbol_values.dtype), None, None, None
+
+
+class RaggedBitstrings:
+  """Rows of int8 bitstrings grouped by source state (stands in for the tf.RaggedTensor returned
+  by the reference `_sample`): `ragged[i]` is int8 [counts[i], num_qubits]."""
+
+  def __init__(self, flat_values, row_splits):
+    self.flat_values = flat_values
+    self.row_splits = row_splits
+    self._splits = row_splits.tolist()
+
+  def __len__(self):
+    return len(self._splits) - 1
+
+  def __getitem__(self, i):
+    return self.flat_values[self._splits[i]:self._splits[i + 1]]
+
+  def row_lengths(self):
+    return self.row_splits[1:] - self.row_splits[:-1]
+
+
+class SampledQuantumInference(QuantumInference):
+  """Expectation values estimated from measurement shots, differentiated by parameter shift.
+
+  Stands where the reference drives `tfq.layers.Sample`, `tfq.layers.SampledExpectation` and
+  `tfq.differentiators.ParameterShift` (qnn.py:142-292).  Final states come from the same sweep
+  kernels as the analytic path; shots are drawn on the GPU (`qhbm_sample_states`), and Pauli-term
+  estimates are exact binomial draws around the simulated term expectation (`qhbm_binomial_shots`),
+  which is the distribution of the mean of `expectation_samples` independent +-1 outcomes."""
+
+  _STATE_BUDGET = 1 << 27  # amplitudes per chunk of final states (1 GiB of complex64)
+
+  def __init__(self, input_circuit, expectation_samples, name=None, initial_seed=None):
+    super().__init__(input_circuit, name)
+    self._expectation_samples = int(expectation_samples)
+    if initial_seed is None:
+      initial_seed = int.from_bytes(os.urandom(8), "little")
+    self._seed_state = int(initial_seed) & ((1 << 64) - 1)
+    self._plans = {}
+
+  def _next_seed(self):
+    """A fresh (seed0, seed1) per measurement (splitmix64 stream)."""
+    out = []
+    for _ in range(2):
+      self._seed_state = (self._seed_state + 0x9E3779B97F4A7C15) & ((1 << 64) - 1)
+      z = self._seed_state
+      z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & ((1 << 64) - 1)
+      z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & ((1 << 64) - 1)
+      out.append(z ^ (z >> 31))
+    return tuple(out)
+
+  # ------------------------------------------------------------------ plans
+  def _compiled(self, circuit, key_obj, term_ops):
+    """(occurrence table, plan) for `circuit`; the plan measures `term_ops` (an OperatorTensor with
+    one Pauli string per entry) or, when None, is used for final states only."""
+    key = (id(circuit), id(key_obj))
+    hit = self._plans.get(key)
+    if hit is None:
+      occ = _Occurrences(circuit.gate_table(), len(circuit.symbol_names))
+      qubits = circuit.qubits
+      if term_ops is None:
+        term_ops = cq.convert_to_tensor([cq.PauliSum.from_pauli_strings(cq.Z(qubits[0]))])
+      terms, offsets = term_ops.tables(qubits)
+      plan = engine.ExpectationPlan(occ.table, len(qubits), occ.total_symbols, terms, offsets, False)
+      hit = (circuit, key_obj, occ, plan)
+      self._plans[key] = hit
+    return hit[2], hit[3]
+
+  @staticmethod
+  def _split_terms(ops, qubits):
+    """Observables [O] -> (one unit-coefficient OperatorTensor entry per non-identity Pauli string,
+    mixing matrix f32[T, O], identity offsets f32[O])."""
+    strings, rows, offsets = [], [], [0.0] * len(ops)
+    for j, pauli_sum in enumerate(ops.pauli_sums):
+      for t in pauli_sum.terms:
+        if abs(t.coefficient.imag) > 1e-12 * max(1.0, abs(t.coefficient)):
+          raise ValueError("PauliSum coefficients must be real (Hermitian observables)")
+        if not t.paulis:
+          offsets[j] += t.coefficient.real
+          continue
+        strings.append(cq.PauliSum.from_pauli_strings(cq.PauliString(1.0, dict(t.paulis))))
+        rows.append((len(strings) - 1, j, t.coefficient.real))
+    mix = torch.zeros((max(len(strings), 1), len(ops)), dtype=torch.float32)
+    for t, j, c in rows:
+      mix[t, j] = c
+    if not strings:  # only identity terms: measure a dummy Z with zero weight
+      strings.append(cq.PauliSum.from_pauli_strings(cq.Z(qubits[0])))
+    return cq.convert_to_tensor(strings), mix, torch.tensor(offsets, dtype=torch.float32)
+
+  # ------------------------------------------------------------------ estimators
+  def _pauli_estimator(self, circuits, ops):
+    key = (id(circuits.circuit), id(ops))
+    cache = self.__dict__.setdefault("_split_cache", {})
+    if key not in cache:
+      cache[key] = (ops,) + self._split_terms(ops, circuits.circuit.qubits)
+    _, term_ops, mix, offsets = cache[key]
+    occ, plan = self._compiled(circuits.circuit, ops, term_ops)
+    basis_idx = circuits.basis_idx
+    dev = basis_idx.device
+    mix_d, offsets_d = mix.to(dev), offsets.to(dev)
+
+    def estimate(values):
+      exact_terms = plan.forward(basis_idx, values)
+      noisy = engine.binomial_shots(exact_terms, self._expectation_samples, self._next_seed())
+      return noisy @ mix_d + offsets_d
+
+    return occ, estimate
+
+  def _final_state_chunks(self, plan, basis_idx, values):
+    n = plan.n_qubits
+    step = max(1, self._STATE_BUDGET >> n)
+    for lo in range(0, basis_idx.shape[0], step):
+      yield lo, plan.final_states(basis_idx[lo:lo + step].contiguous(), values)
+
+  def _bitstring_estimator(self, circuits, observables):
+    occ, plan = self._compiled(circuits.circuit, observables, None)
+    basis_idx = circuits.basis_idx
+    n = plan.n_qubits
+    shots = self._expectation_samples
+    shifts = utils._natural_shifts(n)
+
+    def estimate(values):
+      """mean_k E(x_k) over `shots` measured bitstrings of every state; E is evaluated once per
+      distinct (state, bitstring) pair and differentiable w.r.t. the energy's variables."""
+      pieces = []
+      for lo, states in self._final_state_chunks(plan, basis_idx, values):
+        u = states.shape[0]
+        counts = torch.full((u,), shots, dtype=torch.int64, device=states.device)
+        keys, _ = engine.sample_states(states, counts, self._next_seed())
+        owner = torch.arange(u, dtype=torch.int64, device=states.device).repeat_interleave(shots)
+        uniq, _, cnt = engine.unique_with_counts((owner << n) | keys)
+        energies = observables.energy(engine.unpack_bits(uniq & ((1 << n) - 1), n, shifts)).float()
+        weighted = energies * (cnt.to(torch.float32) / float(shots))
+        pieces.append(torch.zeros(u, dtype=torch.float32, device=states.device).index_add(0, uniq >> n, weighted))
+      return torch.cat(pieces).unsqueeze(1)
+
+    return occ, estimate
+
+  def _expectation(self, circuits, symbol_names, symbol_values, observables):
+    del symbol_names
+    if isinstance(observables, cq.OperatorTensor):
+      occ, estimate = self._pauli_estimator(circuits, observables)
+      post_process = lambda x: x
+    elif isinstance(observables, hamiltonian_lib.Hamiltonian) and isinstance(observables.energy,
+                                                                          energy_lib.PauliMixin):
+      occ, estimate = self._pauli_estimator(circuits, observables.operator_shards)
+      post_process = lambda y: observables.energy.operator_expectation(y).unsqueeze(-1)
+    else:
+      occ, estimate = self._bitstring_estimator(circuits, observables)
+      post_process = lambda x: x
+    values = symbol_values if symbol_values.is_cuda else symbol_values.to(circuits.basis_idx.device)
+    forward_pass = estimate(occ.values(values))
+    if torch.is_grad_enabled() and values.requires_grad:
+      forward_pass = forward_pass + _ParameterShiftOp.apply(values, occ, estimate, tuple(forward_pass.shape))
+    return post_process(forward_pass)
+
+  def _sample(self, initial_states, counts):
+    """`ragged[i]` holds `counts[i]` bitstrings measured on circuit|initial_states[i]>
+    (reference qnn.py:262-292)."""
+    circuits = self.circuit(initial_states)
+    occ, plan = self._compiled(self.circuit, None, None)
+    values = self.circuit.symbol_values
+    if not values.is_cuda:
+      values = values.to(circuits.basis_idx.device)
+    values = occ.values(values)
+    n = plan.n_qubits
+    counts = counts.to(device=circuits.basis_idx.device, dtype=torch.int64)
+    pieces = []
+    for lo, states in self._final_state_chunks(plan, circuits.basis_idx, values):
+      keys, _ = engine.sample_states(states, counts[lo:lo + states.shape[0]], self._next_seed())
+      pieces.append(keys)
+    keys = torch.cat(pieces) if pieces else torch.zeros(0, dtype=torch.int64, device=counts.device)
+    splits = torch.zeros(counts.shape[0] + 1, dtype=torch.int64, device=counts.device)
+    splits[1:] = torch.cumsum(counts, 0)
+    return RaggedBitstrings(engine.unpack_bits(keys, n, utils._natural_shifts(n)), splits)

@@ -220,3 +220,51 @@ def test_qaia_structure():
   etas, thetas, gammas = qaia.value_layers_inputs[0]
   exp = torch.cat([etas.unsqueeze(1) * thetas.unsqueeze(0), gammas], 1).reshape(-1)
   np.testing.assert_allclose(qaia.symbol_values.detach(), exp.detach())
+
+
+# ---------------------------------------------------------------- shot-based inference: host logic
+def test_parameter_shift_occurrence_table():
+  """Every shiftable symbolic exponent becomes its own symbol whose value is scalar*phi+const;
+  three-eigenvalue gates and phase exponents are reported as blocked."""
+  import torch
+  from qhbmlib import circuits as cq
+  from qhbmlib.inference import qnn
+  q = cq.GridQubit.rect(1, 3)
+  a, b = cq.Symbol("a"), cq.Symbol("b")
+  circuit = cq.Circuit(cq.X(q[0])**(a * 2.0), cq.rx(0.3).on(q[1]), cq.CZ(q[0], q[1])**(b * -0.5 + 0.25),
+                       cq.Y(q[2])**a, cq.H(q[1])**0.5)
+  names = ["a", "b"]
+  table = cq.gate_table(circuit, q, names)
+  occ = qnn._Occurrences(table, 2)
+  assert occ.total_symbols == 5 and occ.blocked == []
+  assert occ.sym.tolist() == [0, 1, 0]
+  np.testing.assert_allclose(occ.scalar.numpy(), [2.0, -0.5, 1.0])
+  np.testing.assert_allclose(occ.const.numpy(), [0.0, 0.25, 0.0])
+  assert [int(r["sym"][0]) for r in occ.table] == [2, -1, 3, 4, -1]
+  assert all(float(r["scalar"][0]) == 1.0 and float(r["cnst"][0]) == 0.0 for r in occ.table[[0, 2, 3]])
+  assert int(table[0]["sym"][0]) == 0  # the circuit's own table is untouched
+  vals = occ.values(torch.tensor([0.3, -0.8]))
+  np.testing.assert_allclose(vals.numpy(), [0.3, -0.8, 0.6, 0.65, 0.3], rtol=1e-6)
+  blocked = cq.gate_table(cq.Circuit(cq.ISWAP(q[0], q[1])**b, cq.X(q[0])**a), q, names)
+  occ = qnn._Occurrences(blocked, 2)
+  assert occ.blocked == [1] and occ.sym.tolist() == [0]
+
+
+def test_sampled_split_terms():
+  """PauliSums -> unit Pauli strings + mixing matrix + identity offsets."""
+  from qhbmlib import circuits as cq
+  from qhbmlib.inference import qnn
+  q = cq.GridQubit.rect(1, 2)
+  ops = cq.convert_to_tensor([
+      cq.PauliSum.from_pauli_strings(2.0 * cq.X(q[0])) + cq.PauliSum.from_pauli_strings(-0.5 * cq.Z(q[0]) * cq.Z(q[1])) +
+      cq.PauliSum.from_pauli_strings(cq.PauliString(1.5, {})),
+      cq.PauliSum.from_pauli_strings(3.0 * cq.Y(q[1])),
+  ])
+  term_ops, mix, offsets = qnn.SampledQuantumInference._split_terms(ops, q)
+  assert len(term_ops) == 3
+  assert all(len(s.terms) == 1 and s.terms[0].coefficient == 1.0 for s in term_ops.pauli_sums)
+  np.testing.assert_allclose(mix.numpy(), [[2.0, 0.0], [-0.5, 0.0], [0.0, 3.0]])
+  np.testing.assert_allclose(offsets.numpy(), [1.5, 0.0])
+  only_identity = cq.convert_to_tensor([cq.PauliSum.from_pauli_strings(cq.PauliString(0.7, {}))])
+  term_ops, mix, offsets = qnn.SampledQuantumInference._split_terms(only_identity, q)
+  assert len(term_ops) == 1 and float(mix.abs().sum()) == 0.0 and offsets.tolist() == pytest.approx([0.7])

@@ -644,27 +644,41 @@ __device__ __forceinline__ void wht_diag(const KernelArgs& ka, const float2* s_p
 }
 
 // Coefficients c(i_m) = k0 + sum_t k_t (-1)^{parity(i_m & z_t)} of one x-group for MC amplitudes.
+// A term whose z-mask does not touch the bits that distinguish the thread's amplitudes has the same
+// sign for all of them (warp-uniform test on the host-built sign word): it is added to a scalar.
 template <int MC, bool CPLX>
 __device__ __forceinline__ void group_coefficients(const DevTerm* terms, float (&cr)[MC], float (&ci)[CPLX ? MC : 1],
                                                    const uint32_t gi_tid, const int m0, const int t0, const int t1,
                                                    const float k0r, const float k0i) {
+  constexpr uint32_t kAll = MC >= 32 ? 0xffffffffu : ((1u << MC) - 1u);
+  float c0r = k0r, c0i = k0i;
 #pragma unroll
   for (int m = 0; m < MC; ++m) {
-    cr[m] = k0r;
-    if constexpr (CPLX) ci[m] = k0i;
+    cr[m] = 0.f;
+    if constexpr (CPLX) ci[m] = 0.f;
   }
   for (int t = t0; t < t1; ++t) {
     const float4 tv = *reinterpret_cast<const float4*>(terms + t);
     const uint32_t tp = (uint32_t)(__popc(gi_tid & __float_as_uint(tv.z)) & 1) << 31;
-    const uint32_t word = __float_as_uint(tv.w) >> m0;
+    const uint32_t word = (__float_as_uint(tv.w) >> m0) & kAll;
     // thread parity folded into k once per term; the per-amplitude bit then only selects +k or -k
     const float kx = __uint_as_float(__float_as_uint(tv.x) ^ tp), ky = __uint_as_float(__float_as_uint(tv.y) ^ tp);
+    if (word == 0u || word == kAll) {
+      c0r += word ? -kx : kx;
+      if constexpr (CPLX) c0i += word ? -ky : ky;
+      continue;
+    }
 #pragma unroll
     for (int m = 0; m < MC; ++m) {
       const bool neg = (word >> m) & 1u;
       cr[m] += neg ? -kx : kx;
       if constexpr (CPLX) ci[m] += neg ? -ky : ky;
     }
+  }
+#pragma unroll
+  for (int m = 0; m < MC; ++m) {
+    cr[m] += c0r;
+    if constexpr (CPLX) ci[m] += c0i;
   }
 }
 

@@ -9,8 +9,10 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <utility>
 
 #include "gate_math.h"
 
@@ -655,6 +657,12 @@ class Compiler {
     int n_diag = 0;
     for (const auto& t : o.terms) n_diag += t.xmask == 0;
     const bool use_wht = n_diag >= kWhtMinTerms;
+    // A single observable whose strings flip at most two in-tile qubits runs as observable passes
+    // (OP_HX / OP_HD); everything else stays in the generic x-group tables below.
+    // Adjoint plans only: in the forward-only kernel (K = 5, 128-register cap) the 32 complex registers
+    // of an observable pass spill and the generic tables are faster (measured, profiles/).
+    const bool hpass_ok = hp_.grad && o.n_ops() == 1 && !use_wht && !no_hpass_;
+    std::vector<HCand> hcands;
     for (int j = 0; j < o.n_ops(); ++j) {
       DevOpRange r;
       r.group_begin = (int32_t)hp_.groups.size();
@@ -675,6 +683,25 @@ class Compiler {
             ++i;
           }
           continue;
+        }
+        if (hpass_ok && !(x & ~tile_mask) && __builtin_popcount(x) <= 2) {
+          bool real = true;
+          size_t e = i;
+          while (e < idx.size() && o.terms[idx[e]].xmask == x) {
+            real = real && !(__builtin_popcount(o.terms[idx[e]].xmask & o.terms[idx[e]].zmask) & 1);
+            ++e;
+          }
+          if (real) {
+            HCand hc;
+            hc.x = x;
+            for (; i < e; ++i) {
+              const qhbm_pauli_term_t& t = o.terms[idx[i]];
+              const int ny = __builtin_popcount(t.xmask & t.zmask) & 3;
+              hc.terms.push_back({ny == 0 ? t.coeff : -t.coeff, t.zmask});
+            }
+            hcands.push_back(hc);
+            continue;
+          }
         }
         DevTermGroup g;
         std::memset(&g, 0, sizeof(g));
@@ -702,6 +729,149 @@ class Compiler {
       r.group_end = (int32_t)hp_.groups.size();
       hp_.opranges.push_back(r);
     }
+    build_hpasses(hcands);
+  }
+
+  struct HCand {
+    uint32_t x = 0;                                  // state-index xor mask (0: diagonal terms)
+    std::vector<std::pair<float, uint32_t>> terms;   // (real coefficient incl. the Y phases, z-mask)
+  };
+
+  // Observable passes of the expectation launch (contiguous tile: tile-local bit = state bit).
+  // Off-diagonal candidates are packed greedily into register sets (chains of neighbouring pairs share
+  // qubits); every diagonal term goes to the pass whose registers cover most of its z-mask.  The part
+  // of a z-mask outside the registers becomes a per-thread sign (DevOp::aux0).
+  void build_hpasses(const std::vector<HCand>& cands) {
+    h_begin_ = h_end_ = (int)hp_.passes.size();
+    if (cands.empty()) return;
+    const int K = hp_.K, R = 1 << K, Tl = std::min(hp_.T, hp_.n_eff);
+    struct HP {
+      std::vector<int> regs;
+      std::vector<int> offdiag;
+    };
+    std::vector<HP> hps;
+    auto bits_of = [](uint32_t x) {
+      std::vector<int> b;
+      for (int i = 0; i < 32; ++i) if ((x >> i) & 1) b.push_back(i);
+      return b;
+    };
+    std::vector<int> pending;
+    for (size_t c = 0; c < cands.size(); ++c) if (cands[c].x != 0) pending.push_back((int)c);
+    while (!pending.empty()) {
+      HP p;
+      auto missing = [&](int c) {
+        int m = 0;
+        for (int b : bits_of(cands[c].x)) m += std::find(p.regs.begin(), p.regs.end(), b) == p.regs.end();
+        return m;
+      };
+      auto take = [&](size_t pi) {
+        const int c = pending[pi];
+        for (int b : bits_of(cands[c].x))
+          if (std::find(p.regs.begin(), p.regs.end(), b) == p.regs.end()) p.regs.push_back(b);
+        p.offdiag.push_back(c);
+        pending.erase(pending.begin() + (long)pi);
+      };
+      size_t seed = 0;
+      for (size_t pi = 0; pi < pending.size(); ++pi)
+        if (__builtin_popcount(cands[pending[pi]].x) == 2) { seed = pi; break; }
+      take(seed);
+      for (;;) {
+        // best = fewest new registers; among equals prefer one that shares a qubit with the set
+        int best = -1, best_missing = 99, best_shared = -1;
+        for (size_t pi = 0; pi < pending.size(); ++pi) {
+          const int m = missing(pending[pi]);
+          if ((int)p.regs.size() + m > K) continue;
+          const int shared = __builtin_popcount(cands[pending[pi]].x) - m;
+          if (m < best_missing || (m == best_missing && shared > best_shared)) {
+            best = (int)pi; best_missing = m; best_shared = shared;
+          }
+        }
+        if (best < 0) break;
+        take((size_t)best);
+      }
+      hps.push_back(p);
+    }
+    int diag = -1;
+    for (size_t c = 0; c < cands.size(); ++c) if (cands[c].x == 0) diag = (int)c;
+    if (hps.empty()) hps.push_back(HP());
+    for (HP& p : hps)  // pad the register set from the top of the tile
+      for (int b = Tl - 1; b >= 0 && (int)p.regs.size() < K; --b)
+        if (std::find(p.regs.begin(), p.regs.end(), b) == p.regs.end()) p.regs.push_back(b);
+    std::vector<std::vector<std::pair<float, uint32_t>>> diag_of(hps.size());
+    if (diag >= 0) {
+      for (const auto& t : cands[diag].terms) {
+        size_t best = 0;
+        int cover = -1;
+        for (size_t h = 0; h < hps.size(); ++h) {
+          uint32_t rm = 0;
+          for (int b : hps[h].regs) rm |= 1u << b;
+          const int cv = __builtin_popcount(t.second & rm);
+          if (cv > cover) { cover = cv; best = h; }
+        }
+        diag_of[best].push_back(t);
+      }
+    }
+    for (size_t h = 0; h < hps.size(); ++h) {
+      const HP& p = hps[h];
+      DevPass ps;
+      std::memset(&ps, 0, sizeof(ps));
+      for (int j = 0; j < K; ++j) ps.regbit[j] = p.regs[j];
+      {
+        std::vector<int> srt(p.regs.begin(), p.regs.end());
+        std::sort(srt.begin(), srt.end());
+        for (int j = 0; j < K; ++j) ps.sorted[j] = srt[j];
+      }
+      uint32_t regmask = 0;
+      std::vector<uint32_t> rbits(R, 0);
+      for (int j = 0; j < K; ++j) regmask |= 1u << p.regs[j];
+      for (int r = 0; r < (1 << kMaxRegQubits); ++r) {
+        uint32_t dep = 0;
+        for (int j = 0; j < K; ++j) if ((r >> j) & 1) dep |= 1u << ps.regbit[j];
+        if (r < R) rbits[r] = dep;
+        const uint32_t sw = (dep & ~15u) | ((dep ^ (dep >> 4) ^ (dep >> 8) ^ (dep >> 12)) & 15u);
+        ps.eoff[r] = r < R ? (uint16_t)sw : 0;
+      }
+      ps.op_begin = (int)hp_.ops.size();
+      ps.gsym_off = 0;
+      ps.ngrad = -1;
+      ps.coef_begin = hp_.ncoef;
+      // one table per (xor mask, out-of-register z part)
+      auto emit = [&](int type, int xr, const std::vector<std::pair<float, uint32_t>>& terms) {
+        std::vector<uint32_t> zouts;
+        for (const auto& t : terms) {
+          const uint32_t zo = t.second & ~regmask;
+          if (std::find(zouts.begin(), zouts.end(), zo) == zouts.end()) zouts.push_back(zo);
+        }
+        for (uint32_t zo : zouts) {
+          std::vector<int32_t> tab(R, 0);
+          for (int r = 0; r < R; ++r) {
+            float v = 0.f;
+            for (const auto& t : terms) {
+              if ((t.second & ~regmask) != zo) continue;
+              v += (__builtin_popcount(rbits[r] & t.second) & 1) ? -t.first : t.first;
+            }
+            std::memcpy(&tab[r], &v, sizeof(float));
+          }
+          DevOp op = make_op(type);
+          op.p0 = xr;
+          op.aux0 = (int32_t)zo;
+          op.aux1 = 0;
+          op.coef = alloc_coef(R);
+          add_job(PJ_CONST, op.coef, 0, 0, 0, 0, tab);
+          hp_.ops.push_back(op);
+        }
+      };
+      for (int c : p.offdiag) {
+        int xr = 0;
+        for (int j = 0; j < K; ++j) if ((cands[c].x >> p.regs[j]) & 1) xr |= 1 << j;
+        emit(OP_HX, xr, cands[c].terms);
+      }
+      if (!diag_of[h].empty()) emit(OP_HD, 0, diag_of[h]);
+      ps.op_end = (int)hp_.ops.size();
+      ps.coef_end = hp_.ncoef;
+      if (ps.op_end > ps.op_begin) hp_.passes.push_back(ps);
+    }
+    h_end_ = (int)hp_.passes.size();
   }
 
   void compile(const CircuitIR& c, const OpsIR& o) {
@@ -732,6 +902,8 @@ class Compiler {
       // whole state in one tile: one launch does forward, expectation and backward
       LaunchDesc L = blank();
       L.flags = LF_INIT_BASIS | LF_EXPECT;
+      L.pass_h_begin = h_begin_;
+      L.pass_h_end = h_end_;
       fill_runs(contiguous, L);
       L.pass_a_begin = fs.empty() ? 0 : fs.front().pass_begin;
       L.pass_a_end = fs.empty() ? 0 : fs.back().pass_end;
@@ -759,6 +931,8 @@ class Compiler {
     {
       LaunchDesc L = blank();
       L.flags = LF_LOAD_PSI | LF_EXPECT | (hp_.grad ? LF_STORE_LAM : 0);
+      L.pass_h_begin = h_begin_;
+      L.pass_h_end = h_end_;
       fill_runs(contiguous, L);
       hp_.launches.push_back(L);
     }
@@ -777,6 +951,8 @@ class Compiler {
  private:
   HostPlan& hp_;
   std::vector<int> phase_gates_;  // forward X/Y powers whose global phase was dropped
+  int h_begin_ = 0, h_end_ = 0;   // observable passes
+  bool no_hpass_ = std::getenv("QHBM_NO_HPASS") != nullptr;  // development switch: generic tables only
 };
 
 }  // namespace

@@ -57,6 +57,10 @@ enum OpType : int32_t {
   OP_GD_REG2,     // sel = 2*regbit(p0) + regbit(p1); coef -> 4 complex
   OP_GD_MIX,      // one register bit p0 and one constant bit aux0; coef -> 4 complex indexed
                   //     [2*bit(aux0) + regbit(p0)]
+  // observable passes (DevPass::ngrad == -1): h = H psi accumulated in the lambda registers
+  OP_HX,          // h[r] += s * tab[r] * psi[r ^ p0]: p0 = register xor mask with one or two bits set,
+                  //     coef -> 2^K real coefficients, s = (-1)^{parity(gbase & aux0)} (aux0 = 0: +1)
+  OP_HD,          // h[r] += s * tab[r] * psi[r]  (diagonal terms), same fields
 };
 
 struct DevOp {  // 32 bytes
@@ -72,7 +76,8 @@ struct DevPass {  // 128 bytes
   int32_t regbit[kMaxRegQubits];     // tile-local bit of register position j
   int32_t sorted[kMaxRegQubits];     // the same bits in ascending order
   int32_t op_begin, op_end;
-  int32_t ngrad, gsym_off;           // gradient slots of this pass -> symbols gsym[gsym_off..]
+  int32_t ngrad, gsym_off;           // gradient slots of this pass -> symbols gsym[gsym_off..];
+                                     // ngrad == -1 marks an observable pass (OP_HX / OP_HD only)
   int32_t coef_begin, coef_end;      // float range of the coefficient buffer this pass reads
   uint16_t eoff[1 << kMaxRegQubits]; // swizzled smem offset of register amplitude r (XOR with the thread base)
 };
@@ -101,7 +106,7 @@ struct LaunchDesc {
   BitRun runs[kMaxRuns];             // tile-local bits -> state bits
   BitRun oruns[kMaxRuns];            // tile-id bits -> state bits (the out-of-tile bits)
   uint32_t tile_mask;                // state-index bits covered by the tile
-  int32_t group_set;                 // which term-group table to use for LF_EXPECT
+  int32_t pass_h_begin, pass_h_end;  // observable passes run at the start of the expectation phase
   // the thread's m-th tile element is local index (m << (T-K)) | tid:
   uint32_t moff[1 << kMaxRegQubits]; // its state-index contribution scatter(m << (T-K))
   uint16_t soff[1 << kMaxRegQubits]; // its swizzled smem contribution swz(m << (T-K))
@@ -153,6 +158,7 @@ enum PrepKind : int32_t {
                  //   unnormalised form (tan, -, kappa', 1) and the last one absorbs the product of their
                  //   cosines, unless some cosine is too small (then the plain (c, s, kappa, 0) form)
   PJ_NONE,       // removed job
+  PJ_CONST,      // symbol-independent floats: the list holds their bit patterns
 };
 struct PrepJob {  // 32 bytes
   int32_t kind;

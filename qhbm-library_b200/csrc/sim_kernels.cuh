@@ -568,6 +568,115 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Observable pass: the Pauli strings whose X/Y part acts inside the pass's register qubits are applied
+// like gates -- the partner amplitude psi[i ^ x] is another register of the same thread and the sign
+// pattern over the register index is a host-built coefficient table.
+// BOTH = true (adjoint kernel): h = H psi accumulates in the lambda tile (unscaled; the expectation phase
+// finishes E and lambda from it).  BOTH = false: E is accumulated directly.  Single observable only.
+// ---------------------------------------------------------------------------------
+template <int K, int XR, bool BOTH>
+__device__ __forceinline__ void hx_apply(const float2 (&a)[1 << K], float2 (&b)[BOTH ? (1 << K) : 1],
+                                         const float* cf, const float sgn, float& e) {
+  constexpr int R = 1 << K;
+  float acc = 0.f;
+#pragma unroll
+  for (int r0 = 0; r0 < R; r0 += 4) {
+    const float4 t4 = ldg4(cf + r0);  // coefficients are read four at a time: no table in registers
+    const float tab[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + i, q = r ^ XR;
+      if constexpr (BOTH) {
+        const float t = sgn * tab[i];
+        b[r].x = fmaf(t, a[q].x, b[r].x);
+        b[r].y = fmaf(t, a[q].y, b[r].y);
+      } else {
+        acc = fmaf(tab[i], fmaf(a[r].x, a[q].x, a[r].y * a[q].y), acc);
+      }
+    }
+  }
+  if constexpr (!BOTH) e = fmaf(sgn, acc, e);
+}
+
+template <int K, bool BOTH>
+__device__ __forceinline__ void run_hpass(const KernelArgs& ka, const DevPass* __restrict__ ps, const float2* s_psi,
+                                          float2* s_lam, float4* s_stage, uint32_t goff, uint32_t u) {
+  constexpr int R = 1 << K;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  const int op_begin = __ldg(&ps->op_begin), op_end = __ldg(&ps->op_end);
+  const int cb = __ldg(&ps->coef_begin), ce = __ldg(&ps->coef_end);
+  const bool staged = (op_end - op_begin) <= kStageOps && (ce - cb) <= kStageCoef;
+  const DevOp* ops_base = ka.ops;
+  const float* coef_base = ka.coef;
+  __syncthreads();  // previous pass done (tile stores, staged program)
+  if (staged) {
+    float4* s_ops = s_stage;
+    float4* s_cf = s_stage + 2 * kStageOps;
+    const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
+    for (int i = (int)tid; i < 2 * (op_end - op_begin); i += (int)nthr) s_ops[i] = __ldg(g_ops + i);
+    const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);
+    for (int i = (int)tid; i < (ce - cb + 3) / 4; i += (int)nthr) s_cf[i] = __ldg(g_cf + i);
+    ops_base = reinterpret_cast<const DevOp*>(s_ops) - op_begin;
+    coef_base = reinterpret_cast<const float*>(s_cf) - cb;
+  }
+  uint32_t base = tid;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int sp = __ldg(&ps->sorted[j]);
+    base = ((base >> sp) << (sp + 1)) | (base & ((1u << sp) - 1u));
+  }
+  const uint32_t B = swz(base);
+  const uint32_t gbase = goff | scatter_bits(base, ka.L.runs, ka.L.n_runs);
+  uint32_t eo[R];
+  {
+    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
+#pragma unroll
+    for (int i = 0; i < R / 8; ++i) {
+      const uint4 w = __ldg(ep + i);
+      eo[8 * i + 0] = w.x & 0xffffu; eo[8 * i + 1] = w.x >> 16;
+      eo[8 * i + 2] = w.y & 0xffffu; eo[8 * i + 3] = w.y >> 16;
+      eo[8 * i + 4] = w.z & 0xffffu; eo[8 * i + 5] = w.z >> 16;
+      eo[8 * i + 6] = w.w & 0xffffu; eo[8 * i + 7] = w.w >> 16;
+    }
+  }
+  __syncthreads();  // staged program visible
+  float2 a[R];
+  float2 b[BOTH ? R : 1];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    a[r] = s_psi[B ^ eo[r]];
+    if constexpr (BOTH) b[r] = s_lam[B ^ eo[r]];
+  }
+  float e = 0.f;
+  for (int oi = op_begin; oi < op_end; ++oi) {
+    const OpRec op = load_op(ops_base + oi);
+    const float* cf = coef_base + op.coef;
+    const float sgn = (__popc(gbase & (uint32_t)op.aux0) & 1) ? -1.f : 1.f;
+    if (op.type == OP_HD) {
+      hx_apply<K, 0, BOTH>(a, b, cf, sgn, e);
+    } else {
+      // register xor masks with one or two bits set
+      for_each_pos<K>([&](auto ph) {
+        constexpr int PH = decltype(ph)::value;
+        for_each_pos<K>([&](auto pl) {
+          constexpr int PL = decltype(pl)::value;
+          if constexpr (PL <= PH) {
+            if (op.p0 == ((1 << PH) | (1 << PL))) hx_apply<K, (1 << PH) | (1 << PL), BOTH>(a, b, cf, sgn, e);
+          }
+        });
+      });
+    }
+  }
+  if constexpr (BOTH) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) s_lam[B ^ eo[r]] = b[r];
+  } else {
+    e = warp_sum(e);
+    if ((tid & 31) == 0) atomicAdd(&ka.eacc[(size_t)u * ka.O], (double)e);
+  }
+}
+
 __device__ __forceinline__ uint32_t wsw(uint32_t i) { return i ^ ((i >> 5) & 31u); }  // float scratch swizzle
 
 // In-place Walsh-Hadamard transform of w[2^T] (swizzled with wsw) by the whole CTA, K bits per pass.
@@ -717,7 +826,8 @@ __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const DevTer
 // ---------------------------------------------------------------------------------
 template <int K, bool ADJ>
 __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi, float2* s_lam, float4* s_stage,
-                                             uint32_t goff, uint32_t u, const float2* __restrict__ psi_u) {
+                                             uint32_t goff, uint32_t u, const float2* __restrict__ psi_u,
+                                             const bool hinit) {
   constexpr int R = 1 << K;
   constexpr int MC = ADJ ? (R < 8 ? R : 8) : (R < 16 ? R : 16);  // amplitudes per thread handled at a time
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
@@ -764,6 +874,13 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
       float ej = 0.f;
       float2 h[MC];
       bool offdiag = false;
+      if constexpr (ADJ) {
+        if (hinit) {  // the observable passes left their part of H psi in the lambda tile (single observable)
+          offdiag = true;
+#pragma unroll
+          for (int m = 0; m < MC; ++m) h[m] = s_lam[ph_tid ^ ka.L.soff[m0 + m]];
+        }
+      }
       const int g_end = __ldg(&ka.opranges[j].group_end);
       int g = __ldg(&ka.opranges[j].group_begin);
       int4 gh, gk;
@@ -903,7 +1020,19 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
     const float2 phase = ka.phase_coef >= 0 ? ldg2(ka.coef + ka.phase_coef) : one;
     store_tile<K>(s_psi, ka.state_out + ((size_t)u << ka.n), goff, ka, phase);
   }
-  if (flags & LF_EXPECT) expect_phase<K, ADJ>(ka, s_psi, s_lam, s_stage, goff, u, psi_u);
+  if (flags & LF_EXPECT) {
+    const bool hpasses = ka.L.pass_h_end > ka.L.pass_h_begin;
+    if (hpasses) {
+      if constexpr (ADJ) {
+        const uint32_t pz = swz(threadIdx.x);
+#pragma unroll
+        for (int m = 0; m < (1 << K); ++m) s_lam[pz ^ ka.L.soff[m]] = make_float2(0.f, 0.f);
+      }
+      for (int p = ka.L.pass_h_begin; p < ka.L.pass_h_end; ++p)
+        run_hpass<K, ADJ>(ka, ka.passes + p, s_psi, s_lam, s_stage, goff, u);
+    }
+    expect_phase<K, ADJ>(ka, s_psi, s_lam, s_stage, goff, u, psi_u, hpasses);
+  }
   if constexpr (ADJ) {
     for (int p = ka.L.pass_b_begin; p < ka.L.pass_b_end; ++p)
       run_pass<K, true>(ka, ka.passes + p, s_psi, s_lam, s_stage, goff, u);
@@ -938,6 +1067,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __res
   const int32_t* list = lists + job.list_off;
   float* out = coef + job.out;
   const int tid = threadIdx.x;
+  if (job.kind == PJ_CONST) {
+    for (int i = tid; i < job.list_len; i += kPrepThreads) out[i] = __int_as_float(list[i]);
+    return;
+  }
   if (job.kind == PJ_DTAB) {
     __shared__ cd s_diag[kPrepBatch][4];
     __shared__ int s_pos[kPrepBatch][2];

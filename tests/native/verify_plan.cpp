@@ -57,6 +57,9 @@ static void prep(const HostPlan& hp, const float* symbols, int mode, std::vector
         coef[job.out + 1] = (float)(job.a ? -e.im : e.im);
       } break;
       case PJ_NONE: break;
+      case PJ_CONST:
+        for (int i = 0; i < job.list_len; ++i) std::memcpy(&coef[job.out + i], &list[i], sizeof(float));
+        break;
       case PJ_ROTF: {
         const int K = job.d;
         double c[8], sn[8], kap[8];
@@ -277,6 +280,27 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
   for (int g = 0; g < ps.ngrad; ++g) c.gacc[hp.gsym[ps.gsym_off + g]] += gsum[g];
 }
 
+// Observable pass (OP_HX / OP_HD): th += H_part tp for the strings this pass owns.
+static void run_hpass(Ctx& c, const LaunchDesc& L, const DevPass& ps, const std::vector<cplx>& tp,
+                      std::vector<cplx>& th, uint32_t goff) {
+  const HostPlan& hp = *c.hp;
+  const int K = hp.K, R = 1 << K, nthr = 1 << (hp.T - K);
+  for (int tid = 0; tid < nthr; ++tid) {
+    uint32_t base = tid;
+    for (int j = 0; j < K; ++j) { int sp = ps.sorted[j]; base = ((base >> sp) << (sp + 1)) | (base & ((1u << sp) - 1u)); }
+    const uint32_t gbase = goff | scatter(base, L.runs, L.n_runs);
+    std::vector<uint32_t> idx(R);
+    for (int r = 0; r < R; ++r) { uint32_t dep = 0; for (int j = 0; j < K; ++j) if ((r >> j) & 1) dep |= 1u << ps.regbit[j]; idx[r] = base | dep; }
+    for (int oi = ps.op_begin; oi < ps.op_end; ++oi) {
+      const DevOp& op = hp.ops[oi];
+      if (op.type != OP_HX && op.type != OP_HD) throw std::runtime_error("unexpected op in an observable pass");
+      const double sg = (__builtin_popcount(gbase & (uint32_t)op.aux0) & 1) ? -1.0 : 1.0;
+      const int xr = op.type == OP_HD ? 0 : op.p0;
+      for (int r = 0; r < R; ++r) th[idx[r]] += sg * (double)c.coef[op.coef + r] * tp[idx[r ^ xr]];
+    }
+  }
+}
+
 static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
   const HostPlan& hp = *c.hp;
   const int tiles = hp.tiles(), tsz = 1 << hp.T;
@@ -303,6 +327,15 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
           const double sg = (__builtin_popcount(gi & d.z) & 1) ? -1.0 : 1.0;
           c.eacc[d.op] += sg * d.coeff * std::norm(tp[l]);
           tl[l] += gj * sg * d.coeff * tp[l];
+        }
+      }
+      if (L.pass_h_end > L.pass_h_begin) {  // single observable: its in-register strings
+        std::vector<cplx> th(tsz, 0);
+        for (int p = L.pass_h_begin; p < L.pass_h_end; ++p) run_hpass(c, L, hp.passes[p], tp, th, goff);
+        const double g0 = (adjoint && c.dgrad) ? c.dgrad[0] : 0.0;
+        for (int l = 0; l < tsz; ++l) {
+          c.eacc[0] += (std::conj(tp[l]) * th[l]).real();
+          tl[l] += g0 * th[l];
         }
       }
       for (int j = 0; j < hp.O; ++j) {
@@ -392,23 +425,24 @@ extern "C" int verify_dump(const qhbm_gate_t* gates, int n_gates, int n, int P, 
     HostPlan hp = compile_plan(c, o, with_grad != 0, T, K);
     static const char* names[] = {"NOP", "MAT1", "MAT2", "DCONST_TAB", "DCONST_PAIR", "DREG_TAB", "DAPPLY", "DCROSS",
                                   "XROT", "YROT", "GRAD_MAT1", "GRAD_MAT2", "XROTM", "YROTM", "XROTF", "GRAD_X", "GRAD_Y", "GD_BEGIN",
-                                  "GD_CONST", "GD_REG1", "GD_REG2", "GD_MIX"};
+                                  "GD_CONST", "GD_REG1", "GD_REG2", "GD_MIX", "HX", "HD"};
     printf("n_eff=%d T=%d K=%d ncoef=%d jobs=%zu terms=%zu groups=%zu\n", hp.n_eff, hp.T, hp.K, hp.ncoef, hp.jobs.size(),
            hp.terms.size(), hp.groups.size());
     for (size_t li = 0; li < hp.launches.size(); ++li) {
       const LaunchDesc& L = hp.launches[li];
-      printf("launch %zu flags=0x%x tile_mask=0x%x passA=[%d,%d) passB=[%d,%d)\n", li, L.flags, L.tile_mask,
-             L.pass_a_begin, L.pass_a_end, L.pass_b_begin, L.pass_b_end);
-      for (int pass = 0; pass < 2; ++pass) {
-        int b = pass ? L.pass_b_begin : L.pass_a_begin, e = pass ? L.pass_b_end : L.pass_a_end;
+      printf("launch %zu flags=0x%x tile_mask=0x%x passA=[%d,%d) passH=[%d,%d) passB=[%d,%d)\n", li, L.flags, L.tile_mask,
+             L.pass_a_begin, L.pass_a_end, L.pass_h_begin, L.pass_h_end, L.pass_b_begin, L.pass_b_end);
+      for (int pass = 0; pass < 3; ++pass) {
+        int b = pass == 2 ? L.pass_b_begin : (pass ? L.pass_h_begin : L.pass_a_begin);
+        int e = pass == 2 ? L.pass_b_end : (pass ? L.pass_h_end : L.pass_a_end);
         for (int p = b; p < e; ++p) {
           const DevPass& ps = hp.passes[p];
-          int hist[22] = {0};
+          int hist[24] = {0};
           for (int oi = ps.op_begin; oi < ps.op_end; ++oi) hist[hp.ops[oi].type]++;
           printf("   pass %d regbits=[", p);
           for (int j = 0; j < hp.K; ++j) printf("%d ", ps.regbit[j]);
           printf("] ngrad=%d ops:", ps.ngrad);
-          for (int t = 0; t < 22; ++t) if (hist[t]) printf(" %s=%d", names[t], hist[t]);
+          for (int t = 0; t < 24; ++t) if (hist[t]) printf(" %s=%d", names[t], hist[t]);
           printf("\n");
         }
       }

@@ -80,3 +80,23 @@ def test_qmhl_style_circuit_plus_dagger():
   total = orc.concat_circuits(g1, len(n1), orc.inverse_circuit(g2))
   ops = orc.kobe_shards(n, 2)[:12]
   _check(total, n, len(n1) + len(n2), ops, rng, 9, 4)
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("n,T,K", [(3, 0, 4), (6, 0, 4), (10, 9, 4), (11, 10, 5)])
+def test_single_observable_passes(seed, n, T, K):
+  """One observable made of 1- and 2-local X/Y strings with arbitrary Z tails: the strings whose flips
+  fit the tile run as observable passes (OP_HX / OP_HD), odd-Y strings and cross-tile flips stay in the
+  generic tables; both must add up to the oracle's value and adjoint gradient."""
+  rng = np.random.default_rng(1000 * n + seed)
+  nsym = 4
+  gates = hp.random_circuit(n, 14, nsym, rng)
+  terms = []
+  for _ in range(int(rng.integers(3, 12))):
+    paulis = {}
+    for q in rng.choice(n, int(rng.integers(0, min(n, 2) + 1)), replace=False):
+      paulis[int(q)] = str(rng.choice(["X", "Y"]))
+    for q in rng.choice(n, int(rng.integers(0, min(n, 4) + 1)), replace=False):
+      paulis.setdefault(int(q), "Z")
+    terms.append((float(rng.uniform(-2, 2)), paulis))
+  _check(gates, n, nsym, [terms], rng, T, K)

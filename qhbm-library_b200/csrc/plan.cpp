@@ -928,15 +928,26 @@ class Compiler {
       hp_.launches.push_back(L);
     }
     hp_.n_fwd_launches = (int)fs.size();
+    // The expectation phase needs the contiguous tile map.  When the first backward sweep uses the same
+    // map it runs in the same launch: psi and lambda stay in shared memory instead of a round trip
+    // through global memory.  psi then goes to the alternate buffer, because other tiles of this launch
+    // may still read the final state across tiles (x-groups that flip out-of-tile qubits).
+    const bool fuse = !bs.empty() && bs[0].tile_bits == contiguous && std::getenv("QHBM_NO_FUSE") == nullptr;
     {
       LaunchDesc L = blank();
       L.flags = LF_LOAD_PSI | LF_EXPECT | (hp_.grad ? LF_STORE_LAM : 0);
       L.pass_h_begin = h_begin_;
       L.pass_h_end = h_end_;
       fill_runs(contiguous, L);
+      if (fuse) {
+        L.pass_b_begin = bs[0].pass_begin;
+        L.pass_b_end = bs[0].pass_end;
+        L.flags = LF_LOAD_PSI | LF_EXPECT;
+        if (bs.size() > 1) L.flags |= LF_STORE_PSI | LF_STORE_LAM | LF_PSI_ALT;
+      }
       hp_.launches.push_back(L);
     }
-    for (size_t i = 0; i < bs.size(); ++i) {
+    for (size_t i = fuse ? 1 : 0; i < bs.size(); ++i) {
       LaunchDesc L = blank();
       L.flags = LF_LOAD_PSI | LF_LOAD_LAM;
       if (i + 1 < bs.size()) L.flags |= LF_STORE_PSI | LF_STORE_LAM;

@@ -95,6 +95,8 @@ enum LaunchFlags : uint32_t {
   LF_STORE_PSI = 1u << 4,
   LF_STORE_LAM = 1u << 5,
   LF_WRITE_STATE = 1u << 6, // debug: store psi into a caller buffer
+  LF_PSI_ALT = 1u << 7,     // psi is stored into the alternate workspace buffer (other CTAs of this launch
+                            // still read the old psi across tiles); later launches load from there
 };
 
 // One kernel launch = one sweep of one chunk of states.

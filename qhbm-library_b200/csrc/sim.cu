@@ -60,7 +60,7 @@ struct qhbm_plan {
   DevBuf<DevDiagTerm> d_dterms;
   DevBuf<float> d_coef;
   // workspace (grown on demand)
-  DevBuf<float2> d_psi, d_lam;
+  DevBuf<float2> d_psi, d_psi_alt, d_lam;
   DevBuf<double> d_eacc, d_gacc;
   // staging for the host-buffer entry point
   DevBuf<uint64_t> d_basis;
@@ -168,9 +168,12 @@ void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const flo
   // equal chunks no larger than the workspace allows (one chunk when everything fits)
   const int64_t n_chunks = (U + p->chunk - 1) / p->chunk;
   const int chunk = (int)((U + n_chunks - 1) / n_chunks);
+  bool pingpong = false;
+  for (const LaunchDesc& L : hp.launches) pingpong = pingpong || (L.flags & LF_PSI_ALT);
   if (multi) {
     p->d_psi.reserve((size_t)chunk << hp.n_eff);
     if (adjoint) p->d_lam.reserve((size_t)chunk << hp.n_eff);
+    if (adjoint && pingpong) p->d_psi_alt.reserve((size_t)chunk << hp.n_eff);
   }
   run_prep(p, d_symbols, mode, s);
   QHBM_CUDA(cudaMemsetAsync(p->d_eacc.p, 0, sizeof(double) * U * hp.O, s));
@@ -187,15 +190,21 @@ void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const flo
     ka.dgrad = (adjoint && d_dgrad) ? d_dgrad + u0 * hp.O : nullptr;
     ka.eacc = p->d_eacc.p + u0 * hp.O;
     ka.grow0 = (int)u0;
-    ka.psi = multi ? p->d_psi.p : nullptr;
+    float2* cur_psi = multi ? p->d_psi.p : nullptr;
     ka.lam = (multi && adjoint) ? p->d_lam.p : nullptr;
     for (size_t li = 0; li < hp.launches.size(); ++li) {
       ka.L = hp.launches[li];
       if (!adjoint) {
         if (ka.L.pass_b_end > ka.L.pass_b_begin && !(ka.L.flags & LF_EXPECT)) break;  // backward sweeps
         ka.L.pass_b_begin = ka.L.pass_b_end = 0;
-        ka.L.flags &= ~(uint32_t)LF_STORE_LAM;
+        ka.L.flags &= ~(uint32_t)(LF_STORE_LAM | LF_PSI_ALT);
         if (ka.L.flags & LF_EXPECT) ka.L.flags &= ~(uint32_t)(LF_STORE_PSI);
+      }
+      ka.psi = cur_psi;
+      ka.psi_out = cur_psi;
+      if (multi && (ka.L.flags & LF_PSI_ALT)) {
+        ka.psi_out = cur_psi == p->d_psi.p ? p->d_psi_alt.p : p->d_psi.p;
+        cur_psi = ka.psi_out;
       }
       launch_any(p, hp.grad, ka, c, s);
     }
@@ -233,6 +242,7 @@ void run_states(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const float* d
   fill_common(p, ka);
   ka.eacc = p->d_eacc.p;
   ka.psi = multi ? p->d_psi.p : nullptr;
+  ka.psi_out = ka.psi;
   ka.lam = (multi && hp.grad) ? p->d_lam.p : nullptr;
   for (int64_t u0 = 0; u0 < U; u0 += chunk) {
     const int c = (int)std::min<int64_t>(chunk, U - u0);

@@ -37,6 +37,7 @@ struct KernelArgs {
   const float* dgrad;     // [chunk, O] upstream gradients (adjoint) or nullptr
   double* eacc;           // [chunk, O] expectation accumulators
   double* gacc;           // [rows, P] gradient accumulators
+  float2* psi_out;        // where LF_STORE_PSI writes (== psi unless LF_PSI_ALT)
   float2* state_out;      // debug
   int32_t n, T, O, P;
   int32_t grow0;          // accumulator row of this chunk's first state (per-state gradients)
@@ -1039,7 +1040,7 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
   }
   if (flags & (LF_STORE_PSI | LF_STORE_LAM)) {
     __syncthreads();
-    if (flags & LF_STORE_PSI) store_tile<K>(s_psi, psi_u, goff, ka, one);
+    if (flags & LF_STORE_PSI) store_tile<K>(s_psi, ka.psi_out + ((size_t)u << ka.n), goff, ka, one);
     if constexpr (ADJ) {
       if (flags & LF_STORE_LAM) store_tile<K>(s_lam, lam_u, goff, ka, one);
     }

@@ -22,21 +22,37 @@ from qhbmlib.models import hamiltonian as hamiltonian_lib
 
 class _ExpectationOp(torch.autograd.Function):
   """f32[U, O] expectations; backward = adjoint gradient w.r.t. the symbol values.
-  Like TFQ, the backward pass re-simulates the forward circuit."""
+
+  Several observables: like TFQ, the backward pass re-simulates the forward circuit (the upstream
+  gradient is needed before the reverse sweep can start).  A single observable does not need it:
+  d<H>_u/d phi is computed per state in the forward call (one fused forward + adjoint run) and the
+  backward pass is a [U] x [U, P] contraction."""
 
   @staticmethod
   def forward(ctx, symbol_values, basis_idx, holder):
-    vals = holder.forward_plan.forward(basis_idx, symbol_values.detach().contiguous().float())
+    values = symbol_values.detach().contiguous().float()
     ctx.holder = holder
+    ctx.jacobian = None
+    single = holder.plan.n_ops == 1 and symbol_values.numel() > 0 and basis_idx.shape[0] > 0
+    if single and ctx.needs_input_grad[0] and holder.jacobian_in_forward:
+      ones = torch.ones((basis_idx.shape[0], 1), dtype=torch.float32, device=basis_idx.device)
+      vals, ctx.jacobian = holder.plan.forward_adjoint(basis_idx, values, ones, per_state=True,
+                                                       grad_mode=holder.grad_mode)
+      ctx.save_for_backward(symbol_values)
+      return vals
     ctx.save_for_backward(symbol_values, basis_idx)
-    return vals
+    return holder.forward_plan.forward(basis_idx, values)
 
   @staticmethod
   def backward(ctx, grad_out):
-    symbol_values, basis_idx = ctx.saved_tensors
-    holder = ctx.holder
+    symbol_values = ctx.saved_tensors[0]
     if symbol_values.numel() == 0:
       return torch.zeros_like(symbol_values), None, None
+    if ctx.jacobian is not None:
+      grad = grad_out.reshape(-1).float() @ ctx.jacobian
+      return grad.to(symbol_values.dtype), None, None
+    basis_idx = ctx.saved_tensors[1]
+    holder = ctx.holder
     _, grad = holder.plan.forward_adjoint(basis_idx, symbol_values.detach().contiguous().float(),
                                           grad_out.contiguous().float(), per_state=False,
                                           grad_mode=holder.grad_mode)
@@ -46,6 +62,8 @@ class _ExpectationOp(torch.autograd.Function):
 class _PlanHolder:
   """The adjoint plan, plus a forward-only plan (wider register blocking, no lambda tile) compiled
   lazily for the forward pass of autograd."""
+
+  jacobian_in_forward = True
 
   def __init__(self, plan, grad_mode, make_forward_plan):
     self.plan, self.grad_mode = plan, grad_mode

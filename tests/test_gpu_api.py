@@ -479,3 +479,37 @@ def test_config2_12q_vqt_kobe2_analytic():
   np.testing.assert_allclose(g_phi.cpu(), g_h.sum(0), rtol=1e-4, atol=2e-5)
   ref_gth = orc.expectation_score_gradient(counts, f, orc.parity_features(y, 2), np.zeros(len(th)), 1.0)
   np.testing.assert_allclose(g_theta.cpu(), ref_gth, rtol=1e-4, atol=2e-5)
+
+
+def test_single_observable_jacobian_in_forward_matches_resimulation():
+  """One observable: the autograd forward computes d<H>_u/d phi per state (fused run) and the backward
+  is a contraction; it must equal the re-simulating backward used for several observables, and a
+  no-grad call must not pay for it."""
+  from qhbmlib.inference import qnn as qnn_mod
+  n = 6
+  qubits = cq.GridQubit.rect(1, n)
+  circuit = arch.get_hardware_efficient_model_unitary(qubits, 2, "jac")
+  qnn = models.DirectQuantumCircuit(circuit, initializer=energy_utils.RandomUniform(-1, 1, seed=3))
+  q_infer = inference.AnalyticQuantumInference(qnn, grad_mode="exact")
+  ham = cq.convert_to_tensor([arch.xxz_ring(qubits)])
+  rng = np.random.default_rng(4)
+  bitstrings = _bits(rng.integers(0, 2, (40, n)).tolist())
+  weights = torch.tensor(rng.uniform(-1, 1, (40, 1)), dtype=torch.float32, device=DEV)
+  grads, outs = [], []
+  for flag in (True, False):
+    qnn_mod._PlanHolder.jacobian_in_forward = flag
+    try:
+      for p in qnn.parameters():
+        p.grad = None
+      out = q_infer.expectation(bitstrings, ham)
+      (out * weights).sum().backward()
+      outs.append(out.detach().cpu().numpy())
+      grads.append(qnn.trainable_variables[0].grad.cpu().numpy().copy())
+    finally:
+      qnn_mod._PlanHolder.jacobian_in_forward = True
+  np.testing.assert_allclose(outs[0], outs[1], rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(grads[0], grads[1], rtol=1e-4, atol=1e-4)
+  assert np.abs(grads[0]).max() > 0.1
+  with torch.no_grad():
+    quiet = q_infer.expectation(bitstrings, ham)
+  np.testing.assert_allclose(quiet.cpu().numpy(), outs[0], rtol=1e-5, atol=1e-5)

@@ -1,0 +1,104 @@
+"""Two-GPU NCCL test of the sharded paths: skipped on a single-GPU box.
+
+Every rank runs the CUDA engine on its own GPU; the sharded count-weighted expectation + gradient
+and the sharded 2^n EBM sweep (log Z, entropy, rank-level sample split, local sampling) must equal
+the single-GPU results of the same engine and the oracle."""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import qhbm_oracle as orc
+import helpers as hp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    return s.getsockname()[1]
+
+
+def _inputs():
+  n = 13
+  gates, names = orc.hea_circuit(n, 2)
+  rng = np.random.default_rng(5)
+  phi = rng.uniform(-1, 1, len(names)).astype(np.float32)
+  basis = rng.choice(1 << n, 301, replace=False).astype(np.int64)
+  counts = rng.integers(1, 40, 301).astype(np.int32)
+  ops = [orc.tfim_ring(n), orc.xxz_ring(n)]
+  n_bits = 14
+  thetas = rng.normal(0, 0.3, len(orc.parity_indices(n_bits, 2))).astype(np.float32)
+  return n, gates, names, phi, basis, counts, ops, n_bits, thetas
+
+
+def _worker(rank, world_size, port, out_dir):
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  for p in (root, os.path.join(root, "qhbm-library_b200"), os.path.join(root, "tests")):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  from qhbmlib import distributed as qd
+  from qhbmlib import engine
+  from qhbmlib import _native as nat
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=torch.device("cuda", rank))
+  try:
+    dev = torch.device("cuda", rank)
+    n, gates, names, phi, basis, counts, ops, n_bits, thetas = _inputs()
+    terms, offs = hp.ops_to_tables(ops, n)
+    plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, True)
+    sharded = qd.ShardedExpectation(plan)
+    avg, total, grad = sharded(torch.tensor(basis, device=dev), torch.tensor(counts, device=dev),
+                               torch.tensor(phi, device=dev), grad_mode="exact")
+    masks = [sum(1 << (n_bits - 1 - i) for i in grp) for grp in orc.parity_indices(n_bits, 2)]
+    desc = engine.EnergyDescriptor(nat.ENERGY_KOBE, n_bits, torch.tensor(masks, dtype=torch.int32, device=dev),
+                                   torch.tensor(thetas, device=dev))
+    logits, (lo, hi), log_z, entropy, masses = qd.sharded_ebm_sweep(desc, n_bits, device=dev)
+    split = qd.split_samples(200000, masses, (7, 8))
+    rows = engine.categorical_sample(logits, int(split[rank]), (7, 8 + rank), row_offset=lo)
+    hist = torch.bincount(rows, minlength=1 << n_bits).double()
+    dist.all_reduce(hist)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), avg=avg.cpu().numpy(), total=float(total), grad=grad.cpu().numpy(),
+             log_z=log_z, entropy=entropy, split=split, hist=hist.cpu().numpy(), lo=lo, hi=hi,
+             rows_min=int(rows.min()), rows_max=int(rows.max()))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_sharded_expectation_and_ebm_sweep(tmp_path):
+  world_size = 2
+  mp.spawn(_worker, args=(world_size, _free_port(), str(tmp_path)), nprocs=world_size, join=True)
+  r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+  for key in ("avg", "total", "grad", "log_z", "entropy", "split", "hist"):
+    np.testing.assert_array_equal(r0[key], r1[key])  # identical on every rank after the collectives
+  n, gates, names, phi, basis, counts, ops, n_bits, thetas = _inputs()
+  dg = np.tile((counts / counts.sum())[:, None], (1, 2))
+  e, g = orc.batch_expectation_and_gradient(gates, n, phi, basis, ops, dg)
+  np.testing.assert_allclose(r0["avg"], orc.weighted_average(counts, e), rtol=1e-5, atol=1e-5)
+  assert r0["total"] == counts.sum()
+  np.testing.assert_allclose(r0["grad"], g.sum(0), rtol=1e-5, atol=2e-5)
+  energies = orc.kobe_energy(orc.all_bitstrings(n_bits), 2, thetas.astype(np.float64))
+  np.testing.assert_allclose(float(r0["log_z"]), orc.analytic_log_partition(energies), rtol=1e-6)
+  np.testing.assert_allclose(float(r0["entropy"]), orc.analytic_entropy(energies), rtol=1e-5)
+  # every rank sampled inside its own row range; together the samples follow p(x)
+  half = 1 << (n_bits - 1)
+  assert (int(r0["lo"]), int(r0["hi"])) == (0, half) and (int(r1["lo"]), int(r1["hi"])) == (half, 2 * half)
+  assert 0 <= int(r0["rows_min"]) and int(r0["rows_max"]) < half <= int(r1["rows_min"]) and int(r1["rows_max"]) < 2 * half
+  assert int(r0["split"].sum()) == 200000 and r0["hist"].sum() == 200000
+  p = orc.analytic_probabilities(energies)
+  p0 = p[:half].sum()
+  assert abs(r0["split"][0] / 200000 - p0) < 5 * math.sqrt(p0 * (1 - p0) / 200000)
+  # coarse chi-square over 64 bins of the row index
+  obs = r0["hist"].reshape(64, -1).sum(1)
+  exp = p.reshape(64, -1).sum(1) * 200000
+  assert np.sum((obs - exp)**2 / exp) < 2.5 * 64

@@ -377,16 +377,33 @@ __global__ void __launch_bounds__(kEnergyThreads) ebm_sweep_kernel(const __grid_
 }
 // ------------------------------------------------------------------ dense-stack sweep, register tiled
 // The dense stack over 2^n rows is a chain of small GEMMs ([rows x in] x [in x out], widths <= 64) that must
-// stay in fp32 FMA (energies feed exp()).  One CTA pushes tiles of kMlpRows rows through all layers with
-// the activations feature-major in shared memory ([feature][row]); each thread owns an 8-row x 4-output
-// micro-tile, so one LDS.128 of weights and two of activations feed 32 FMAs.
+// stay in fp32 FMA (energies feed exp()).  One CTA of 128 threads pushes tiles of 128 consecutive rows
+// through all layers with the activations feature-major in ONE shared-memory buffer ([feature][row]);
+// each thread owns an 8-row x 8-output micro-tile (rows tx*4..+3 and 64+tx*4..+3), so four LDS.128
+// feed 64 FMAs.  The first layer never multiplies: its inputs are the bits of the row index, so a
+// thread adds the weight rows of the set bits -- once per tile for the bits its rows share, and from
+// three preloaded weight rows for the bits (0, 1, 6) that distinguish its rows.
 constexpr int kMlpRows = 128;
-constexpr int kMlpThreads = 256;
+constexpr int kMlpThreads = 128;
 
 __device__ __forceinline__ float fast_tanh(float x) {
   x = fminf(fmaxf(x, -9.f), 9.f);
   const float e = __expf(2.f * x);
   return __fdividef(e - 1.f, e + 1.f);
+}
+__device__ __forceinline__ float mlp_act(float y, int act) {
+  if (act == 1) return fast_tanh(y);
+  if (act == 2) return fmaxf(y, 0.f);
+  return y;
+}
+
+size_t mlp_sweep_weight_floats(const qhbm_energy_desc_t& d) {
+  size_t f = 0;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const int out8 = (d.widths[l + 1] + 7) & ~7;
+    f += (size_t)d.widths[l] * out8 + out8;
+  }
+  return f;
 }
 
 __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid_constant__ EnergyArgs ea, uint64_t lo,
@@ -395,89 +412,146 @@ __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid
   extern __shared__ __align__(16) float s_f[];
   __shared__ Stat s_st[kMlpThreads / 32];
   const qhbm_energy_desc_t& d = ea.d;
-  stage_energy(ea, s_f);  // weights [in][out4] + bias[out4] per layer, as in the per-row kernel
+  const int tid = threadIdx.x;
+  // weights [in][out8] + bias[out8] per layer (outputs padded to 8 with zeros)
   int wfloats = 0;
   for (int l = 0; l < d.n_layers; ++l) {
-    const int out4 = (d.widths[l + 1] + 3) & ~3;
-    wfloats += d.widths[l] * out4 + out4;
+    const int in = d.widths[l], out = d.widths[l + 1];
+    const int out8 = (out + 7) & ~7;
+    for (int i = tid; i < in * out8; i += kMlpThreads) {
+      const int r = i / out8, c = i - r * out8;
+      s_f[wfloats + i] = c < out ? d.d_weights[l][r * out + c] : 0.f;
+    }
+    for (int i = tid; i < out8; i += kMlpThreads) s_f[wfloats + in * out8 + i] = i < out ? d.d_bias[l][i] : 0.f;
+    wfloats += in * out8 + out8;
   }
-  float* bufA = s_f + ((wfloats + 3) & ~3);
-  float* bufB = bufA + kMaxWidth * kMlpRows;
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;  // rows tx*8.., outputs ty*4..
+  float* buf = s_f + ((wfloats + 3) & ~3);
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;  // rows tx*4.. (+64), outputs ty*8..
   const int n = d.n_bits;
-  const uint64_t rows = hi - lo;
-  const uint64_t ntiles = (rows + kMlpRows - 1) / kMlpRows;
+  const uint64_t t_first = lo / kMlpRows, t_last = (hi - 1) / kMlpRows;  // tiles of the ABSOLUTE row index
   Stat acc_st;
   acc_st.m = 0.0; acc_st.s = 0.0; acc_st.t = 0.0;
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint64_t row0 = lo + tile * kMlpRows;
+  for (uint64_t tile = t_first + blockIdx.x; tile <= t_last; tile += gridDim.x) {
+    const uint64_t row0 = tile * kMlpRows;
     __syncthreads();  // previous tile fully consumed
-    for (int i = tid; i < n * kMlpRows; i += kMlpThreads) {
-      const int k = i / kMlpRows, r = i - k * kMlpRows;
-      bufA[i] = (float)(((row0 + r) >> (n - 1 - k)) & 1ull);
-    }
-    __syncthreads();
-    float* src = bufA;
-    float* dst = bufB;
-    int off = 0;
-    for (int l = 0; l + 1 < d.n_layers; ++l) {
-      const int in = d.widths[l], out = d.widths[l + 1];
-      const int out4 = (out + 3) & ~3;
-      const float* W = s_f + off;
-      const float* Bv = W + in * out4;
-      if (ty * 4 < out4) {
-        float acc[8][4];
-        const float4 b4 = *reinterpret_cast<const float4*>(Bv + ty * 4);
+    // ---- layer 0: sums of weight rows selected by the bits of the row index
+    {
+      const int out8 = (d.widths[1] + 7) & ~7;
+      const float* W = s_f;
+      const float* Bv = W + n * out8;
+      if (ty * 8 < out8) {
+        float base[8];
+        {
+          const float4 b0 = *reinterpret_cast<const float4*>(Bv + ty * 8), b1 = *reinterpret_cast<const float4*>(Bv + ty * 8 + 4);
+          base[0] = b0.x; base[1] = b0.y; base[2] = b0.z; base[3] = b0.w;
+          base[4] = b1.x; base[5] = b1.y; base[6] = b1.z; base[7] = b1.w;
+        }
+        const uint64_t rowbase = row0 + (uint64_t)tx * 4;  // bits 0, 1 and 6 are clear
+        for (int p = 2; p < n; ++p) {
+          if (p == 6 || !((rowbase >> p) & 1ull)) continue;
+          const float* wr = W + (n - 1 - p) * out8 + ty * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+          base[0] += w0.x; base[1] += w0.y; base[2] += w0.z; base[3] += w0.w;
+          base[4] += w1.x; base[5] += w1.y; base[6] += w1.z; base[7] += w1.w;
+        }
+        float wp[3][8];  // weight rows of index bits 0, 1, 6 (zero when the model has fewer bits)
+        const int pb[3] = {0, 1, 6};
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { acc[r][0] = b4.x; acc[r][1] = b4.y; acc[r][2] = b4.z; acc[r][3] = b4.w; }
-#pragma unroll 4
-        for (int k = 0; k < in; ++k) {
-          const float4 x0 = *reinterpret_cast<const float4*>(src + k * kMlpRows + tx * 8);
-          const float4 x1 = *reinterpret_cast<const float4*>(src + k * kMlpRows + tx * 8 + 4);
-          const float4 w = *reinterpret_cast<const float4*>(W + k * out4 + ty * 4);
-          const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        for (int q = 0; q < 3; ++q) {
+          if (pb[q] < n) {
+            const float* wr = W + (n - 1 - pb[q]) * out8 + ty * 8;
+            const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+            wp[q][0] = w0.x; wp[q][1] = w0.y; wp[q][2] = w0.z; wp[q][3] = w0.w;
+            wp[q][4] = w1.x; wp[q][5] = w1.y; wp[q][6] = w1.z; wp[q][7] = w1.w;
+          } else {
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            acc[r][0] = fmaf(xs[r], w.x, acc[r][0]);
-            acc[r][1] = fmaf(xs[r], w.y, acc[r][1]);
-            acc[r][2] = fmaf(xs[r], w.z, acc[r][2]);
-            acc[r][3] = fmaf(xs[r], w.w, acc[r][3]);
+            for (int j = 0; j < 8; ++j) wp[q][j] = 0.f;
           }
         }
-        const int act = d.act[l];
+        const int act = d.act[0];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           float v[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            float y = acc[r][j];
-            if (act == 1) y = fast_tanh(y);
-            else if (act == 2) y = fmaxf(y, 0.f);
-            v[r] = y;
+            float y = base[j];
+            if (r & 1) y += wp[0][j];
+            if (r & 2) y += wp[1][j];
+            if (r & 4) y += wp[2][j];
+            v[r] = mlp_act(y, act);
           }
-          float* o = dst + (ty * 4 + j) * kMlpRows + tx * 8;
+          float* o = buf + (ty * 8 + j) * kMlpRows + tx * 4;
           *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          *reinterpret_cast<float4*>(o + 64) = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
-      off += in * out4 + out4;
-      __syncthreads();
-      float* t = src; src = dst; dst = t;
     }
-    // last layer: one output per row
+    __syncthreads();
+    int off = n * ((d.widths[1] + 7) & ~7) + ((d.widths[1] + 7) & ~7);
+    // ---- middle layers: [128 x in] x [in x out], 8 x 8 micro-tiles, in place through registers
+    for (int l = 1; l + 1 < d.n_layers; ++l) {
+      const int in = d.widths[l], out = d.widths[l + 1];
+      const int out8 = (out + 7) & ~7;
+      const float* W = s_f + off;
+      const float* Bv = W + in * out8;
+      const bool mine = ty * 8 < out8;
+      float acc[8][8];
+      if (mine) {
+        const float4 b0 = *reinterpret_cast<const float4*>(Bv + ty * 8), b1 = *reinterpret_cast<const float4*>(Bv + ty * 8 + 4);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
+          acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
+        }
+#pragma unroll 2
+        for (int k = 0; k < in; ++k) {
+          const float4 x0 = *reinterpret_cast<const float4*>(buf + k * kMlpRows + tx * 4);
+          const float4 x1 = *reinterpret_cast<const float4*>(buf + k * kMlpRows + tx * 4 + 64);
+          const float4 w0 = *reinterpret_cast<const float4*>(W + k * out8 + ty * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(W + k * out8 + ty * 8 + 4);
+          const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(xs[r], ws[j], acc[r][j]);
+        }
+      }
+      __syncthreads();  // every thread has read its inputs: the buffer can take the outputs
+      if (mine) {
+        const int act = d.act[l];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float* o = buf + (ty * 8 + j) * kMlpRows + tx * 4;
+          *reinterpret_cast<float4*>(o) = make_float4(mlp_act(acc[0][j], act), mlp_act(acc[1][j], act),
+                                                      mlp_act(acc[2][j], act), mlp_act(acc[3][j], act));
+          *reinterpret_cast<float4*>(o + 64) = make_float4(mlp_act(acc[4][j], act), mlp_act(acc[5][j], act),
+                                                           mlp_act(acc[6][j], act), mlp_act(acc[7][j], act));
+        }
+      }
+      off += in * out8 + out8;
+      __syncthreads();
+    }
+    // ---- last layer: one output per row, one row per thread
     {
       const int l = d.n_layers - 1;
       const int in = d.widths[l];
-      const int out4 = (d.widths[l + 1] + 3) & ~3;
+      const int out8 = (d.widths[l + 1] + 7) & ~7;
       const float* W = s_f + off;
-      if (tid < kMlpRows && row0 + tid < hi) {
-        float e = W[in * out4];
-        for (int k = 0; k < in; ++k) e = fmaf(src[k * kMlpRows + tid], W[k * out4], e);
-        if (d.act[l] == 1) e = fast_tanh(e);
-        else if (d.act[l] == 2) e = fmaxf(e, 0.f);
-        const float lg = -e;
-        if (logits) logits[row0 + tid - lo] = lg;
+      const uint64_t row = row0 + (uint64_t)tid;
+      float e0 = W[in * out8], e1 = 0.f, e2 = 0.f, e3 = 0.f;
+      int k = 0;
+      for (; k + 3 < in; k += 4) {
+        e0 = fmaf(buf[k * kMlpRows + tid], W[k * out8], e0);
+        e1 = fmaf(buf[(k + 1) * kMlpRows + tid], W[(k + 1) * out8], e1);
+        e2 = fmaf(buf[(k + 2) * kMlpRows + tid], W[(k + 2) * out8], e2);
+        e3 = fmaf(buf[(k + 3) * kMlpRows + tid], W[(k + 3) * out8], e3);
+      }
+      for (; k < in; ++k) e0 = fmaf(buf[k * kMlpRows + tid], W[k * out8], e0);
+      if (row >= lo && row < hi) {
+        const float lg = -mlp_act((e0 + e1) + (e2 + e3), d.act[l]);
+        if (logits) logits[row - lo] = lg;
         Stat one;
         one.m = (double)lg; one.s = 1.0; one.t = (double)lg;
         acc_st = stat_merge(acc_st, one);
@@ -786,10 +860,12 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
       g_sweep_partial_cap = 148 * 8;
     }
     if (e->kind == QHBM_ENERGY_MLP && e->n_layers >= 2 && rows >= 4096) {
-      // register-tiled dense-stack kernel: weights + two [64][128] activation buffers in shared memory
-      const size_t msmem = ((smem + 15) & ~(size_t)15) + 2 * sizeof(float) * kMaxWidth * kMlpRows;
+      // register-tiled dense-stack kernel: weights + one [64][128] activation buffer in shared memory
+      const size_t msmem = ((mlp_sweep_weight_floats(*e) * sizeof(float) + 15) & ~(size_t)15) +
+                           sizeof(float) * kMaxWidth * kMlpRows;
       QHBM_CUDA(cudaFuncSetAttribute(ebm_mlp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-      blocks = (int)std::min<uint64_t>((rows + kMlpRows - 1) / kMlpRows, 148 * 2);
+      const uint64_t ntiles = (hi - 1) / kMlpRows - lo / kMlpRows + 1;
+      blocks = (int)std::min<uint64_t>(ntiles, 148 * 3);
       ebm_mlp_sweep_kernel<<<blocks, kMlpThreads, msmem, s>>>(ea, lo, hi, d_logits, (Stat*)g_sweep_partial);
     } else {
       QHBM_CUDA(cudaFuncSetAttribute(ebm_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -144,6 +144,39 @@ def test_mlp_energy_sweep_against_oracle():
   np.testing.assert_allclose(m + np.log(s), orc.analytic_log_partition(e_ref), rtol=1e-6)
 
 
+@pytest.mark.parametrize("n,widths,acts,lo,hi", [
+    (14, [14, 64, 64, 1], ["tanh", "tanh", "linear"], 1000, 13001),       # ragged ends inside tiles
+    (13, [13, 37, 5, 1], ["relu", "tanh", "linear"], 0, 1 << 13),         # widths that are not multiples of 8
+    (13, [13, 20, 1], ["tanh", "linear"], 77, 8000),                      # two layers: bit-select + output layer
+    (13, [13, 64, 64, 64, 1], ["tanh", "relu", "tanh", "tanh"], 64, 4200),  # three hidden layers, bounded output
+    (16, [16, 8, 1], ["linear", "linear"], 3 * 4096 + 5, 5 * 4096 + 3),   # range away from row 0
+])
+def test_mlp_sweep_tiled_kernel_edge_cases(n, widths, acts, lo, hi):
+  """The register-tiled sweep kernel (>= 4096 rows) on row ranges that do not align with its 128-row
+  tiles and on layer shapes that exercise its output padding; statistics cover [lo, hi) only."""
+  eng = _eng()
+  from qhbmlib import _native as nat
+  rng = np.random.default_rng(n * 100 + len(widths))
+  layers = []
+  for l in range(len(widths) - 1):
+    lim = np.sqrt(6.0 / (widths[l] + widths[l + 1]))
+    layers.append((rng.uniform(-lim, lim, (widths[l], widths[l + 1])).astype(np.float32),
+                   rng.normal(0, 0.1, widths[l + 1]).astype(np.float32), acts[l]))
+  d = eng.EnergyDescriptor(nat.ENERGY_MLP, n, layers=[(torch.tensor(w, device="cuda"),
+                                                       torch.tensor(b, device="cuda"), a)
+                                                      for w, b, a in layers])
+  assert hi - lo >= 4096
+  logits, stats = d.sweep(lo, hi)
+  assert logits.shape == (hi - lo,)
+  e_ref = orc.mlp_energy(orc.all_bitstrings(n)[lo:hi], layers)
+  np.testing.assert_allclose(-logits.cpu().numpy(), e_ref, rtol=1e-5, atol=2e-6)
+  m, s, t = stats.cpu().numpy()
+  np.testing.assert_allclose(m + np.log(s), orc.analytic_log_partition(e_ref), rtol=1e-6)
+  np.testing.assert_allclose(m + np.log(s) - t / s, orc.analytic_entropy(e_ref), rtol=1e-5)
+  _, stats_only = d.sweep(lo, hi, want_logits=False)
+  np.testing.assert_allclose(stats_only.cpu().numpy(), stats.cpu().numpy(), rtol=1e-12)
+
+
 def test_categorical_sampling_distribution_and_seeding():
   eng = _eng()
   rng = np.random.default_rng(9)

@@ -648,10 +648,22 @@ class Compiler {
     }
   }
 
+  // Expectation stages.  Stage 0 runs in the expectation launch (contiguous tile map) and owns every
+  // x-group whose flips stay inside that tile, all diagonal terms and -- as a fallback -- groups that
+  // fit no tile (their partner amplitudes are read across tiles through L2).  Forward-only plans on
+  // multi-tile states add stages with other tile maps so that the remaining groups also find their
+  // partners in shared memory: one extra read of the state instead of one per out-of-tile qubit.
+  struct RawGroup {
+    int op = 0;
+    uint32_t x = 0;
+    std::vector<int> term_idx;
+    int stage = 0;
+  };
+
   void build_terms(const OpsIR& o) {
     // k = coeff * (-i)^{ny}; sign from parity(i & z) of the OUTPUT index i (derivation in DESIGN.md).
-    const uint32_t tile_mask = hp_.n_eff <= hp_.T ? 0xffffffffu : ((1u << hp_.T) - 1u);
-    const int mshift = hp_.T - hp_.K;  // the thread's m-th amplitude has tile-local index m << mshift | tid
+    const int Tl = std::min(hp_.T, hp_.n_eff);
+    const bool multi = hp_.n_eff > hp_.T;
     // Many diagonal terms (e.g. the K Z-string shards of a modular Hamiltonian, hamiltonian.py:48-51):
     // evaluate them all at once from one Walsh-Hadamard transform of |psi|^2 per tile.
     int n_diag = 0;
@@ -659,94 +671,172 @@ class Compiler {
     const bool use_wht = n_diag >= kWhtMinTerms;
     // A single observable whose strings flip at most two in-tile qubits runs as observable passes
     // (OP_HX / OP_HD); everything else stays in the generic x-group tables below.
-    // Adjoint plans only: in the forward-only kernel (K = 5, 128-register cap) the 32 complex registers
-    // of an observable pass spill and the generic tables are faster (measured, profiles/).
-    const bool hpass_ok = hp_.grad && o.n_ops() == 1 && !use_wht && !no_hpass_;
-    std::vector<HCand> hcands;
+    // Adjoint plans only: measured on B200, the forward-only kernel is faster with the generic tables
+    // (the passes' barriers and staging cost more than the per-amplitude sign arithmetic they save).
+    const bool hpass_ok = (hp_.grad || std::getenv("QHBM_HPASS_FORWARD")) && o.n_ops() == 1 && !use_wht && !no_hpass_;
+    std::vector<RawGroup> raw;
     for (int j = 0; j < o.n_ops(); ++j) {
-      DevOpRange r;
-      r.group_begin = (int32_t)hp_.groups.size();
       std::vector<int> idx;
       for (int t = o.offsets[j]; t < o.offsets[j + 1]; ++t) idx.push_back(t);
       std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return o.terms[a].xmask < o.terms[b].xmask; });
       size_t i = 0;
       while (i < idx.size()) {
         const uint32_t x = o.terms[idx[i]].xmask;
+        size_t e = i;
+        while (e < idx.size() && o.terms[idx[e]].xmask == x) ++e;
         if (x == 0 && use_wht) {
-          while (i < idx.size() && o.terms[idx[i]].xmask == 0) {
+          for (; i < e; ++i) {
             DevDiagTerm d;
             d.coeff = o.terms[idx[i]].coeff;
             d.z = o.terms[idx[i]].zmask;
             d.op = j;
             d.pad = 0;
             hp_.dterms.push_back(d);
-            ++i;
           }
           continue;
         }
-        if (hpass_ok && !(x & ~tile_mask) && __builtin_popcount(x) <= 2) {
-          bool real = true;
-          size_t e = i;
-          while (e < idx.size() && o.terms[idx[e]].xmask == x) {
-            real = real && !(__builtin_popcount(o.terms[idx[e]].xmask & o.terms[idx[e]].zmask) & 1);
-            ++e;
-          }
-          if (real) {
-            HCand hc;
-            hc.x = x;
-            for (; i < e; ++i) {
-              const qhbm_pauli_term_t& t = o.terms[idx[i]];
-              const int ny = __builtin_popcount(t.xmask & t.zmask) & 3;
-              hc.terms.push_back({ny == 0 ? t.coeff : -t.coeff, t.zmask});
-            }
-            hcands.push_back(hc);
-            continue;
-          }
-        }
-        DevTermGroup g;
-        std::memset(&g, 0, sizeof(g));
+        RawGroup g;
+        g.op = j;
         g.x = x;
-        g.xl = (x & ~tile_mask) ? -1 : (int32_t)x;
-        g.term_begin = (int32_t)hp_.terms.size();
-        while (i < idx.size() && o.terms[idx[i]].xmask == x) {
-          const qhbm_pauli_term_t& t = o.terms[idx[i]];
-          const int ny = __builtin_popcount(t.xmask & t.zmask) & 3;
-          DevTerm d;
-          d.kr = ny == 0 ? t.coeff : (ny == 2 ? -t.coeff : 0.f);
-          d.ki = ny == 1 ? -t.coeff : (ny == 3 ? t.coeff : 0.f);
-          d.z = t.zmask;
-          d.mword = 0;
-          for (int m = 0; m < (1 << hp_.K); ++m)
-            if (__builtin_popcount(((uint32_t)m << mshift) & t.zmask) & 1) d.mword |= 1u << m;
-          if (d.ki != 0.f) g.is_complex = 1;
-          if (t.zmask == 0) { g.k0r += d.kr; g.k0i += d.ki; }
-          else hp_.terms.push_back(d);
-          ++i;
-        }
-        g.term_end = (int32_t)hp_.terms.size();
-        hp_.groups.push_back(g);
+        g.term_idx.assign(idx.begin() + (long)i, idx.begin() + (long)e);
+        raw.push_back(g);
+        i = e;
       }
-      r.group_end = (int32_t)hp_.groups.size();
-      hp_.opranges.push_back(r);
     }
-    build_hpasses(hcands);
+    // ---- stage tile maps
+    stage_bits_.clear();
+    {
+      std::vector<int> contiguous;
+      for (int b = 0; b < Tl; ++b) contiguous.push_back(b);
+      stage_bits_.push_back(contiguous);
+    }
+    auto mask_of = [](const std::vector<int>& bits) {
+      uint32_t m = 0;
+      for (int b : bits) m |= 1u << b;
+      return m;
+    };
+    const uint32_t mask0 = multi ? mask_of(stage_bits_[0]) : 0xffffffffu;
+    // Extra stages are OFF by default: on B200 the cross-tile partner reads are served by L2 and the
+    // extra launch costs as much as it saves (n = 20 TFIM forward: 48.0 vs 47.1 ms; profiles/).  The
+    // switch keeps the path testable.
+    const bool extra_stages = multi && !hp_.grad && std::getenv("QHBM_EXPECT_STAGES") != nullptr;
+    for (RawGroup& g : raw) g.stage = (g.x & ~mask0) ? -1 : 0;
+    if (extra_stages) {
+      for (;;) {
+        // next map: bits 0..4 (coalescing) + the flips of as many unplaced groups as fit
+        uint32_t want = 0x1fu;
+        bool any = false;
+        for (const RawGroup& g : raw) {
+          if (g.stage >= 0) continue;
+          if (__builtin_popcount(want | g.x) <= Tl) { want |= g.x; any = true; }
+        }
+        if (!any) break;
+        for (int b = 0; b < hp_.n_eff && __builtin_popcount(want) < Tl; ++b) want |= 1u << b;
+        std::vector<int> bits;
+        for (int b = 0; b < hp_.n_eff; ++b) if ((want >> b) & 1) bits.push_back(b);
+        const int st = (int)stage_bits_.size();
+        stage_bits_.push_back(bits);
+        for (RawGroup& g : raw) if (g.stage < 0 && !(g.x & ~want)) g.stage = st;
+      }
+    }
+    for (RawGroup& g : raw) if (g.stage < 0) g.stage = 0;  // partner read across tiles
+    // ---- emit per stage
+    stage_ranges_.clear();
+    for (int st = 0; st < (int)stage_bits_.size(); ++st) {
+      const std::vector<int>& bits = stage_bits_[st];
+      const uint32_t smask = multi ? mask_of(bits) : 0xffffffffu;
+      std::vector<int> local_of(32, -1);
+      for (size_t j = 0; j < bits.size(); ++j) local_of[bits[j]] = (int)j;
+      const int mshift = (int)bits.size() - hp_.K;  // the thread's m-th amplitude: local index m << mshift | tid
+      std::vector<uint32_t> mstate(1 << hp_.K, 0);  // its state-index contribution
+      for (int m = 0; m < (1 << hp_.K); ++m)
+        for (size_t j = 0; j < bits.size(); ++j)
+          if ((((uint32_t)m << mshift) >> j) & 1) mstate[m] |= 1u << bits[j];
+      std::vector<HCand> hcands;
+      StageRange sr;
+      sr.grp_begin = (int32_t)hp_.groups.size();
+      sr.term_begin = (int32_t)hp_.terms.size();
+      for (int j = 0; j < o.n_ops(); ++j) {
+        DevOpRange r;
+        r.group_begin = (int32_t)hp_.groups.size();
+        for (const RawGroup& rg : raw) {
+          if (rg.op != j || rg.stage != st) continue;
+          const uint32_t x = rg.x;
+          if (hpass_ok && !(x & ~smask) && __builtin_popcount(x) <= 2) {
+            bool real = true;
+            for (int ti : rg.term_idx) real = real && !(__builtin_popcount(o.terms[ti].xmask & o.terms[ti].zmask) & 1);
+            if (real) {
+              HCand hc;
+              hc.x = x;
+              for (int ti : rg.term_idx) {
+                const qhbm_pauli_term_t& t = o.terms[ti];
+                const int ny = __builtin_popcount(t.xmask & t.zmask) & 3;
+                hc.terms.push_back({ny == 0 ? t.coeff : -t.coeff, t.zmask});
+              }
+              hcands.push_back(hc);
+              continue;
+            }
+          }
+          DevTermGroup g;
+          std::memset(&g, 0, sizeof(g));
+          g.x = x;
+          g.xl = -1;
+          if (!(x & ~smask)) {
+            g.xl = 0;
+            for (int b = 0; b < 32; ++b) if ((x >> b) & 1) g.xl |= 1 << (multi ? local_of[b] : b);
+          }
+          g.term_begin = (int32_t)hp_.terms.size();
+          for (int ti : rg.term_idx) {
+            const qhbm_pauli_term_t& t = o.terms[ti];
+            const int ny = __builtin_popcount(t.xmask & t.zmask) & 3;
+            DevTerm d;
+            d.kr = ny == 0 ? t.coeff : (ny == 2 ? -t.coeff : 0.f);
+            d.ki = ny == 1 ? -t.coeff : (ny == 3 ? t.coeff : 0.f);
+            d.z = t.zmask;
+            d.mword = 0;
+            for (int m = 0; m < (1 << hp_.K); ++m)
+              if (__builtin_popcount(mstate[m] & t.zmask) & 1) d.mword |= 1u << m;
+            if (d.ki != 0.f) g.is_complex = 1;
+            if (t.zmask == 0) { g.k0r += d.kr; g.k0i += d.ki; }
+            else hp_.terms.push_back(d);
+          }
+          g.term_end = (int32_t)hp_.terms.size();
+          hp_.groups.push_back(g);
+        }
+        r.group_end = (int32_t)hp_.groups.size();
+        hp_.opranges.push_back(r);
+      }
+      sr.grp_end = (int32_t)hp_.groups.size();
+      sr.term_end = (int32_t)hp_.terms.size();
+      stage_ranges_.push_back(sr);
+      build_hpasses(st, hcands);
+    }
   }
+
+  struct StageRange {
+    int32_t grp_begin = 0, grp_end = 0, term_begin = 0, term_end = 0;
+  };
 
   struct HCand {
     uint32_t x = 0;                                  // state-index xor mask (0: diagonal terms)
     std::vector<std::pair<float, uint32_t>> terms;   // (real coefficient incl. the Y phases, z-mask)
   };
 
-  // Observable passes of the expectation launch (contiguous tile: tile-local bit = state bit).
-  // Off-diagonal candidates are packed greedily into register sets (chains of neighbouring pairs share
-  // qubits); every diagonal term goes to the pass whose registers cover most of its z-mask.  The part
-  // of a z-mask outside the registers becomes a per-thread sign (DevOp::aux0).
-  void build_hpasses(const std::vector<HCand>& cands) {
-    h_begin_ = h_end_ = (int)hp_.passes.size();
+  // Observable passes of one expectation stage.  Off-diagonal candidates are packed greedily into sets
+  // of four register qubits (chains of neighbouring pairs share qubits); with K = 5 a fifth, flip-free
+  // register qubit pads the set.  Every diagonal term goes to the pass whose registers cover most of
+  // its z-mask.  The part of a z-mask outside the registers becomes a per-thread sign (DevOp::aux0).
+  // Register qubits are STATE bits here; DevPass stores them as tile-local bits of the stage's map.
+  void build_hpasses(int stage, const std::vector<HCand>& cands) {
+    if ((int)h_ranges_.size() <= stage) h_ranges_.resize(stage + 1, {0, 0});
+    h_ranges_[stage] = {(int)hp_.passes.size(), (int)hp_.passes.size()};
     if (cands.empty()) return;
-    const int K = hp_.K, R = 1 << K, Tl = std::min(hp_.T, hp_.n_eff);
+    const int K = hp_.K, R = 1 << K, Kx = 4;
+    const std::vector<int>& tile_bits = stage_bits_[stage];
+    std::vector<int> local_of(32, -1);
+    for (size_t j = 0; j < tile_bits.size(); ++j) local_of[tile_bits[j]] = (int)j;
     struct HP {
-      std::vector<int> regs;
+      std::vector<int> regs;  // state bits; positions 0..3 may carry flips
       std::vector<int> offdiag;
     };
     std::vector<HP> hps;
@@ -780,7 +870,7 @@ class Compiler {
         int best = -1, best_missing = 99, best_shared = -1;
         for (size_t pi = 0; pi < pending.size(); ++pi) {
           const int m = missing(pending[pi]);
-          if ((int)p.regs.size() + m > K) continue;
+          if ((int)p.regs.size() + m > Kx) continue;
           const int shared = __builtin_popcount(cands[pending[pi]].x) - m;
           if (m < best_missing || (m == best_missing && shared > best_shared)) {
             best = (int)pi; best_missing = m; best_shared = shared;
@@ -795,8 +885,8 @@ class Compiler {
     for (size_t c = 0; c < cands.size(); ++c) if (cands[c].x == 0) diag = (int)c;
     if (hps.empty()) hps.push_back(HP());
     for (HP& p : hps)  // pad the register set from the top of the tile
-      for (int b = Tl - 1; b >= 0 && (int)p.regs.size() < K; --b)
-        if (std::find(p.regs.begin(), p.regs.end(), b) == p.regs.end()) p.regs.push_back(b);
+      for (int j = (int)tile_bits.size() - 1; j >= 0 && (int)p.regs.size() < K; --j)
+        if (std::find(p.regs.begin(), p.regs.end(), tile_bits[j]) == p.regs.end()) p.regs.push_back(tile_bits[j]);
     std::vector<std::vector<std::pair<float, uint32_t>>> diag_of(hps.size());
     if (diag >= 0) {
       for (const auto& t : cands[diag].terms) {
@@ -815,19 +905,19 @@ class Compiler {
       const HP& p = hps[h];
       DevPass ps;
       std::memset(&ps, 0, sizeof(ps));
-      for (int j = 0; j < K; ++j) ps.regbit[j] = p.regs[j];
+      for (int j = 0; j < K; ++j) ps.regbit[j] = local_of[p.regs[j]];
       {
-        std::vector<int> srt(p.regs.begin(), p.regs.end());
+        std::vector<int> srt(ps.regbit, ps.regbit + K);
         std::sort(srt.begin(), srt.end());
         for (int j = 0; j < K; ++j) ps.sorted[j] = srt[j];
       }
       uint32_t regmask = 0;
-      std::vector<uint32_t> rbits(R, 0);
+      std::vector<uint32_t> rbits(R, 0);  // state-index bits set in register amplitude r
       for (int j = 0; j < K; ++j) regmask |= 1u << p.regs[j];
       for (int r = 0; r < (1 << kMaxRegQubits); ++r) {
-        uint32_t dep = 0;
-        for (int j = 0; j < K; ++j) if ((r >> j) & 1) dep |= 1u << ps.regbit[j];
-        if (r < R) rbits[r] = dep;
+        uint32_t dep = 0, sdep = 0;
+        for (int j = 0; j < K; ++j) if ((r >> j) & 1) { dep |= 1u << ps.regbit[j]; sdep |= 1u << p.regs[j]; }
+        if (r < R) rbits[r] = sdep;
         const uint32_t sw = (dep & ~15u) | ((dep ^ (dep >> 4) ^ (dep >> 8) ^ (dep >> 12)) & 15u);
         ps.eoff[r] = r < R ? (uint16_t)sw : 0;
       }
@@ -863,7 +953,7 @@ class Compiler {
       };
       for (int c : p.offdiag) {
         int xr = 0;
-        for (int j = 0; j < K; ++j) if ((cands[c].x >> p.regs[j]) & 1) xr |= 1 << j;
+        for (int j = 0; j < Kx; ++j) if ((cands[c].x >> p.regs[j]) & 1) xr |= 1 << j;
         emit(OP_HX, xr, cands[c].terms);
       }
       if (!diag_of[h].empty()) emit(OP_HD, 0, diag_of[h]);
@@ -871,7 +961,7 @@ class Compiler {
       ps.coef_end = hp_.ncoef;
       if (ps.op_end > ps.op_begin) hp_.passes.push_back(ps);
     }
-    h_end_ = (int)hp_.passes.size();
+    h_ranges_[stage].second = (int)hp_.passes.size();
   }
 
   void compile(const CircuitIR& c, const OpsIR& o) {
@@ -898,12 +988,20 @@ class Compiler {
       std::memset(&L, 0, sizeof(L));
       return L;
     };
+    auto set_stage = [&](LaunchDesc& L, int st) {
+      L.expect_stage = st;
+      L.pass_h_begin = h_ranges_[st].first;
+      L.pass_h_end = h_ranges_[st].second;
+      L.grp_begin = stage_ranges_[st].grp_begin;
+      L.grp_end = stage_ranges_[st].grp_end;
+      L.term_begin = stage_ranges_[st].term_begin;
+      L.term_end = stage_ranges_[st].term_end;
+    };
     if (hp_.n_eff <= hp_.T) {
       // whole state in one tile: one launch does forward, expectation and backward
       LaunchDesc L = blank();
       L.flags = LF_INIT_BASIS | LF_EXPECT;
-      L.pass_h_begin = h_begin_;
-      L.pass_h_end = h_end_;
+      set_stage(L, 0);
       fill_runs(contiguous, L);
       L.pass_a_begin = fs.empty() ? 0 : fs.front().pass_begin;
       L.pass_a_end = fs.empty() ? 0 : fs.back().pass_end;
@@ -936,8 +1034,7 @@ class Compiler {
     {
       LaunchDesc L = blank();
       L.flags = LF_LOAD_PSI | LF_EXPECT | (hp_.grad ? LF_STORE_LAM : 0);
-      L.pass_h_begin = h_begin_;
-      L.pass_h_end = h_end_;
+      set_stage(L, 0);
       fill_runs(contiguous, L);
       if (fuse) {
         L.pass_b_begin = bs[0].pass_begin;
@@ -945,6 +1042,13 @@ class Compiler {
         L.flags = LF_LOAD_PSI | LF_EXPECT;
         if (bs.size() > 1) L.flags |= LF_STORE_PSI | LF_STORE_LAM | LF_PSI_ALT;
       }
+      hp_.launches.push_back(L);
+    }
+    for (int st = 1; st < (int)stage_bits_.size(); ++st) {  // forward-only plans: the other tile maps
+      LaunchDesc L = blank();
+      L.flags = LF_LOAD_PSI | LF_EXPECT;
+      set_stage(L, st);
+      fill_runs(stage_bits_[st], L);
       hp_.launches.push_back(L);
     }
     for (size_t i = fuse ? 1 : 0; i < bs.size(); ++i) {
@@ -962,7 +1066,9 @@ class Compiler {
  private:
   HostPlan& hp_;
   std::vector<int> phase_gates_;  // forward X/Y powers whose global phase was dropped
-  int h_begin_ = 0, h_end_ = 0;   // observable passes
+  std::vector<std::pair<int, int>> h_ranges_;  // observable passes of every stage
+  std::vector<std::vector<int>> stage_bits_;  // tile map of every expectation stage
+  std::vector<StageRange> stage_ranges_;
   bool no_hpass_ = std::getenv("QHBM_NO_HPASS") != nullptr;  // development switch: generic tables only
 };
 

@@ -109,6 +109,9 @@ struct LaunchDesc {
   BitRun oruns[kMaxRuns];            // tile-id bits -> state bits (the out-of-tile bits)
   uint32_t tile_mask;                // state-index bits covered by the tile
   int32_t pass_h_begin, pass_h_end;  // observable passes run at the start of the expectation phase
+  int32_t expect_stage;              // LF_EXPECT: which stage's tables (opranges[stage * O + j]) this launch uses
+  int32_t grp_begin, grp_end;        // that stage's slice of the group / term tables (staged in shared memory)
+  int32_t term_begin, term_end;
   // the thread's m-th tile element is local index (m << (T-K)) | tid:
   uint32_t moff[1 << kMaxRegQubits]; // its state-index contribution scatter(m << (T-K))
   uint16_t soff[1 << kMaxRegQubits]; // its swizzled smem contribution swz(m << (T-K))

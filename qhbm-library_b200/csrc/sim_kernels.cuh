@@ -576,13 +576,12 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
 // BOTH = true (adjoint kernel): h = H psi accumulates in the lambda tile (unscaled; the expectation phase
 // finishes E and lambda from it).  BOTH = false: E is accumulated directly.  Single observable only.
 // ---------------------------------------------------------------------------------
-template <int K, int XR, bool BOTH>
-__device__ __forceinline__ void hx_apply(const float2 (&a)[1 << K], float2 (&b)[BOTH ? (1 << K) : 1],
-                                         const float* cf, const float sgn, float& e) {
-  constexpr int R = 1 << K;
+template <int XR, bool BOTH>
+__device__ __forceinline__ void hx_apply(const float2 (&a)[16], float2 (&b)[BOTH ? 16 : 1], const float* cf,
+                                         const float sgn, float& e) {
   float acc = 0.f;
 #pragma unroll
-  for (int r0 = 0; r0 < R; r0 += 4) {
+  for (int r0 = 0; r0 < 16; r0 += 4) {
     const float4 t4 = ldg4(cf + r0);  // coefficients are read four at a time: no table in registers
     const float tab[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
@@ -600,6 +599,9 @@ __device__ __forceinline__ void hx_apply(const float2 (&a)[1 << K], float2 (&b)[
   if constexpr (!BOTH) e = fmaf(sgn, acc, e);
 }
 
+// The pass works on 16 amplitudes at a time (register positions 0..3 carry the flips); with K = 5 the
+// fifth register position only selects the half, so the forward-only kernel never holds 32 complex
+// registers here.
 template <int K, bool BOTH>
 __device__ __forceinline__ void run_hpass(const KernelArgs& ka, const DevPass* __restrict__ ps, const float2* s_psi,
                                           float2* s_lam, float4* s_stage, uint32_t goff, uint32_t u) {
@@ -629,50 +631,54 @@ __device__ __forceinline__ void run_hpass(const KernelArgs& ka, const DevPass* _
   }
   const uint32_t B = swz(base);
   const uint32_t gbase = goff | scatter_bits(base, ka.L.runs, ka.L.n_runs);
-  uint32_t eo[R];
-  {
-    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
-#pragma unroll
-    for (int i = 0; i < R / 8; ++i) {
-      const uint4 w = __ldg(ep + i);
-      eo[8 * i + 0] = w.x & 0xffffu; eo[8 * i + 1] = w.x >> 16;
-      eo[8 * i + 2] = w.y & 0xffffu; eo[8 * i + 3] = w.y >> 16;
-      eo[8 * i + 4] = w.z & 0xffffu; eo[8 * i + 5] = w.z >> 16;
-      eo[8 * i + 6] = w.w & 0xffffu; eo[8 * i + 7] = w.w >> 16;
-    }
-  }
   __syncthreads();  // staged program visible
-  float2 a[R];
-  float2 b[BOTH ? R : 1];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    a[r] = s_psi[B ^ eo[r]];
-    if constexpr (BOTH) b[r] = s_lam[B ^ eo[r]];
-  }
   float e = 0.f;
-  for (int oi = op_begin; oi < op_end; ++oi) {
-    const OpRec op = load_op(ops_base + oi);
-    const float* cf = coef_base + op.coef;
-    const float sgn = (__popc(gbase & (uint32_t)op.aux0) & 1) ? -1.f : 1.f;
-    if (op.type == OP_HD) {
-      hx_apply<K, 0, BOTH>(a, b, cf, sgn, e);
-    } else {
-      // register xor masks with one or two bits set
-      for_each_pos<K>([&](auto ph) {
-        constexpr int PH = decltype(ph)::value;
-        for_each_pos<K>([&](auto pl) {
-          constexpr int PL = decltype(pl)::value;
-          if constexpr (PL <= PH) {
-            if (op.p0 == ((1 << PH) | (1 << PL))) hx_apply<K, (1 << PH) | (1 << PL), BOTH>(a, b, cf, sgn, e);
-          }
+#pragma unroll 1
+  for (int half = 0; half < R / 16; ++half) {
+    uint32_t eo[16];
+    {
+      const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff) + 2 * half;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint4 w = __ldg(ep + i);
+        eo[8 * i + 0] = w.x & 0xffffu; eo[8 * i + 1] = w.x >> 16;
+        eo[8 * i + 2] = w.y & 0xffffu; eo[8 * i + 3] = w.y >> 16;
+        eo[8 * i + 4] = w.z & 0xffffu; eo[8 * i + 5] = w.z >> 16;
+        eo[8 * i + 6] = w.w & 0xffffu; eo[8 * i + 7] = w.w >> 16;
+      }
+    }
+    float2 a[16];
+    float2 b[BOTH ? 16 : 1];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      a[r] = s_psi[B ^ eo[r]];
+      if constexpr (BOTH) b[r] = s_lam[B ^ eo[r]];
+    }
+    for (int oi = op_begin; oi < op_end; ++oi) {
+      const OpRec op = load_op(ops_base + oi);
+      const float* cf = coef_base + op.coef + 16 * half;
+      const float sgn = (__popc(gbase & (uint32_t)op.aux0) & 1) ? -1.f : 1.f;
+      if (op.type == OP_HD) {
+        hx_apply<0, BOTH>(a, b, cf, sgn, e);
+      } else {
+        // register xor masks with one or two of the low four bits set
+        for_each_pos<4>([&](auto ph) {
+          constexpr int PH = decltype(ph)::value;
+          for_each_pos<4>([&](auto pl) {
+            constexpr int PL = decltype(pl)::value;
+            if constexpr (PL <= PH) {
+              if (op.p0 == ((1 << PH) | (1 << PL))) hx_apply<(1 << PH) | (1 << PL), BOTH>(a, b, cf, sgn, e);
+            }
+          });
         });
-      });
+      }
+    }
+    if constexpr (BOTH) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) s_lam[B ^ eo[r]] = b[r];
     }
   }
-  if constexpr (BOTH) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) s_lam[B ^ eo[r]] = b[r];
-  } else {
+  if constexpr (!BOTH) {
     e = warp_sum(e);
     if ((tid & 31) == 0) atomicAdd(&ka.eacc[(size_t)u * ka.O], (double)e);
   }
@@ -836,20 +842,24 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
   const uint32_t gi_tid = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
   const uint32_t ph_tid = swz(tid);
   __syncthreads();
-  // stage the Pauli tables (group headers: 2 float4 each, terms: 1 float4 each) next to the program
+  // stage this launch's slice of the Pauli tables (group headers: 2 float4 each, terms: 1 float4 each)
   const DevTermGroup* groups = ka.groups;
   const DevTerm* terms = ka.terms;
-  if (2 * ka.n_groups + ka.n_terms <= 2 * kStageOps + kStageCoef / 4) {
-    const float4* gg = reinterpret_cast<const float4*>(ka.groups);
-    const float4* gt = reinterpret_cast<const float4*>(ka.terms);
-    for (int i = (int)tid; i < 2 * ka.n_groups; i += (int)nthr) s_stage[i] = __ldg(gg + i);
-    for (int i = (int)tid; i < ka.n_terms; i += (int)nthr) s_stage[2 * ka.n_groups + i] = __ldg(gt + i);
-    groups = reinterpret_cast<const DevTermGroup*>(s_stage);
-    terms = reinterpret_cast<const DevTerm*>(s_stage + 2 * ka.n_groups);
-    __syncthreads();
+  const DevOpRange* opranges = ka.opranges + (size_t)ka.L.expect_stage * ka.O;
+  {
+    const int ng = ka.L.grp_end - ka.L.grp_begin, nt = ka.L.term_end - ka.L.term_begin;
+    if (2 * ng + nt <= 2 * kStageOps + kStageCoef / 4) {
+      const float4* gg = reinterpret_cast<const float4*>(ka.groups + ka.L.grp_begin);
+      const float4* gt = reinterpret_cast<const float4*>(ka.terms + ka.L.term_begin);
+      for (int i = (int)tid; i < 2 * ng; i += (int)nthr) s_stage[i] = __ldg(gg + i);
+      for (int i = (int)tid; i < nt; i += (int)nthr) s_stage[2 * ng + i] = __ldg(gt + i);
+      groups = reinterpret_cast<const DevTermGroup*>(s_stage) - ka.L.grp_begin;
+      terms = reinterpret_cast<const DevTerm*>(s_stage + 2 * ng) - ka.L.term_begin;
+      __syncthreads();
+    }
   }
   float dgall[ADJ ? R : 1];
-  const bool wht = ka.n_dterms > 0;
+  const bool wht = ka.n_dterms > 0 && ka.L.expect_stage == 0;  // diagonal terms live in stage 0
   if (wht) {
     // float scratch: the (not yet written) lambda tile, or the extra tile of the forward-only kernel
     float* W = reinterpret_cast<float*>(s_psi + (1u << ka.T));
@@ -882,8 +892,8 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
           for (int m = 0; m < MC; ++m) h[m] = s_lam[ph_tid ^ ka.L.soff[m0 + m]];
         }
       }
-      const int g_end = __ldg(&ka.opranges[j].group_end);
-      int g = __ldg(&ka.opranges[j].group_begin);
+      const int g_end = __ldg(&opranges[j].group_end);
+      int g = __ldg(&opranges[j].group_begin);
       int4 gh, gk;
       if (g < g_end) {
         gh = reinterpret_cast<const int4*>(groups + g)[0];

@@ -321,6 +321,7 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
     if (active) for (int p = L.pass_a_begin; p < L.pass_a_end; ++p) run_pass(c, L, hp.passes[p], tp, tl, goff, false);
     if (L.flags & LF_EXPECT) {
       for (const DevDiagTerm& d : hp.dterms) {  // WHT-path terms: same mathematics, evaluated directly here
+        if (L.expect_stage != 0) break;
         const double gj = (adjoint && c.dgrad) ? c.dgrad[d.op] : 0.0;
         for (int l = 0; l < tsz; ++l) {
           const uint32_t gi = goff | scatter(l, L.runs, L.n_runs);
@@ -341,7 +342,9 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
       for (int j = 0; j < hp.O; ++j) {
         const double gj = (adjoint && c.dgrad) ? c.dgrad[j] : 0.0;
         double ej = 0;
-        for (int g = hp.opranges[j].group_begin; g < hp.opranges[j].group_end; ++g) {
+        const DevOpRange& orng = hp.opranges[(size_t)L.expect_stage * hp.O + j];
+        for (int g = orng.group_begin; g < orng.group_end; ++g) {
+          if (g < L.grp_begin || g >= L.grp_end) throw std::runtime_error("group outside the launch's stage slice");
           const DevTermGroup& G = hp.groups[g];
           for (int l = 0; l < tsz; ++l) {
             const uint32_t gi = goff | scatter(l, L.runs, L.n_runs);

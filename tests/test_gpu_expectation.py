@@ -115,6 +115,26 @@ def test_observable_passes_match_generic_tables(monkeypatch):
                                atol=RTOL * float(g_g.abs().max()) * 3)
 
 
+@pytest.mark.parametrize("n,T,K,ham", [(15, 0, 0, "tfim"), (15, 12, 5, "xxz"), (12, 10, 5, "tfim")])
+def test_forward_only_expectation_stages_and_passes(n, T, K, ham, monkeypatch):
+  """The optional forward-only paths (extra expectation stages with their own tile maps, observable
+  passes in the K = 5 kernel) stay correct although they are off by default."""
+  from qhbmlib import engine
+  monkeypatch.setenv("QHBM_EXPECT_STAGES", "1")
+  monkeypatch.setenv("QHBM_HPASS_FORWARD", "1")
+  rng = np.random.default_rng(n)
+  gates, names = orc.hea_circuit(n, 2)
+  ops = [orc.tfim_ring(n) if ham == "tfim" else orc.xxz_ring(n)]
+  terms, offs = hp.ops_to_tables(ops, n)
+  plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, False, T, K)
+  assert plan.info["launches"] > plan.info["sweeps_fwd"] + 1
+  phi = rng.uniform(-1, 1, len(names)).astype(np.float32)
+  basis = rng.choice(1 << n, 6, replace=False).astype(np.int64)
+  e = plan.forward(torch.tensor(basis, device="cuda"), torch.tensor(phi, device="cuda")).cpu().numpy()
+  e_ref = orc.expectations(gates, n, phi, basis, ops)
+  np.testing.assert_allclose(e, e_ref, rtol=RTOL, atol=RTOL * _scale(ops).max())
+
+
 @pytest.mark.parametrize("n,T,K", [(4, 0, 4), (11, 9, 4)])
 def test_tfq_fd_mode(n, T, K):
   rng = np.random.default_rng(7)

@@ -100,3 +100,31 @@ def test_single_observable_passes(seed, n, T, K):
       paulis.setdefault(int(q), "Z")
     terms.append((float(rng.uniform(-2, 2)), paulis))
   _check(gates, n, nsym, [terms], rng, T, K)
+
+
+@pytest.mark.parametrize("n,T,K,kind", [(11, 10, 5, "tfim"), (12, 10, 5, "xxz"), (13, 10, 5, "random"),
+                                        (12, 9, 4, "random"), (14, 10, 5, "tfim"), (6, 0, 5, "random")])
+def test_forward_only_plans_with_expectation_stages(n, T, K, kind, monkeypatch):
+  """Forward-only plans of multi-tile states can evaluate x-groups that flip out-of-tile qubits in extra
+  expectation stages with their own tile maps (QHBM_EXPECT_STAGES; off by default because it measured
+  neutral on B200) and run a single observable as observable passes (QHBM_HPASS_FORWARD); values must
+  match the oracle for every observable."""
+  monkeypatch.setenv("QHBM_EXPECT_STAGES", "1")
+  monkeypatch.setenv("QHBM_HPASS_FORWARD", "1")
+  rng = np.random.default_rng(n * 7 + T)
+  gates, names = orc.hea_circuit(n, 2)
+  nsym = len(names)
+  if kind == "tfim":
+    ops = [orc.tfim_ring(n)]
+  elif kind == "xxz":
+    ops = [orc.xxz_ring(n), orc.tfim_ring(n)]
+  else:
+    ops = hp.random_ops(n, 3, rng, max_terms=6)
+  phi = rng.uniform(-1, 1, nsym).astype(np.float32)
+  basis = int(rng.integers(0, 1 << n))
+  e, _, state, info = hp.verify_run(gates, n, nsym, ops, phi, basis, np.zeros(len(ops), np.float32), False, T, K)
+  np.testing.assert_allclose(state, orc.simulate(gates, n, phi, basis), atol=2e-5)
+  e_ref = orc.expectations(gates, n, phi, [basis], ops)[0]
+  np.testing.assert_allclose(e, e_ref, atol=2e-4)
+  if n > max(T, K + 5) and kind != "random":
+    assert info[6] > info[0] + 1  # launches > forward sweeps + one expectation launch

@@ -8,6 +8,9 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <stdexcept>
 #include <vector>
 
@@ -743,6 +746,21 @@ static UniqueWs carve_unique(void* ws, int64_t n) {
 
 using namespace qhbm;
 
+namespace {
+// 28 KB of scratch per (device, stream): work on one stream is ordered, so the buffer can be reused by
+// the next sweep on that stream; different streams and devices never share one.
+void* sweep_scratch(cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, void*> cache;
+  int dev = 0;
+  QHBM_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  void*& p = cache[{dev, s}];
+  if (!p) QHBM_CUDA(cudaMalloc(&p, sizeof(Stat) * 148 * 8));
+  return p;
+}
+}  // namespace
+
 extern "C" {
 
 int qhbm_pack_bits(const int8_t* d_bits, int64_t n_rows, int32_t n_bits, const int32_t* h_shift, uint64_t* d_keys,
@@ -837,8 +855,6 @@ int qhbm_energy_rows(const qhbm_energy_desc_t* e, const uint64_t* d_keys, int64_
   });
 }
 
-static void* g_sweep_partial = nullptr;
-static int g_sweep_partial_cap = 0;
 
 int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float* d_logits, double* d_stats,
                    void* stream) {
@@ -854,11 +870,7 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
     const uint64_t rows = hi - lo;
     int blocks = (int)std::min<uint64_t>((rows + kEnergyThreads - 1) / kEnergyThreads, 148 * 8);
     blocks = std::max(blocks, 1);
-    if (g_sweep_partial_cap < blocks) {
-      if (g_sweep_partial) QHBM_CUDA(cudaFree(g_sweep_partial));
-      QHBM_CUDA(cudaMalloc(&g_sweep_partial, sizeof(Stat) * 148 * 8));
-      g_sweep_partial_cap = 148 * 8;
-    }
+    void* partial = sweep_scratch(s);  // per-CTA partial statistics
     if (e->kind == QHBM_ENERGY_MLP && e->n_layers >= 2 && rows >= 4096) {
       // register-tiled dense-stack kernel: weights + one [64][128] activation buffer in shared memory
       const size_t msmem = ((mlp_sweep_weight_floats(*e) * sizeof(float) + 15) & ~(size_t)15) +
@@ -866,12 +878,12 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
       QHBM_CUDA(cudaFuncSetAttribute(ebm_mlp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
       const uint64_t ntiles = (hi - 1) / kMlpRows - lo / kMlpRows + 1;
       blocks = (int)std::min<uint64_t>(ntiles, 148 * 3);
-      ebm_mlp_sweep_kernel<<<blocks, kMlpThreads, msmem, s>>>(ea, lo, hi, d_logits, (Stat*)g_sweep_partial);
+      ebm_mlp_sweep_kernel<<<blocks, kMlpThreads, msmem, s>>>(ea, lo, hi, d_logits, (Stat*)partial);
     } else {
       QHBM_CUDA(cudaFuncSetAttribute(ebm_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      ebm_sweep_kernel<<<blocks, kEnergyThreads, smem, s>>>(ea, lo, hi, d_logits, (Stat*)g_sweep_partial);
+      ebm_sweep_kernel<<<blocks, kEnergyThreads, smem, s>>>(ea, lo, hi, d_logits, (Stat*)partial);
     }
-    stat_final_kernel<<<1, 256, 0, s>>>((const Stat*)g_sweep_partial, blocks, d_stats);
+    stat_final_kernel<<<1, 256, 0, s>>>((const Stat*)partial, blocks, d_stats);
     QHBM_CUDA(cudaGetLastError());
   });
 }

@@ -74,11 +74,8 @@ namespace {
 
 template <int K, bool ADJ>
 void launch_sweep(const KernelArgs& ka, int n_states, int tiles, int threads, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  // per-device, per-function attribute; setting it on every launch keeps the library free of global state
+  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sweep_kernel<K, ADJ><<<(unsigned)(n_states * tiles), threads, smem, s>>>(ka);
   QHBM_CUDA(cudaGetLastError());
 }

@@ -351,3 +351,33 @@ def test_empty_batch_and_empty_circuit():
   np.testing.assert_allclose(e, [[2.0, 0.0], [1.0, 0.0], [1.0, 0.0]], atol=1e-6)
   e0 = plan.forward(basis[:0], torch.zeros(0, device="cuda"))
   assert tuple(e0.shape) == (0, 2)
+
+
+def test_plan_lifecycle_does_not_leak_device_memory():
+  """Creating, running and destroying many plans returns the device memory they took (handles own
+  their workspace; nothing is cached per call)."""
+  import gc
+  from qhbmlib import engine
+  n = 13
+  gates, names = orc.hea_circuit(n, 2)
+  terms, offs = hp.ops_to_tables([orc.tfim_ring(n)], n)
+  phi = torch.zeros(len(names), device="cuda")
+  basis = torch.arange(64, dtype=torch.int64, device="cuda")
+  dg = torch.ones((64, 1), device="cuda")
+
+  def cycle():
+    plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, True)
+    plan.forward_adjoint(basis, phi, dg)
+    plan.final_states(basis[:4], phi)
+    del plan
+
+  cycle()
+  gc.collect()
+  torch.cuda.synchronize()
+  free0, _ = torch.cuda.mem_get_info()
+  for _ in range(40):
+    cycle()
+  gc.collect()
+  torch.cuda.synchronize()
+  free1, _ = torch.cuda.mem_get_info()
+  assert free0 - free1 < 8 << 20, (free0, free1)

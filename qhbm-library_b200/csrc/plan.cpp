@@ -756,6 +756,7 @@ class Compiler {
       StageRange sr;
       sr.grp_begin = (int32_t)hp_.groups.size();
       sr.term_begin = (int32_t)hp_.terms.size();
+      sr.rng_begin = (int32_t)hp_.opranges.size();
       for (int j = 0; j < o.n_ops(); ++j) {
         DevOpRange r;
         r.group_begin = (int32_t)hp_.groups.size();
@@ -804,8 +805,13 @@ class Compiler {
           hp_.groups.push_back(g);
         }
         r.group_end = (int32_t)hp_.groups.size();
-        hp_.opranges.push_back(r);
+        r.op = j;
+        r.pad = 0;
+        // observables without generic groups cost nothing in the kernel; the single observable of a
+        // stage with observable passes keeps its (possibly empty) range: the phase finishes E and lambda
+        if (r.group_end > r.group_begin || !hcands.empty()) hp_.opranges.push_back(r);
       }
+      sr.rng_end = (int32_t)hp_.opranges.size();
       sr.grp_end = (int32_t)hp_.groups.size();
       sr.term_end = (int32_t)hp_.terms.size();
       stage_ranges_.push_back(sr);
@@ -814,7 +820,7 @@ class Compiler {
   }
 
   struct StageRange {
-    int32_t grp_begin = 0, grp_end = 0, term_begin = 0, term_end = 0;
+    int32_t grp_begin = 0, grp_end = 0, term_begin = 0, term_end = 0, rng_begin = 0, rng_end = 0;
   };
 
   struct HCand {
@@ -996,6 +1002,8 @@ class Compiler {
       L.grp_end = stage_ranges_[st].grp_end;
       L.term_begin = stage_ranges_[st].term_begin;
       L.term_end = stage_ranges_[st].term_end;
+      L.rng_begin = stage_ranges_[st].rng_begin;
+      L.rng_end = stage_ranges_[st].rng_end;
     };
     if (hp_.n_eff <= hp_.T) {
       // whole state in one tile: one launch does forward, expectation and backward

@@ -109,7 +109,8 @@ struct LaunchDesc {
   BitRun oruns[kMaxRuns];            // tile-id bits -> state bits (the out-of-tile bits)
   uint32_t tile_mask;                // state-index bits covered by the tile
   int32_t pass_h_begin, pass_h_end;  // observable passes run at the start of the expectation phase
-  int32_t expect_stage;              // LF_EXPECT: which stage's tables (opranges[stage * O + j]) this launch uses
+  int32_t expect_stage;              // LF_EXPECT: which stage's tables this launch uses
+  int32_t rng_begin, rng_end;        // its slice of the observable ranges (DevOpRange)
   int32_t grp_begin, grp_end;        // that stage's slice of the group / term tables (staged in shared memory)
   int32_t term_begin, term_end;
   // the thread's m-th tile element is local index (m << (T-K)) | tid:
@@ -132,8 +133,9 @@ struct DevTermGroup {  // terms sharing one x-mask: H psi[i] += coefficient(i) *
   int32_t is_complex;  // some term has an imaginary coefficient (odd number of Y)
   int32_t pad;
 };
-struct DevOpRange {
-  int32_t group_begin, group_end;
+struct DevOpRange {  // the x-groups of one observable in one expectation stage; only observables
+  int32_t group_begin, group_end;  // that have generic groups (or observable passes to finish) get one
+  int32_t op, pad;
 };
 // Diagonal (Z-string) term evaluated through a Walsh-Hadamard transform of |psi|^2 (many-shard case)
 struct DevDiagTerm {

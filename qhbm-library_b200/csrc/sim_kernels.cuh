@@ -845,7 +845,6 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
   // stage this launch's slice of the Pauli tables (group headers: 2 float4 each, terms: 1 float4 each)
   const DevTermGroup* groups = ka.groups;
   const DevTerm* terms = ka.terms;
-  const DevOpRange* opranges = ka.opranges + (size_t)ka.L.expect_stage * ka.O;
   {
     const int ng = ka.L.grp_end - ka.L.grp_begin, nt = ka.L.term_end - ka.L.term_begin;
     if (2 * ng + nt <= 2 * kStageOps + kStageCoef / 4) {
@@ -880,7 +879,9 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
         dg[m] = wht ? dgall[m0 + m] : 0.f;  // m0 is a constant after unrolling the chunk loop
       }
     }
-    for (int j = 0; j < ka.O; ++j) {
+    for (int ri = ka.L.rng_begin; ri < ka.L.rng_end; ++ri) {
+      const int4 orng = __ldg(reinterpret_cast<const int4*>(ka.opranges + ri));
+      const int j = orng.z;
       const float gj = want_lam ? __ldg(&ka.dgrad[(size_t)u * ka.O + j]) : 0.f;
       float ej = 0.f;
       float2 h[MC];
@@ -892,8 +893,8 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
           for (int m = 0; m < MC; ++m) h[m] = s_lam[ph_tid ^ ka.L.soff[m0 + m]];
         }
       }
-      const int g_end = __ldg(&opranges[j].group_end);
-      int g = __ldg(&opranges[j].group_begin);
+      const int g_end = orng.y;
+      int g = orng.x;
       int4 gh, gk;
       if (g < g_end) {
         gh = reinterpret_cast<const int4*>(groups + g)[0];

@@ -339,10 +339,11 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
           tl[l] += g0 * th[l];
         }
       }
-      for (int j = 0; j < hp.O; ++j) {
+      for (int ri = L.rng_begin; ri < L.rng_end; ++ri) {
+        const DevOpRange& orng = hp.opranges[ri];
+        const int j = orng.op;
         const double gj = (adjoint && c.dgrad) ? c.dgrad[j] : 0.0;
         double ej = 0;
-        const DevOpRange& orng = hp.opranges[(size_t)L.expect_stage * hp.O + j];
         for (int g = orng.group_begin; g < orng.group_end; ++g) {
           if (g < L.grp_begin || g >= L.grp_end) throw std::runtime_error("group outside the launch's stage slice");
           const DevTermGroup& G = hp.groups[g];

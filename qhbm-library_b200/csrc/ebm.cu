@@ -573,6 +573,100 @@ __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------ parity-energy sweep, Walsh-Hadamard tiles
+// E(i) = sum_t theta_t (-1)^{parity(i & mask_t)}.  Inside a tile of 256 consecutive rows only the low
+// 8 index bits vary, so E restricted to the tile is the 256-point Walsh-Hadamard transform of the
+// sparse vector c[m] = sum over the terms whose low mask byte is m of theta_t (-1)^{parity(hi & mask_t)}.
+// Per tile: every term is touched once (not once per row) and the transform costs 8 butterflies per
+// row.  Bucket sums run in term order, so results do not depend on scheduling (seeded sampling from
+// the logits stays exactly repeatable).
+constexpr int kParThreads = 256;
+
+__global__ void __launch_bounds__(kParThreads) ebm_parity_sweep_kernel(const __grid_constant__ EnergyArgs ea, uint64_t lo,
+                                                                       uint64_t hi, float* __restrict__ logits,
+                                                                       Stat* __restrict__ partial) {
+  extern __shared__ __align__(16) float s_f[];
+  __shared__ Stat s_st[kParThreads / 32];
+  __shared__ int s_start[kParThreads + 1];
+  __shared__ float s_x[kParThreads];
+  const qhbm_energy_desc_t& d = ea.d;
+  const int nt = d.n_terms;
+  const int tid = threadIdx.x;
+  float* s_theta = s_f;
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_f + nt);
+  int* s_order = reinterpret_cast<int*>(s_f + 2 * nt);
+  for (int i = tid; i < nt; i += kParThreads) {
+    s_theta[i] = d.d_theta[i];
+    s_mask[i] = d.d_masks[i];
+  }
+  __syncthreads();
+  // terms grouped by the low byte of their mask, in term order inside a group (stable, deterministic)
+  {
+    int cnt = 0;
+    for (int t = 0; t < nt; ++t) cnt += (int)(s_mask[t] & 255u) == tid;
+    s_x[tid] = __int_as_float(cnt);
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int b = 0; b < kParThreads; ++b) {
+        s_start[b] = run;
+        run += __float_as_int(s_x[b]);
+      }
+      s_start[kParThreads] = run;
+    }
+    __syncthreads();
+    int pos = s_start[tid];
+    for (int t = 0; t < nt; ++t)
+      if ((int)(s_mask[t] & 255u) == tid) s_order[pos++] = t;
+    __syncthreads();
+  }
+  const int k0 = s_start[tid], k1 = s_start[tid + 1];
+  const uint64_t t_first = lo >> 8, t_last = (hi - 1) >> 8;
+  Stat acc_st;
+  acc_st.m = 0.0; acc_st.s = 0.0; acc_st.t = 0.0;
+  for (uint64_t tile = t_first + blockIdx.x; tile <= t_last; tile += gridDim.x) {
+    const uint32_t hbits = (uint32_t)(tile << 8);  // parity energies have at most 32 bits
+    float c = 0.f;
+    for (int k = k0; k < k1; ++k) {
+      const int t = s_order[k];
+      const uint32_t sgn = (uint32_t)(__popc(hbits & s_mask[t]) & 1) << 31;
+      c += __uint_as_float(__float_as_uint(s_theta[t]) ^ sgn);
+    }
+    // 256-point Walsh-Hadamard transform: bits 0-4 by shuffles, bits 5-7 through shared memory
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      const float o = __shfl_xor_sync(0xffffffffu, c, 1 << b);
+      c = (tid & (1 << b)) ? o - c : c + o;
+    }
+#pragma unroll
+    for (int b = 5; b < 8; ++b) {
+      __syncthreads();
+      s_x[tid] = c;
+      __syncthreads();
+      const float o = s_x[tid ^ (1 << b)];
+      c = (tid & (1 << b)) ? o - c : c + o;
+    }
+    const uint64_t row = (tile << 8) | (uint64_t)tid;
+    if (row >= lo && row < hi) {
+      const float lg = -c;
+      if (logits) logits[row - lo] = lg;
+      Stat one;
+      one.m = (double)lg; one.s = 1.0; one.t = (double)lg;
+      acc_st = stat_merge(acc_st, one);
+    }
+  }
+  acc_st = stat_warp(acc_st);
+  if ((tid & 31) == 0) s_st[tid >> 5] = acc_st;
+  __syncthreads();
+  if (tid < 32) {
+    Stat v;
+    v.m = 0.0; v.s = 0.0; v.t = 0.0;
+    if (tid < kParThreads / 32) v = s_st[tid];
+    v = stat_warp(v);
+    if (tid == 0) partial[blockIdx.x] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) stat_final_kernel(const Stat* __restrict__ partial, int n, double* __restrict__ out) {
   __shared__ Stat s_st[8];
   Stat acc;
@@ -879,6 +973,13 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
       const uint64_t ntiles = (hi - 1) / kMlpRows - lo / kMlpRows + 1;
       blocks = (int)std::min<uint64_t>(ntiles, 148 * 3);
       ebm_mlp_sweep_kernel<<<blocks, kMlpThreads, msmem, s>>>(ea, lo, hi, d_logits, (Stat*)partial);
+    } else if (e->kind != QHBM_ENERGY_MLP && rows >= 4096 && (size_t)e->n_terms * 12 <= 200 * 1024) {
+      // Walsh-Hadamard tiles of 256 rows: theta, masks and the bucket order in shared memory
+      const size_t psmem = (size_t)std::max(e->n_terms, 1) * 12;
+      QHBM_CUDA(cudaFuncSetAttribute(ebm_parity_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      const uint64_t ntiles = ((hi - 1) >> 8) - (lo >> 8) + 1;
+      blocks = (int)std::min<uint64_t>(ntiles, 148 * 8);
+      ebm_parity_sweep_kernel<<<blocks, kParThreads, psmem, s>>>(ea, lo, hi, d_logits, (Stat*)partial);
     } else {
       QHBM_CUDA(cudaFuncSetAttribute(ebm_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       ebm_sweep_kernel<<<blocks, kEnergyThreads, smem, s>>>(ea, lo, hi, d_logits, (Stat*)partial);

@@ -340,6 +340,20 @@ __device__ __forceinline__ Stat stat_merge(Stat a, Stat b) {
   r.t = a.t * fa + b.t * fb;
   return r;
 }
+// one more logit: a single exp instead of the two of a general merge
+__device__ __forceinline__ void stat_add(Stat& a, double l) {
+  if (a.s == 0.0) { a.m = l; a.s = 1.0; a.t = l; return; }
+  if (l <= a.m) {
+    const double w = exp(l - a.m);
+    a.s += w;
+    a.t = fma(w, l, a.t);
+  } else {
+    const double f = exp(a.m - l);
+    a.s = fma(a.s, f, 1.0);
+    a.t = fma(a.t, f, l);
+    a.m = l;
+  }
+}
 __device__ __forceinline__ Stat stat_warp(Stat v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -363,9 +377,7 @@ __global__ void __launch_bounds__(kEnergyThreads) ebm_sweep_kernel(const __grid_
   for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
     const float l = -eval_energy(ea, s_f, i);
     if (logits) logits[i - lo] = l;
-    Stat one;
-    one.m = (double)l; one.s = 1.0; one.t = (double)l;
-    acc = stat_merge(acc, one);
+    stat_add(acc, (double)l);
   }
   acc = stat_warp(acc);
   if ((threadIdx.x & 31) == 0) s_st[threadIdx.x >> 5] = acc;
@@ -555,9 +567,7 @@ __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid
       if (row >= lo && row < hi) {
         const float lg = -mlp_act((e0 + e1) + (e2 + e3), d.act[l]);
         if (logits) logits[row - lo] = lg;
-        Stat one;
-        one.m = (double)lg; one.s = 1.0; one.t = (double)lg;
-        acc_st = stat_merge(acc_st, one);
+        stat_add(acc_st, (double)lg);
       }
     }
   }
@@ -621,16 +631,40 @@ __global__ void __launch_bounds__(kParThreads) ebm_parity_sweep_kernel(const __g
     __syncthreads();
   }
   const int k0 = s_start[tid], k1 = s_start[tid + 1];
+  const int n_b0 = s_start[1];  // bucket 0 occupies order[0 .. n_b0)
   const uint64_t t_first = lo >> 8, t_last = (hi - 1) >> 8;
   Stat acc_st;
   acc_st.m = 0.0; acc_st.s = 0.0; acc_st.t = 0.0;
   for (uint64_t tile = t_first + blockIdx.x; tile <= t_last; tile += gridDim.x) {
     const uint32_t hbits = (uint32_t)(tile << 8);  // parity energies have at most 32 bits
     float c = 0.f;
-    for (int k = k0; k < k1; ++k) {
-      const int t = s_order[k];
-      const uint32_t sgn = (uint32_t)(__popc(hbits & s_mask[t]) & 1) << 31;
-      c += __uint_as_float(__float_as_uint(s_theta[t]) ^ sgn);
+    if (tid != 0) {
+      for (int k = k0; k < k1; ++k) {
+        const int t = s_order[k];
+        const uint32_t sgn = (uint32_t)(__popc(hbits & s_mask[t]) & 1) << 31;
+        c += __uint_as_float(__float_as_uint(s_theta[t]) ^ sgn);
+      }
+    }
+    // bucket 0 (terms that do not touch the low byte: most of them) is summed by the whole CTA in a
+    // fixed order: strided partials, shuffle tree, then the eight warp sums
+    {
+      float p0 = 0.f;
+      for (int k = tid; k < n_b0; k += kParThreads) {
+        const int t = s_order[k];
+        const uint32_t sgn = (uint32_t)(__popc(hbits & s_mask[t]) & 1) << 31;
+        p0 += __uint_as_float(__float_as_uint(s_theta[t]) ^ sgn);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+      __syncthreads();  // previous tile's last exchange is read
+      if ((tid & 31) == 0) s_x[tid >> 5] = p0;
+      __syncthreads();
+      if (tid == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kParThreads / 32; ++w) sum += s_x[w];
+        c = sum;
+      }
     }
     // 256-point Walsh-Hadamard transform: bits 0-4 by shuffles, bits 5-7 through shared memory
 #pragma unroll
@@ -650,9 +684,7 @@ __global__ void __launch_bounds__(kParThreads) ebm_parity_sweep_kernel(const __g
     if (row >= lo && row < hi) {
       const float lg = -c;
       if (logits) logits[row - lo] = lg;
-      Stat one;
-      one.m = (double)lg; one.s = 1.0; one.t = (double)lg;
-      acc_st = stat_merge(acc_st, one);
+      stat_add(acc_st, (double)lg);
     }
   }
   acc_st = stat_warp(acc_st);

@@ -121,6 +121,30 @@ def test_kobe_sweep_against_oracle(n, order):
   np.testing.assert_allclose(er, e_ref[keys.cpu().numpy()], rtol=1e-5, atol=atol)
 
 
+@pytest.mark.parametrize("n,order,lo,hi", [(14, 3, 1000, 13001), (13, 1, 77, 8000), (16, 2, 3 * 4096 + 5, 5 * 4096 + 3),
+                                           (12, 12, 0, 4096)])
+def test_parity_sweep_tiled_kernel_edge_cases(n, order, lo, hi):
+  """The Walsh-Hadamard tiled sweep (>= 4096 rows) on ranges that do not align with its 256-row tiles,
+  for single-Z (Bernoulli-like), order-3 and full-order term sets; repeated runs are bit-identical."""
+  rng = np.random.default_rng(n * 10 + order)
+  thetas = rng.normal(0, 0.3, len(orc.parity_indices(n, order))).astype(np.float32)
+  if order == 12:
+    thetas[rng.random(len(thetas)) < 0.9] = 0.0  # keep the fp32 sum of 4095 terms well conditioned
+  d = _kobe_desc(n, order, thetas)
+  logits, stats = d.sweep(lo, hi)
+  e_ref = orc.kobe_energy(orc.all_bitstrings(n)[lo:hi], order, thetas)
+  atol = 2e-6 * float(np.abs(thetas).sum()) + 1e-6
+  np.testing.assert_allclose(-logits.cpu().numpy(), e_ref, rtol=1e-5, atol=atol)
+  m, s, t = stats.cpu().numpy()
+  np.testing.assert_allclose(m + np.log(s), orc.analytic_log_partition(e_ref), rtol=1e-6, atol=atol)
+  np.testing.assert_allclose(m + np.log(s) - t / s, orc.analytic_entropy(e_ref), rtol=1e-5, atol=atol)
+  logits2, stats2 = d.sweep(lo, hi)
+  assert torch.equal(logits, logits2)
+  # rows evaluated one by one (per-row kernel) agree with the tiled sweep
+  keys = torch.arange(lo, min(hi, lo + 3000), device="cuda")
+  np.testing.assert_allclose(d.energies(keys).cpu().numpy(), -logits[:len(keys)].cpu().numpy(), rtol=1e-5, atol=atol)
+
+
 def test_mlp_energy_sweep_against_oracle():
   """Dense(64,tanh)->Dense(64,tanh)->Dense(1) on raw bits (ebm_utils_test.py:33-47 family)."""
   eng = _eng()

@@ -352,7 +352,7 @@ def run_gpu(args, cfg):
                              "not skipped work (see profiles/ for dram bytes and smem throughput)"},
         "e2e": {"value": e2e_value, "unit": "bitstrings/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "last_loss": loss},
-        "gpu_launches": sweep_launches + 4,
+        "gpu_launches": sweep_launches + 3,  # + prep (incl. accumulator clears), finalize, weighted sum
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

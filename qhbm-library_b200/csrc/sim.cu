@@ -137,11 +137,16 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
   ka.phase_coef = hp.phase_coef;
 }
 
-void run_prep(qhbm_plan* p, const float* d_symbols, int mode, cudaStream_t s) {
+// Coefficient jobs + clearing of the call's float64 accumulators in one launch.
+void run_prep(qhbm_plan* p, const float* d_symbols, int mode, cudaStream_t s, double* zero_a = nullptr,
+              int64_t n_a = 0, double* zero_b = nullptr, int64_t n_b = 0) {
   const HostPlan& hp = p->hp;
-  if (hp.jobs.empty()) return;
-  prep_kernel<<<(unsigned)hp.jobs.size(), kPrepThreads, 0, s>>>(p->d_jobs.p, p->d_lists.p, p->d_gates.p,
-                                                                d_symbols, p->d_coef.p, mode);
+  const int n_jobs = (int)hp.jobs.size();
+  const int64_t nz = n_a + n_b;
+  const int zero_blocks = nz > 0 ? (int)std::min<int64_t>((nz + kPrepThreads - 1) / kPrepThreads, 148 * 4) : 0;
+  if (n_jobs + zero_blocks == 0) return;
+  prep_kernel<<<(unsigned)(n_jobs + zero_blocks), kPrepThreads, 0, s>>>(p->d_jobs.p, n_jobs, p->d_lists.p, p->d_gates.p,
+                                                                       d_symbols, p->d_coef.p, mode, zero_a, n_a, zero_b, n_b);
   QHBM_CUDA(cudaGetLastError());
 }
 
@@ -172,9 +177,7 @@ void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const flo
     if (adjoint) p->d_lam.reserve((size_t)chunk << hp.n_eff);
     if (adjoint && pingpong) p->d_psi_alt.reserve((size_t)chunk << hp.n_eff);
   }
-  run_prep(p, d_symbols, mode, s);
-  QHBM_CUDA(cudaMemsetAsync(p->d_eacc.p, 0, sizeof(double) * U * hp.O, s));
-  if (grows && hp.P > 0) QHBM_CUDA(cudaMemsetAsync(p->d_gacc.p, 0, sizeof(double) * grows * hp.P, s));
+  run_prep(p, d_symbols, mode, s, p->d_eacc.p, U * hp.O, p->d_gacc.p, (grows && hp.P > 0) ? grows * hp.P : 0);
 
   KernelArgs ka;
   fill_common(p, ka);
@@ -207,14 +210,11 @@ void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const flo
     }
   }
   {
-    const int64_t ne = U * hp.O;
-    finalize_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(p->d_eacc.p, d_out, ne);
-    QHBM_CUDA(cudaGetLastError());
-  }
-  if (grows && hp.P > 0) {
-    const int64_t ng = grows * hp.P;
-    finalize_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, s>>>(p->d_gacc.p, d_grad_out, ng);
-    QHBM_CUDA(cudaGetLastError());
+    const int64_t ne = U * hp.O, ng = (grows && hp.P > 0) ? grows * hp.P : 0;
+    if (ne + ng > 0) {
+      finalize_kernel<<<(unsigned)((ne + ng + 255) / 256), 256, 0, s>>>(p->d_eacc.p, d_out, ne, p->d_gacc.p, d_grad_out, ng);
+      QHBM_CUDA(cudaGetLastError());
+    }
   }
 }
 

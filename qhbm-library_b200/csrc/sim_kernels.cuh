@@ -1070,11 +1070,23 @@ __device__ __forceinline__ void write_c(float* out, int i, cd v) {
 constexpr int kPrepThreads = 128;
 constexpr int kPrepBatch = 64;
 
-__global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __restrict__ jobs,
+// CTAs [0, n_jobs) run one coefficient job each; the CTAs after them clear the float64 accumulators of
+// the call (so a call needs no separate memsets).
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __restrict__ jobs, int n_jobs,
                                                             const int32_t* __restrict__ lists,
                                                             const qhbm_gate_t* __restrict__ gates,
                                                             const float* __restrict__ symbols,
-                                                            float* __restrict__ coef, int mode) {
+                                                            float* __restrict__ coef, int mode,
+                                                            double* __restrict__ zero_a, int64_t n_a,
+                                                            double* __restrict__ zero_b, int64_t n_b) {
+  if ((int)blockIdx.x >= n_jobs) {
+    const int64_t stride = (int64_t)(gridDim.x - n_jobs) * kPrepThreads;
+    for (int64_t i = (int64_t)(blockIdx.x - n_jobs) * kPrepThreads + threadIdx.x; i < n_a + n_b; i += stride) {
+      if (i < n_a) zero_a[i] = 0.0;
+      else zero_b[i - n_a] = 0.0;
+    }
+    return;
+  }
   const PrepJob job = jobs[blockIdx.x];
   const int32_t* list = lists + job.list_off;
   float* out = coef + job.out;
@@ -1234,9 +1246,12 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __res
   }
 }
 
-__global__ void finalize_kernel(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+// float64 accumulators -> the caller's float32 outputs (expectations and, if present, gradients)
+__global__ void finalize_kernel(const double* __restrict__ src_a, float* __restrict__ dst_a, int64_t n_a,
+                                const double* __restrict__ src_b, float* __restrict__ dst_b, int64_t n_b) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = (float)src[i];
+  if (i < n_a) dst_a[i] = (float)src_a[i];
+  else if (i < n_a + n_b) dst_b[i - n_a] = (float)src_b[i - n_a];
 }
 
 }  // namespace qhbm

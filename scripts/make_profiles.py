@@ -50,7 +50,7 @@ with open("profiles/r1_bench_launches.md", "w") as f:
     if "sweep_kernel" not in d["name"]:
       names[d["name"][:70]] += d["ns"]
   f.write("Share of all GPU time in the run by kernel (the kernel's share of the step agrees with bench.py's "
-          "`gpu_launches`: 4 sweep launches + prep + 2 finalize + weighted sum):\n\n| kernel | total ms | share |\n|---|---|---|\n")
+          "`gpu_launches`: 4 sweep launches + prep + finalize + weighted sum):\n\n| kernel | total ms | share |\n|---|---|---|\n")
   f.write(f"| qhbm::sweep_kernel<4,true> | {sum(d['ns'] for d in sw) / 1e6:.2f} | {100 * sum(d['ns'] for d in sw) / tot_all:.1f}% |\n")
   for n, v in names.most_common(6):
     f.write(f"| {n} | {v / 1e6:.3f} | {100 * v / tot_all:.2f}% |\n")

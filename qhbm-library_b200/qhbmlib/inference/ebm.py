@@ -178,6 +178,23 @@ class EnergyInferenceBase(torch.nn.Module, abc.ABC):
   def sample(self, num_samples):
     return self._sample(num_samples)
 
+  @preface_inference
+  def unique_samples(self, num_samples):
+    """(unique bitstrings int8 [U, n] in first-occurrence order, idx int32 [N], counts int32 [U]) of
+    `num_samples` fresh samples -- the same draw `sample` would return (same seed step).  Engines
+    that sample packed keys (`_sample_keys`) never materialise the int8 [N, n] tensor here."""
+    keys = self._sample_keys(num_samples)
+    if keys is None:
+      return utils.unique_bitstrings_with_counts(self._sample(num_samples).detach())
+    n = self.energy.num_bits
+    uniq, idx, count = engine.unique_with_counts(keys)
+    return engine.unpack_bits(uniq, n, utils._natural_shifts(n)), idx, count
+
+  def _sample_keys(self, num_samples):
+    """Packed uint64 keys (bit n-1-j of the key = column j) of `num_samples` samples, or None."""
+    del num_samples
+    return None
+
   @abc.abstractmethod
   def _call(self, inputs, *args, **kwargs):
     raise NotImplementedError()
@@ -215,8 +232,7 @@ class EnergyInference(EnergyInferenceBase):
   def _expectation(self, function):
     """Sample average; d/dtheta = E[c]E[dE] - E[c dE] + E[d function] (reference ebm.py:282-325),
     realised by adding a zero-valued surrogate whose gradient is the covariance term."""
-    samples = self.sample(self.num_expectation_samples).detach()
-    bitstrings, _, counts = utils.unique_bitstrings_with_counts(samples)
+    bitstrings, _, counts = self.unique_samples(self.num_expectation_samples)
     values = function(bitstrings)
     average_of_values = map_structure(lambda x: utils.weighted_average(counts, x), values)
     if not self._energy_needs_grad():
@@ -238,8 +254,7 @@ class EnergyInference(EnergyInferenceBase):
     result = self._log_partition_forward_pass().detach()
     if not self._energy_needs_grad():
       return result
-    samples = self.sample(self.num_expectation_samples).detach()
-    unique_samples, _, counts = utils.unique_bitstrings_with_counts(samples)
+    unique_samples, _, counts = self.unique_samples(self.num_expectation_samples)
     unique_energies = self.energy(unique_samples)
     surrogate = -utils.weighted_average(counts, unique_energies)
     return result + (surrogate - surrogate.detach())
@@ -388,10 +403,12 @@ class AnalyticEnergyInference(EnergyInference):
     m, s, _ = self._stats.tolist()
     return torch.tensor(m + math.log(s), dtype=torch.float32, device=self.device)
 
+  def _sample_keys(self, num_samples):
+    return engine.categorical_sample(self._logits, int(num_samples), self.seed)  # row index IS the key
+
   def _sample(self, num_samples):
     n = self.energy.num_bits
-    rows = engine.categorical_sample(self._logits, int(num_samples), self.seed)
-    return engine.unpack_bits(rows, n, utils._natural_shifts(n))
+    return engine.unpack_bits(self._sample_keys(num_samples), n, utils._natural_shifts(n))
 
 
 class Bernoulli:
@@ -442,11 +459,16 @@ class BernoulliEnergyInference(EnergyInference):
     thetas = 0.5 * self._logits
     return torch.sum(torch.log(torch.exp(thetas) + torch.exp(-thetas)))
 
+  def _keys_with(self, num_samples, seed):
+    shifts = utils._natural_shifts(self.energy.num_bits)
+    return engine.bernoulli_sample(self._logits.contiguous(), shifts, int(num_samples), sanitize_seed(seed))
+
+  def _sample_keys(self, num_samples):
+    return self._keys_with(num_samples, self.seed)
+
   def _sample_with(self, num_samples, seed):
     n = self.energy.num_bits
-    shifts = utils._natural_shifts(n)
-    keys = engine.bernoulli_sample(self._logits.contiguous(), shifts, int(num_samples), sanitize_seed(seed))
-    return engine.unpack_bits(keys, n, shifts)
+    return engine.unpack_bits(self._keys_with(num_samples, seed), n, utils._natural_shifts(n))
 
   def _sample(self, num_samples):
     return self._sample_with(num_samples, self.seed)

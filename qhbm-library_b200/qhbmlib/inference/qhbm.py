@@ -35,8 +35,10 @@ class QHBM(torch.nn.Module):
 
   def circuits(self, num_samples):
     """(CircuitBatch of U_phi|x_i> for the unique sampled x_i, int32 counts)."""
-    samples = self.e_inference.sample(num_samples)
-    bitstrings, _, counts = utils.unique_bitstrings_with_counts(samples)
+    if hasattr(self.e_inference, "unique_samples"):
+      bitstrings, _, counts = self.e_inference.unique_samples(num_samples)
+    else:
+      bitstrings, _, counts = utils.unique_bitstrings_with_counts(self.e_inference.sample(num_samples))
     states = self.q_inference.circuit(bitstrings)
     return states, counts
 

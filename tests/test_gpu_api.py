@@ -513,3 +513,72 @@ def test_single_observable_jacobian_in_forward_matches_resimulation():
   with torch.no_grad():
     quiet = q_infer.expectation(bitstrings, ham)
   np.testing.assert_allclose(quiet.cpu().numpy(), outs[0], rtol=1e-5, atol=1e-5)
+
+
+def test_expectation_nested_structure_and_energy_gradient():
+  """tests/inference/ebm_test.py:test_expectation_finite_difference: a function with nested outputs
+  (scalar, vector, a list holding a tensor that itself depends on the energy variable); value and
+  d/d theta of the summed outputs against the exact distribution (the reference compares with
+  sampled finite differences)."""
+  num_bits, order, num_samples = 3, 2, int(2e6)
+  energy = models.KOBE(list(range(num_bits)), order, energy_utils.RandomUniform(1, 2, seed=7))
+  energy.to(DEV)
+  e_infer = inference.AnalyticEnergyInference(energy, num_samples, initial_seed=[5, 6])
+  theta = energy.trainable_variables[0]
+  gen = torch.Generator().manual_seed(3)
+  scalar_var = torch.nn.Parameter((1 + torch.rand((), generator=gen)).to(DEV))
+  dense = torch.nn.Linear(num_bits, 5).to(DEV)
+  with torch.no_grad():
+    dense.weight.copy_((1 + torch.rand(5, num_bits, generator=gen)).to(DEV))
+    dense.bias.copy_((1 + torch.rand(5, generator=gen)).to(DEV))
+
+  def f(bitstrings):
+    reduced = bitstrings.float().sum(1)
+    return [scalar_var * reduced, dense(bitstrings.float()), [torch.einsum("i,j->ij", reduced, theta)]]
+
+  actual = e_infer.expectation(f)
+  assert tuple(actual[0].shape) == () and tuple(actual[1].shape) == (5,) and tuple(actual[2][0].shape) == (6,)
+  total = actual[0] + actual[1].sum() + actual[2][0].sum()
+  (g_actual,) = torch.autograd.grad(total, theta)
+
+  all_bits = _bits(list(itertools.product([0, 1], repeat=num_bits)))
+  probs = torch.softmax(-energy(all_bits).double(), 0)
+  exact = [torch.tensordot(probs, v.double(), dims=([0], [0])) for v in (f(all_bits)[0], f(all_bits)[1], f(all_bits)[2][0])]
+  exact_total = exact[0] + exact[1].sum() + exact[2].sum()
+  (g_exact,) = torch.autograd.grad(exact_total, theta)
+  for a, e in zip((actual[0], actual[1], actual[2][0]), exact):
+    assert float(e.abs().min()) > 1e-3
+    np.testing.assert_allclose(a.detach().cpu().numpy(), e.detach().cpu().numpy(), rtol=5e-3)
+  assert float(g_exact.abs().min()) > 1e-3
+  np.testing.assert_allclose(g_actual.cpu().numpy(), g_exact.cpu().numpy(), rtol=3e-2, atol=5e-3)
+
+
+def test_qhbm_circuit_param_update():
+  """tests/inference/qhbm_test.py:test_circuit_param_update: expectations follow in-place updates of
+  the circuit variables (compiled plans keep no symbol values)."""
+  n = 3
+  qubits, qhbm = _random_qhbm(n, 2, 11, 50_000, ebm_seed=[3, 4])
+  ops = cq.convert_to_tensor([arch.tfim_ring(qubits)])
+  circ = qhbm.q_inference.circuit
+  bits = orc.all_bitstrings(n)
+  oracle_ops = [[(t.coefficient.real, {qubits.index(q): pp for q, pp in t.paulis.items()}) for t in s.terms]
+                for s in ops.pauli_sums]
+  bitstrings = _bits(bits.tolist())
+
+  def reference():
+    return orc.expectations(circ.gate_table().astype(orc.GATE_DTYPE), n, circ.symbol_values.detach().cpu().numpy(),
+                            orc.bitstrings_to_index(bits), oracle_ops)
+
+  before = qhbm.q_inference.expectation(bitstrings, ops).detach().cpu().numpy()
+  np.testing.assert_allclose(before, reference(), rtol=1e-5, atol=1e-5)
+  with torch.no_grad():
+    for p in circ.parameters():
+      p.add_(0.37)
+  after = qhbm.q_inference.expectation(bitstrings, ops).detach().cpu().numpy()
+  np.testing.assert_allclose(after, reference(), rtol=1e-5, atol=1e-5)
+  assert np.abs(after - before).max() > 1e-2
+  # and the QHBM-level estimate moves with it
+  est = qhbm.expectation(ops).detach().cpu().numpy()
+  th = qhbm.e_inference.energy.post_process[0].kernel.detach().cpu().numpy()
+  p = orc.analytic_probabilities(orc.kobe_energy(bits, n, th))
+  np.testing.assert_allclose(est, p @ reference(), atol=3e-2)

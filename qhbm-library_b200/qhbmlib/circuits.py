@@ -9,7 +9,6 @@ it to the C ABI's tables (include/qhbm_b200.h).  `from_cirq` converts real cirq 
 cirq is importable.
 """
 import functools
-import itertools
 import math
 import numbers
 

@@ -17,7 +17,6 @@ import torch
 from qhbmlib import _native as nat
 from qhbmlib import engine
 from qhbmlib import utils
-from qhbmlib.models import energy as energy_lib
 
 
 def preface_inference(f):

@@ -5,7 +5,6 @@ names and the layers that produce the symbol values.  Where the reference serial
 circuit per bitstring (`tfq.resolve_parameters` + `tfq.append_circuit`, circuit.py:129-136), this
 class emits the gate table once and a uint64 basis index per bitstring.
 """
-import numpy as np
 import torch
 
 from qhbmlib import circuits as cq

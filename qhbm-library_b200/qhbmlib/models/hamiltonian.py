@@ -2,7 +2,6 @@
 import torch
 
 from qhbmlib import circuits as cq
-from qhbmlib.models import circuit as circuit_lib
 from qhbmlib.models import energy as energy_lib
 
 

@@ -1,7 +1,6 @@
 """Development timing sweep over tile / register-qubit choices (not the contract bench)."""
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "qhbm-library_b200"), os.path.join(ROOT, "tests")):

@@ -21,7 +21,7 @@ constexpr int kMaxTileQubits = 14;
 constexpr int kMaxQubits = 30;
 constexpr int kConstGroupBits = 7;  // width of one "thread-constant" phase table
 constexpr int kMaxRuns = 16;
-constexpr int kStageOps = 96;      // ops of one pass staged in shared memory (else read from global)
+constexpr int kStageOps = 192;     // ops of one pass staged in shared memory (else read from global)
 constexpr int kStageCoef = 1792;   // floats of one pass's coefficients staged in shared memory
 
 enum OpType : int32_t {
@@ -71,6 +71,22 @@ struct DevOp {  // 32 bytes
   int32_t aux0, aux1;
   int32_t pad;
 };
+
+// Device form of a DevOp: 16 bytes, one shared-memory load per op.  type, p0, p1 and gslot are bytes
+// (-1 becomes 255; no kernel path tests them for sign).
+struct PackedOp {
+  uint32_t w0;  // type | p0 << 8 | p1 << 16 | gslot << 24
+  int32_t coef, aux0, aux1;
+};
+inline PackedOp pack_op(const DevOp& o) {
+  PackedOp q;
+  q.w0 = ((uint32_t)o.type & 0xffu) | (((uint32_t)o.p0 & 0xffu) << 8) | (((uint32_t)o.p1 & 0xffu) << 16) |
+         (((uint32_t)o.gslot & 0xffu) << 24);
+  q.coef = o.coef;
+  q.aux0 = o.aux0;
+  q.aux1 = o.aux1;
+  return q;
+}
 
 struct DevPass {  // 128 bytes
   int32_t regbit[kMaxRegQubits];     // tile-local bit of register position j

@@ -49,7 +49,7 @@ struct qhbm_ops {
 struct qhbm_plan {
   HostPlan hp;
   DevBuf<DevPass> d_passes;
-  DevBuf<DevOp> d_ops;
+  DevBuf<PackedOp> d_ops;
   DevBuf<int32_t> d_gsym;
   DevBuf<PrepJob> d_jobs;
   DevBuf<int32_t> d_lists;
@@ -329,7 +329,11 @@ int qhbm_plan_create(const qhbm_circuit_t* c, const qhbm_ops_t* o, int32_t with_
       p->hp = compile_plan(c->ir, o->ir, with_gradient != 0, tile_qubits, reg_qubits);
       const HostPlan& hp = p->hp;
       p->d_passes.upload(hp.passes);
-      p->d_ops.upload(hp.ops);
+      {
+        std::vector<PackedOp> packed(hp.ops.size());
+        for (size_t i = 0; i < hp.ops.size(); ++i) packed[i] = pack_op(hp.ops[i]);
+        p->d_ops.upload(packed);
+      }
       p->d_gsym.upload(hp.gsym);
       p->d_jobs.upload(hp.jobs);
       p->d_lists.upload(hp.lists);

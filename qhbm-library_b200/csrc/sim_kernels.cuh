@@ -22,7 +22,7 @@ namespace qhbm {
 struct KernelArgs {
   LaunchDesc L;
   const DevPass* passes;
-  const DevOp* ops;
+  const PackedOp* ops;
   const float* coef;
   const int32_t* gsym;
   const DevTerm* terms;
@@ -78,12 +78,11 @@ __device__ __forceinline__ float2 ldg2(const float* p) { return *reinterpret_cas
 struct OpRec {
   int type, p0, p1, coef, gslot, aux0, aux1;
 };
-__device__ __forceinline__ OpRec load_op(const DevOp* op) {
+__device__ __forceinline__ OpRec load_op(const PackedOp* op) {
   const int4 a = *reinterpret_cast<const int4*>(op);
-  const int4 b = reinterpret_cast<const int4*>(op)[1];
   OpRec r;
-  r.type = a.x; r.p0 = a.y; r.p1 = a.z; r.coef = a.w;
-  r.gslot = b.x; r.aux0 = b.y; r.aux1 = b.z;
+  r.type = a.x & 0xff; r.p0 = (a.x >> 8) & 0xff; r.p1 = (a.x >> 16) & 0xff; r.gslot = (int)((uint32_t)a.x >> 24);
+  r.coef = a.y; r.aux0 = a.z; r.aux1 = a.w;
   return r;
 }
 
@@ -303,7 +302,7 @@ __device__ __forceinline__ void compute_marginals(const float2 (&a)[1 << K], con
 
 template <int K>
 __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
-                                              const DevOp* __restrict__ ops, const int n_const, const int n_reg1,
+                                              const PackedOp* __restrict__ ops, const int n_const, const int n_reg1,
                                               const int count, const bool pairs, const float* __restrict__ coef,
                                               float* scratch, uint32_t gbase, uint32_t tid, uint32_t nthr) {
   OpRec nxt = load_op(ops);  // issued before the marginals so that its latency is covered
@@ -360,17 +359,17 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   const int op_begin = __ldg(&ps->op_begin), op_end = __ldg(&ps->op_end);
   const int cb = __ldg(&ps->coef_begin), ce = __ldg(&ps->coef_end);
   const bool staged = (op_end - op_begin) <= kStageOps && (ce - cb) <= kStageCoef;
-  const DevOp* ops_base = ka.ops;       // indexed by absolute op number
+  const PackedOp* ops_base = ka.ops;    // indexed by absolute op number
   const float* coef_base = ka.coef;     // indexed by absolute float offset
   __syncthreads();  // the previous pass (its tile stores and its staged program) is finished everywhere
   if (staged) {
-    float4* s_ops = s_stage;                       // kStageOps * 2 float4
-    float4* s_cf = s_stage + 2 * kStageOps;        // kStageCoef / 4 float4
+    float4* s_ops = s_stage;                       // kStageOps float4 (one per op)
+    float4* s_cf = s_stage + kStageOps;            // kStageCoef / 4 float4
     const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
-    for (int i = (int)tid; i < 2 * (op_end - op_begin); i += (int)nthr) s_ops[i] = __ldg(g_ops + i);
+    for (int i = (int)tid; i < (op_end - op_begin); i += (int)nthr) s_ops[i] = __ldg(g_ops + i);
     const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);  // coefficient slots are 16-byte aligned
     for (int i = (int)tid; i < (ce - cb + 3) / 4; i += (int)nthr) s_cf[i] = __ldg(g_cf + i);
-    ops_base = reinterpret_cast<const DevOp*>(s_ops) - op_begin;
+    ops_base = reinterpret_cast<const PackedOp*>(s_ops) - op_begin;
     coef_base = reinterpret_cast<const float*>(s_cf) - cb;
   }
   uint32_t base = tid;
@@ -610,17 +609,17 @@ __device__ __forceinline__ void run_hpass(const KernelArgs& ka, const DevPass* _
   const int op_begin = __ldg(&ps->op_begin), op_end = __ldg(&ps->op_end);
   const int cb = __ldg(&ps->coef_begin), ce = __ldg(&ps->coef_end);
   const bool staged = (op_end - op_begin) <= kStageOps && (ce - cb) <= kStageCoef;
-  const DevOp* ops_base = ka.ops;
+  const PackedOp* ops_base = ka.ops;
   const float* coef_base = ka.coef;
   __syncthreads();  // previous pass done (tile stores, staged program)
   if (staged) {
     float4* s_ops = s_stage;
-    float4* s_cf = s_stage + 2 * kStageOps;
+    float4* s_cf = s_stage + kStageOps;
     const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
-    for (int i = (int)tid; i < 2 * (op_end - op_begin); i += (int)nthr) s_ops[i] = __ldg(g_ops + i);
+    for (int i = (int)tid; i < (op_end - op_begin); i += (int)nthr) s_ops[i] = __ldg(g_ops + i);
     const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);
     for (int i = (int)tid; i < (ce - cb + 3) / 4; i += (int)nthr) s_cf[i] = __ldg(g_cf + i);
-    ops_base = reinterpret_cast<const DevOp*>(s_ops) - op_begin;
+    ops_base = reinterpret_cast<const PackedOp*>(s_ops) - op_begin;
     coef_base = reinterpret_cast<const float*>(s_cf) - cb;
   }
   uint32_t base = tid;
@@ -847,7 +846,7 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
   const DevTerm* terms = ka.terms;
   {
     const int ng = ka.L.grp_end - ka.L.grp_begin, nt = ka.L.term_end - ka.L.term_begin;
-    if (2 * ng + nt <= 2 * kStageOps + kStageCoef / 4) {
+    if (2 * ng + nt <= kStageOps + kStageCoef / 4) {
       const float4* gg = reinterpret_cast<const float4*>(ka.groups + ka.L.grp_begin);
       const float4* gt = reinterpret_cast<const float4*>(ka.terms + ka.L.term_begin);
       for (int i = (int)tid; i < 2 * ng; i += (int)nthr) s_stage[i] = __ldg(gg + i);
@@ -991,7 +990,7 @@ constexpr int sweep_max_threads() { return ADJ ? (1 << (13 - K)) : 512; }
 template <int K, bool ADJ>
 __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(const __grid_constant__ KernelArgs ka) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float4 s_stage[2 * kStageOps + kStageCoef / 4];
+  __shared__ float4 s_stage[kStageOps + kStageCoef / 4];
   float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float2* s_lam = s_psi + (ADJ ? (1u << ka.T) : 0u);
   constexpr int R = 1 << K;

@@ -582,3 +582,41 @@ def test_qhbm_circuit_param_update():
   th = qhbm.e_inference.energy.post_process[0].kernel.detach().cpu().numpy()
   p = orc.analytic_probabilities(orc.kobe_energy(bits, n, th))
   np.testing.assert_allclose(est, p @ reference(), atol=3e-2)
+
+
+def test_vqt_training_approaches_free_energy():
+  """End-to-end training loop (the reference's baselines/train.py in miniature): minimising the VQT loss
+  of a 5-qubit TFIM at beta = 1 with Adam drives it towards the exact free energy -log tr exp(-beta H),
+  which bounds it from below."""
+  n, beta_val = 5, 1.0
+  qubits = cq.GridQubit.rect(1, n)
+  energy = models.KOBE(list(range(n)), 2, energy_utils.RandomNormal(0.0, 0.1, 4))
+  e_infer = inference.AnalyticEnergyInference(energy, 20_000, initial_seed=[1, 2])
+  circ = models.DirectQuantumCircuit(arch.get_hardware_efficient_model_unitary(qubits, 3, "t"),
+                                     energy_utils.RandomUniform(-0.2, 0.2, 5))
+  qhbm = inference.QHBM(e_infer, inference.AnalyticQuantumInference(circ))
+  ham = arch.tfim_ring(qubits)
+  h = cq.convert_to_tensor([ham])
+  beta = torch.tensor(beta_val, device=DEV)
+  # exact free energy from the dense Hamiltonian (float64 on the host)
+  dim = 1 << n
+  pauli = {"X": np.array([[0, 1], [1, 0]], complex), "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.diag([1.0 + 0j, -1.0])}
+  dense = np.zeros((dim, dim), complex)
+  for t in ham.terms:
+    m = np.array([[1.0 + 0j]])
+    for q in qubits:
+      m = np.kron(m, pauli[t.paulis[q]] if q in t.paulis else np.eye(2))
+    dense += t.coefficient.real * m
+  free_energy = -np.log(np.exp(-beta_val * np.linalg.eigvalsh(dense)).sum())
+  opt = torch.optim.Adam(qhbm.trainable_variables, lr=0.05)
+  losses = []
+  for _ in range(150):
+    opt.zero_grad()
+    loss = inference.vqt(qhbm, h, beta)
+    loss.backward()
+    opt.step()
+    losses.append(float(loss.detach()))
+  first, last = np.mean(losses[:5]), np.mean(losses[-10:])
+  assert last < first - 1.0, (first, last)
+  assert last > free_energy - 0.05            # variational bound (sampling noise allowance)
+  assert last - free_energy < 0.35 * (first - free_energy), (first, last, free_energy)

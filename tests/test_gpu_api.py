@@ -620,3 +620,27 @@ def test_vqt_training_approaches_free_energy():
   assert last < first - 1.0, (first, last)
   assert last > free_energy - 0.05            # variational bound (sampling noise allowance)
   assert last - free_energy < 0.35 * (first - free_energy), (first, last, free_energy)
+
+
+def test_qmhl_training_raises_fidelity_with_target_state():
+  """Quantum modular Hamiltonian learning in miniature (reference qmhl_loss.py + qhbm_utils.py): a model
+  QHBM trained on samples of a target QHBM with the QMHL loss ends up with a thermal state close to the
+  target's (fidelity from the dense metrics)."""
+  n, num_samples = 3, 50_000
+  _, target = _random_qhbm(n, 2, 31, num_samples, ebm_seed=[9, 10])
+  _, model = _random_qhbm(n, 2, 32, num_samples, ebm_seed=[11, 12])
+  # the model must be able to express the target: same ansatz family, different starting point
+  sigma = inference.density_matrix(target.modular_hamiltonian)
+  f0 = float(inference.fidelity(model.modular_hamiltonian, sigma))
+  target_data = data.QHBMData(target)
+  opt = torch.optim.Adam(model.trainable_variables, lr=0.05)
+  losses = []
+  for _ in range(200):
+    opt.zero_grad()
+    loss = inference.qmhl(target_data, model)
+    loss.backward()
+    opt.step()
+    losses.append(float(loss.detach()))
+  f1 = float(inference.fidelity(model.modular_hamiltonian, sigma))
+  assert np.mean(losses[-10:]) < np.mean(losses[:5])
+  assert f1 > max(f0 + 0.05, 0.9), (f0, f1)

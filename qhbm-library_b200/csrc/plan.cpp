@@ -245,6 +245,30 @@ class Compiler {
     while (remaining > 0) {
       SweepOut sw;
       sw.tile_bits = choose_tile(atoms, done);
+      if (backward && sweeps.empty() && n > hp_.T && std::getenv("QHBM_NO_FUSE") == nullptr) {
+        // The expectation phase runs on the contiguous tile map and shares a launch with the first
+        // backward sweep when that sweep uses the same map: prefer it unless it would run fewer of the
+        // gates that are ready now.
+        std::vector<int> contiguous;
+        for (int b = 0; b < hp_.T; ++b) contiguous.push_back(b);
+        auto ready_inside = [&](const std::vector<int>& bits) {
+          uint32_t mask = 0;
+          for (int b : bits) mask |= 1u << b;
+          Block blk(n);
+          int count = 0;
+          for (size_t ai = 0; ai < atoms.size(); ++ai) {
+            if (done[ai]) continue;
+            const Atom& a = atoms[ai];
+            if (!blk.ready(a)) { blk.block(a); continue; }
+            bool inside = true;
+            for (int i = 0; i < a.nq; ++i) inside = inside && ((mask >> a.bit[i]) & 1);
+            if (inside && !a.diag) ++count;
+            else if (!inside) blk.block(a);
+          }
+          return count;
+        };
+        if (ready_inside(contiguous) >= ready_inside(sw.tile_bits)) sw.tile_bits = contiguous;
+      }
       sw.pass_begin = (int)hp_.passes.size();
       std::vector<int> local_of(n, -1);
       for (size_t j = 0; j < sw.tile_bits.size(); ++j) local_of[sw.tile_bits[j]] = (int)j;

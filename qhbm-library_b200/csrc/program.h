@@ -31,7 +31,7 @@ enum OpType : int32_t {
                   //     matrix index = 2*bit(hi position) + bit(lo position)
   OP_DCONST_TAB,  // F *= tab[(gidx >> aux0) & aux1]; coef -> complex table
   OP_DCONST_PAIR, // F *= c[2*bit(aux0) + bit(aux1)] (aux1 < 0: c[bit(aux0)]); coef -> 4 complex
-  OP_DREG_TAB,    // amp[r] *= F * tab[r]; F = 1; coef -> 2^K complex
+  OP_DREG_TAB,    // amp[r] *= F * tab[r]; F = 1; coef -> 2^K complex; aux0 = 0: F is known to be 1
   OP_DAPPLY,      // amp[r] *= F; F = 1
   OP_DCROSS,      // amps with register bit p0 = v: *= c[2*bit(aux0) + v]; coef -> 4 complex
   OP_XROT,        // (c I - i s X) on register position p0, global phase dropped; coef -> (c, s)

@@ -495,10 +495,12 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
         F = cmul(F, ldg2(cf + 2 * sel));
       } break;
       case OP_DREG_TAB: {
+        const bool pending = op.aux0 != 0;  // uniform: some thread-constant factor was folded into F
 #pragma unroll
         for (int r = 0; r < R; r += 2) {
           const float4 t = ldg4(cf + 2 * r);
-          const float2 c0 = cmul(F, make_float2(t.x, t.y)), c1 = cmul(F, make_float2(t.z, t.w));
+          float2 c0 = make_float2(t.x, t.y), c1 = make_float2(t.z, t.w);
+          if (pending) { c0 = cmul(F, c0); c1 = cmul(F, c1); }
           a[r] = cmul(a[r], c0);
           a[r + 1] = cmul(a[r + 1], c1);
           if constexpr (BOTH) {

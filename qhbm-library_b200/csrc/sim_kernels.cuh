@@ -801,16 +801,51 @@ __device__ __forceinline__ void group_coefficients(const DevTerm* terms, float (
 
 // h[m] += c(i_m) * psi[i_m ^ x] for one off-diagonal x-group.  GLOBAL: the partner lives in
 // another tile (read through L2), else inside this tile's shared memory.
-template <int MC, bool CPLX, bool GLOBAL>
+// True when no term of the group distinguishes the thread's MC amplitudes (warp-uniform): the
+// coefficient is then one scalar per thread, returned in (c0r, c0i).
+template <int MC, bool CPLX>
+__device__ __forceinline__ bool uniform_coefficient(const DevTerm* terms, const uint32_t gi_tid, const int m0,
+                                                    const int t0, const int t1, float& c0r, float& c0i) {
+  constexpr uint32_t kAll = MC >= 32 ? 0xffffffffu : ((1u << MC) - 1u);
+  for (int t = t0; t < t1; ++t) {
+    const float4 tv = *reinterpret_cast<const float4*>(terms + t);
+    const uint32_t word = (__float_as_uint(tv.w) >> m0) & kAll;
+    if (word != 0u && word != kAll) return false;
+    const uint32_t sg = (uint32_t)((__popc(gi_tid & __float_as_uint(tv.z)) + (int)(word & 1u)) & 1) << 31;
+    c0r += __uint_as_float(__float_as_uint(tv.x) ^ sg);
+    if constexpr (CPLX) c0i += __uint_as_float(__float_as_uint(tv.y) ^ sg);
+  }
+  return true;
+}
+
+template <int MC, bool CPLX, bool GLOBAL, bool SCALAR>
 __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const DevTerm* terms, const float2* s_psi,
                                               const float2* __restrict__ psi_u, float2 (&h)[MC],
                                               const uint32_t gi_tid, const uint32_t ph_tid,
                                               const uint32_t nthr, const int m0, const uint32_t x, const int xl,
                                               const int t0, const int t1, const float k0r, const float k0i) {
+  const uint32_t pxor = GLOBAL ? 0u : swz((uint32_t)xl);
+  if constexpr (SCALAR) {  // forward-only kernel: in the adjoint kernel the extra code costs more than it saves
+    float c0r = k0r, c0i = k0i;
+    if (uniform_coefficient<MC, CPLX>(terms, gi_tid, m0, t0, t1, c0r, c0i)) {
+#pragma unroll
+      for (int m = 0; m < MC; ++m) {
+        float2 p;
+        if constexpr (GLOBAL) p = psi_u[(gi_tid | ka.L.moff[m0 + m]) ^ x];
+        else p = s_psi[ph_tid ^ ka.L.soff[m0 + m] ^ pxor];
+        h[m].x = fmaf(c0r, p.x, h[m].x);
+        h[m].y = fmaf(c0r, p.y, h[m].y);
+        if constexpr (CPLX) {
+          h[m].x = fmaf(-c0i, p.y, h[m].x);
+          h[m].y = fmaf(c0i, p.x, h[m].y);
+        }
+      }
+      return;
+    }
+  }
   float cr[MC];
   float ci[CPLX ? MC : 1];
   group_coefficients<MC, CPLX>(terms, cr, ci, gi_tid, m0, t0, t1, k0r, k0i);
-  const uint32_t pxor = GLOBAL ? 0u : swz((uint32_t)xl);
 #pragma unroll
   for (int m = 0; m < MC; ++m) {
     float2 p;
@@ -871,10 +906,12 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
     float p2[MC];
     float2 lam[ADJ ? MC : 1];
     float dg[ADJ ? MC : 1];
+    float p2sum = 0.f;
 #pragma unroll
     for (int m = 0; m < MC; ++m) {
       a[m] = s_psi[ph_tid ^ ka.L.soff[m0 + m]];
       p2[m] = a[m].x * a[m].x + a[m].y * a[m].y;
+      if constexpr (!ADJ) p2sum += p2[m];
       if constexpr (ADJ) {
         lam[m] = make_float2(0.f, 0.f);
         dg[m] = wht ? dgall[m0 + m] : 0.f;  // m0 is a constant after unrolling the chunk loop
@@ -911,6 +948,13 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
         const int xl = ch.y;
         const float k0r = __int_as_float(ck.x), k0i = __int_as_float(ck.y);
         if (x == 0) {
+          if constexpr (!ADJ) {
+            float c0r = k0r, c0i = 0.f;
+            if (uniform_coefficient<MC, false>(terms, gi_tid, m0, ch.z, ch.w, c0r, c0i)) {
+              ej = fmaf(c0r, p2sum, ej);
+              continue;
+            }
+          }
           float cr[MC], ci[1];
           group_coefficients<MC, false>(terms, cr, ci, gi_tid, m0, ch.z, ch.w, k0r, 0.f);
 #pragma unroll
@@ -926,11 +970,11 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
           for (int m = 0; m < MC; ++m) h[m] = make_float2(0.f, 0.f);
         }
         if (ck.z == 0) {
-          if (xl >= 0) group_offdiag<MC, false, false>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
-          else group_offdiag<MC, false, true>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          if (xl >= 0) group_offdiag<MC, false, false, !ADJ>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          else group_offdiag<MC, false, true, !ADJ>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
         } else {
-          if (xl >= 0) group_offdiag<MC, true, false>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
-          else group_offdiag<MC, true, true>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          if (xl >= 0) group_offdiag<MC, true, false, !ADJ>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          else group_offdiag<MC, true, true, !ADJ>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
         }
       }
       if (offdiag) {

@@ -220,6 +220,9 @@ def run_gpu(args, cfg):
   import torch.distributed as dist
   from qhbmlib import engine
 
+  if not torch.cuda.is_available():
+    sys.exit("bench.py: no CUDA device. The qhbm_b200 engine has no CPU fallback; "
+             "`--impl reference` times the CPU restatement of the reference path.")
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -13,7 +13,11 @@
  *     categorical sampling sweep (qhbmlib/inference/ebm.py:445-492) and
  *     BernoulliEnergyInference's sampler (ebm.py:559-561);
  *   - `unique_bitstrings_with_counts` (qhbmlib/utils.py:61-78,
- *     tf.raw_ops.UniqueWithCountsV2) in first-occurrence order.
+ *     tf.raw_ops.UniqueWithCountsV2) in first-occurrence order;
+ *   - (widened) the simulation and measurement halves of
+ *     `tfq.layers.Sample`, `tfq.layers.SampledExpectation` and `tfq.layers.Unitary`
+ *     as used by SampledQuantumInference and the dense metrics
+ *     (qhbmlib/inference/qnn.py:142-292, qnn_utils.py:23-33).
  *
  * Conventions: every function returns 0 on success, non-zero on error; the
  * message is available from qhbm_last_error() (thread-local).  All `d_` pointers

@@ -42,8 +42,8 @@ def lib():
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, f"libtfq_cpu_{_cpu_tag()}.so")
     if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
-      subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-std=c11",
-                             src, "-o", out, "-lm"])
+      subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-fno-math-errno", "-fno-trapping-math",
+                             "-ffp-contract=fast", "-shared", "-fPIC", "-std=c11", src, "-o", out, "-lm"])
     _lib = ctypes.CDLL(out)
     _lib.tfq_cpu_max_threads.restype = ctypes.c_int
   return _lib

@@ -623,8 +623,8 @@ class Compiler {
     if (!run.reg_list.empty()) {
       DevOp o = make_op(OP_DREG_TAB);
       o.aux0 = run.any_const ? 1 : 0;  // 0: no thread-constant factor is pending (F == 1)
-      o.coef = alloc_coef(2 << hp_.K);
-      add_job(PJ_DTAB, o.coef, dag, 0, 0, hp_.K, run.reg_list);
+      o.coef = alloc_coef(4 << hp_.K);  // entries (re, im, -im, im): see OP_DREG_TAB
+      add_job(PJ_DTAB, o.coef, dag, 1, 0, hp_.K, run.reg_list);
       hp_.ops.push_back(o);
     } else if (run.any_const) {
       hp_.ops.push_back(make_op(OP_DAPPLY));

@@ -31,7 +31,8 @@ enum OpType : int32_t {
                   //     matrix index = 2*bit(hi position) + bit(lo position)
   OP_DCONST_TAB,  // F *= tab[(gidx >> aux0) & aux1]; coef -> complex table
   OP_DCONST_PAIR, // F *= c[2*bit(aux0) + bit(aux1)] (aux1 < 0: c[bit(aux0)]); coef -> 4 complex
-  OP_DREG_TAB,    // amp[r] *= F * tab[r]; F = 1; coef -> 2^K complex; aux0 = 0: F is known to be 1
+  OP_DREG_TAB,    // amp[r] *= F * tab[r]; F = 1; coef -> 2^K entries of 4 floats (re, im, -im, im);
+                  //     aux0 = 0: F is known to be 1
   OP_DAPPLY,      // amp[r] *= F; F = 1
   OP_DCROSS,      // amps with register bit p0 = v: *= c[2*bit(aux0) + v]; coef -> 4 complex
   OP_XROT,        // (c I - i s X) on register position p0, global phase dropped; coef -> (c, s)
@@ -170,7 +171,8 @@ enum PrepKind : int32_t {
   PJ_GRAD2,      // same, 4x4; b: swap qubit roles
   PJ_GDIAG,      // diagonal of M for a diagonal gate; b: swap roles (4 entries) ; 1q gate: 2 entries
   PJ_DTAB,       // phase table with 2^d entries; list = triples (gate, posA, posB): entry[v] =
-                 //   prod_g diag_g[2*bit(v,posA) + bit(v,posB)] (posB < 0 -> 1q gate); a: dagger
+                 //   prod_g diag_g[2*bit(v,posA) + bit(v,posB)] (posB < 0 -> 1q gate); a: dagger;
+                 //   b: entries are 4 floats (re, im, -im, im) instead of (re, im)
   PJ_DPAIR,      // 4 (or 2) diagonal entries of one gate; a: dagger; b: swap roles
   PJ_ROT,        // (cos, sin)(pi t / 2) of an XPow / YPow gate; a: dagger (sin negated)
   PJ_KAPPA,      // kappa of a two-level X/Y-type gate (b: 0 = X, 1 = Y) for param c:

@@ -65,6 +65,33 @@ __device__ __forceinline__ uint32_t gather_bits(uint32_t g, const BitRun* runs, 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+// ---- packed FP32 (sm_100 FFMA2 / FMUL2 / FADD2: two lanes per instruction).  A complex amplitude is
+// one 64-bit register pair (re, im); ptxas folds half swaps (.LO_HI), per-half sign patterns (.NP) and
+// scalar broadcasts (.F32) into the operand modifiers of the packed instruction, so a complex
+// multiply-add is 2 issue slots instead of 4.
+__device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 swp(float2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// Sign pair in the constant bank.  A pair such as (-y, y) built with register moves is re-materialised by
+// ptxas at every use (one MOV per packed instruction, measured); as the product bc(y) * kNP it is ONE
+// FMUL2 whose result is an ordinary register pair.
+__constant__ float2 kNP = {-1.f, 1.f};
+__device__ __forceinline__ float2 np_pair(float y) { return mul2(bc(y), kNP); }  // (-y, y)
+// A complex constant c prepared for packed use: re = c.x and q = (-c.y, c.y).
+struct CK {
+  float re;
+  float2 q;
+};
+__device__ __forceinline__ CK make_ck(float2 c) { CK k; k.re = c.x; k.q = np_pair(c.y); return k; }
+// a * c
+__device__ __forceinline__ float2 cmulk(float2 a, const CK& k) { return fma2(k.q, swp(a), mul2(bc(k.re), a)); }
+// acc + a * c
+__device__ __forceinline__ float2 cfmak(float2 a, const CK& k, float2 acc) {
+  return fma2(k.q, swp(a), fma2(bc(k.re), a, acc));
+}
+__device__ __forceinline__ float hsum(float2 a) { return a.x + a.y; }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -119,40 +146,38 @@ __device__ __forceinline__ void for_each_pos(F&& f) {
 
 template <int K, int P>
 __device__ __forceinline__ void mat1(float2 (&a)[1 << K], const float4 m0, const float4 m1) {
+  const CK k00 = make_ck(make_float2(m0.x, m0.y)), k01 = make_ck(make_float2(m0.z, m0.w));
+  const CK k10 = make_ck(make_float2(m1.x, m1.y)), k11 = make_ck(make_float2(m1.z, m1.w));
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
     if (r & (1 << P)) continue;
     const float2 x0 = a[r], x1 = a[r | (1 << P)];
-    a[r].x = m0.x * x0.x - m0.y * x0.y + m0.z * x1.x - m0.w * x1.y;
-    a[r].y = m0.x * x0.y + m0.y * x0.x + m0.z * x1.y + m0.w * x1.x;
-    a[r | (1 << P)].x = m1.x * x0.x - m1.y * x0.y + m1.z * x1.x - m1.w * x1.y;
-    a[r | (1 << P)].y = m1.x * x0.y + m1.y * x0.x + m1.z * x1.y + m1.w * x1.x;
+    a[r] = cfmak(x1, k01, cmulk(x0, k00));
+    a[r | (1 << P)] = cfmak(x1, k11, cmulk(x0, k10));
   }
 }
 // (c I - i s X): y0 = c x0 - i s x1, y1 = -i s x0 + c x1
 template <int K, int P>
 __device__ __forceinline__ void xrot(float2 (&a)[1 << K], const float c, const float s) {
+  const float2 ms = np_pair(s);  // (-s, s)
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
     if (r & (1 << P)) continue;
     const float2 x0 = a[r], x1 = a[r | (1 << P)];
-    a[r].x = fmaf(s, x1.y, c * x0.x);
-    a[r].y = fmaf(-s, x1.x, c * x0.y);
-    a[r | (1 << P)].x = fmaf(s, x0.y, c * x1.x);
-    a[r | (1 << P)].y = fmaf(-s, x0.x, c * x1.y);
+    a[r] = fma2(make_float2(-ms.x, -ms.y), swp(x1), mul2(bc(c), x0));
+    a[r | (1 << P)] = fma2(make_float2(-ms.x, -ms.y), swp(x0), mul2(bc(c), x1));
   }
 }
 // unnormalised (I - i t X), t = tan: one FMA per component; the missing factor cos is restored later
 template <int K, int P>
 __device__ __forceinline__ void xrot_fast(float2 (&a)[1 << K], const float t) {
+  const float2 mt = np_pair(t);  // (-t, t)
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
     if (r & (1 << P)) continue;
     const float2 x0 = a[r], x1 = a[r | (1 << P)];
-    a[r].x = fmaf(t, x1.y, x0.x);
-    a[r].y = fmaf(-t, x1.x, x0.y);
-    a[r | (1 << P)].x = fmaf(t, x0.y, x1.x);
-    a[r | (1 << P)].y = fmaf(-t, x0.x, x1.y);
+    a[r] = fma2(make_float2(-mt.x, -mt.y), swp(x1), x0);
+    a[r | (1 << P)] = fma2(make_float2(-mt.x, -mt.y), swp(x0), x1);
   }
 }
 // (c I - i s Y) = [[c, -s], [s, c]]
@@ -162,59 +187,59 @@ __device__ __forceinline__ void yrot(float2 (&a)[1 << K], const float c, const f
   for (int r = 0; r < (1 << K); ++r) {
     if (r & (1 << P)) continue;
     const float2 x0 = a[r], x1 = a[r | (1 << P)];
-    a[r].x = fmaf(-s, x1.x, c * x0.x);
-    a[r].y = fmaf(-s, x1.y, c * x0.y);
-    a[r | (1 << P)].x = fmaf(s, x0.x, c * x1.x);
-    a[r | (1 << P)].y = fmaf(s, x0.y, c * x1.y);
+    a[r] = fma2(bc(-s), x1, mul2(bc(c), x0));
+    a[r | (1 << P)] = fma2(bc(s), x0, mul2(bc(c), x1));
   }
 }
 // Im <b| X_P |a> and Im <b| Y_P |a> over the thread's amplitudes
 template <int K, int P>
 __device__ __forceinline__ float im_bxa(const float2 (&a)[1 << K], const float2 (&b)[1 << K]) {
-  float s = 0.f;
+  // Im conj(b) a = b.x a.y - b.y a.x = the two halves of b * (a.y, -a.x), summed at the end
+  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
     if (r & (1 << P)) continue;
     const int q = r | (1 << P);
-    s += b[r].x * a[q].y - b[r].y * a[q].x + b[q].x * a[r].y - b[q].y * a[r].x;
+    s0 = fma2(b[r], make_float2(a[q].y, -a[q].x), s0);
+    s1 = fma2(b[q], make_float2(a[r].y, -a[r].x), s1);
   }
-  return s;
+  return hsum(add2(s0, s1));
 }
 template <int K, int P>
 __device__ __forceinline__ float im_bya(const float2 (&a)[1 << K], const float2 (&b)[1 << K]) {
-  float s = 0.f;
+  float2 sp = make_float2(0.f, 0.f), sm = make_float2(0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
     if (r & (1 << P)) continue;
     const int q = r | (1 << P);
-    s += b[q].x * a[r].x + b[q].y * a[r].y - b[r].x * a[q].x - b[r].y * a[q].y;
+    sp = fma2(b[q], a[r], sp);
+    sm = fma2(b[r], a[q], sm);
   }
-  return s;
+  return hsum(sp) - hsum(sm);
 }
 
 // 2 Re sum_r conj(b_r) (M a)_r over the thread's amplitudes.
 template <int K, int P>
 __device__ __forceinline__ float grad_mat1(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
                                            const float4 m0, const float4 m1) {
-  float s = 0.f;
+  const CK k00 = make_ck(make_float2(m0.x, m0.y)), k01 = make_ck(make_float2(m0.z, m0.w));
+  const CK k10 = make_ck(make_float2(m1.x, m1.y)), k11 = make_ck(make_float2(m1.z, m1.w));
+  float2 s = make_float2(0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
     if (r & (1 << P)) continue;
     const float2 x0 = a[r], x1 = a[r | (1 << P)];
-    const float y0x = m0.x * x0.x - m0.y * x0.y + m0.z * x1.x - m0.w * x1.y;
-    const float y0y = m0.x * x0.y + m0.y * x0.x + m0.z * x1.y + m0.w * x1.x;
-    const float y1x = m1.x * x0.x - m1.y * x0.y + m1.z * x1.x - m1.w * x1.y;
-    const float y1y = m1.x * x0.y + m1.y * x0.x + m1.z * x1.y + m1.w * x1.x;
-    s += b[r].x * y0x + b[r].y * y0y + b[r | (1 << P)].x * y1x + b[r | (1 << P)].y * y1y;
+    s = fma2(b[r], cfmak(x1, k01, cmulk(x0, k00)), s);
+    s = fma2(b[r | (1 << P)], cfmak(x1, k11, cmulk(x0, k10)), s);
   }
-  return 2.f * s;
+  return 2.f * hsum(s);
 }
 
 // 4x4 block on register positions (LO+1, LO); matrix index = 2*bit(LO+1) + bit(LO).
 // GRAD: returns 2 Re <b| M |a> and leaves a untouched.
 template <int K, int LO, bool GRAD>
 __device__ __forceinline__ float mat2(float2 (&a)[1 << K], const float2 (&b)[1 << K], const float* __restrict__ mp) {
-  float s = 0.f;
+  float2 s = make_float2(0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
     if (r & (3 << LO)) continue;
@@ -223,32 +248,33 @@ __device__ __forceinline__ float mat2(float2 (&a)[1 << K], const float2 (&b)[1 <
     for (int j = 0; j < 4; ++j) x[j] = a[r | (j << LO)];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      // the matrix rows are re-read (uniform, L1-resident) instead of holding 32 registers
+      // the matrix rows are re-read (uniform, staged in shared memory) instead of holding 32 registers
       const float4 m01 = ldg4(mp + 8 * i), m23 = ldg4(mp + 8 * i + 4);
-      y[i].x = m01.x * x[0].x - m01.y * x[0].y + m01.z * x[1].x - m01.w * x[1].y +
-               m23.x * x[2].x - m23.y * x[2].y + m23.z * x[3].x - m23.w * x[3].y;
-      y[i].y = m01.x * x[0].y + m01.y * x[0].x + m01.z * x[1].y + m01.w * x[1].x +
-               m23.x * x[2].y + m23.y * x[2].x + m23.z * x[3].y + m23.w * x[3].x;
+      y[i] = cmulk(x[0], make_ck(make_float2(m01.x, m01.y)));
+      y[i] = cfmak(x[1], make_ck(make_float2(m01.z, m01.w)), y[i]);
+      y[i] = cfmak(x[2], make_ck(make_float2(m23.x, m23.y)), y[i]);
+      y[i] = cfmak(x[3], make_ck(make_float2(m23.z, m23.w)), y[i]);
     }
     if constexpr (GRAD) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) s += b[r | (i << LO)].x * y[i].x + b[r | (i << LO)].y * y[i].y;
+      for (int i = 0; i < 4; ++i) s = fma2(b[r | (i << LO)], y[i], s);
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[r | (i << LO)] = y[i];
     }
   }
-  return 2.f * s;
+  return 2.f * hsum(s);
 }
 
 // amplitudes with register bit P = v are multiplied by e_v; exact identities are skipped
 template <int K, int P>
 __device__ __forceinline__ void mul_sel(float2 (&a)[1 << K], const float2 e0, const float2 e1, const bool id0,
                                         const bool id1) {
+  const CK k0 = make_ck(e0), k1 = make_ck(e1);
 #pragma unroll
   for (int r = 0; r < (1 << K); ++r) {
-    if (r & (1 << P)) { if (!id1) a[r] = cmul(a[r], e1); }
-    else { if (!id0) a[r] = cmul(a[r], e0); }
+    if (r & (1 << P)) { if (!id1) a[r] = cmulk(a[r], k1); }
+    else { if (!id0) a[r] = cmulk(a[r], k0); }
   }
 }
 
@@ -260,46 +286,81 @@ __device__ __forceinline__ float pick(const float (&v)[N], int i) {
   return r;
 }
 
-// Marginal sums of w_r = conj(b_r) a_r = u_r + i v_r over the register index r:
-// totals, per register bit, and per pair of register bits.  No diagonal gate changes w,
-// so one set of marginals serves a whole run of diagonal-gate gradients.
+// Marginal sums of w_r = conj(b_r) a_r = u_r + i v_r over the register index r, kept as (u, -v) pairs
+// (so that Re(m w) = m.x u - m.y v is the half-sum of the plain product m * (u, -v)):
+// totals T, per register bit S[p] (sum over r with bit p set) and per pair of register bits SS[pi]
+// (both set; pi = ph (ph - 1) / 2 + pl, ph > pl).  No diagonal gate changes w, so one set of marginals
+// serves a whole run of diagonal-gate gradients.  The sums are built four amplitudes at a time (a
+// two-level subset-sum tree over register bits 0 and 1, then one accumulate per higher bit), every add a
+// packed FADD2 on the (u, v) pair: ~45 adds instead of one per (amplitude, membership).
 template <int K>
 struct Marginals {
   static constexpr int NP = K * (K - 1) / 2;
-  float U, V;
-  float Up[K], Vp[K];
-  float Upp[NP > 0 ? NP : 1], Vpp[NP > 0 ? NP : 1];
+  float2 T;
+  float2 S[K];
+  float2 SS[NP > 0 ? NP : 1];
 };
+__device__ __forceinline__ void acc2(float2& dst, const float2 v, const bool first) {
+  dst = first ? v : add2(dst, v);
+}
 template <int K>
 __device__ __forceinline__ void compute_marginals(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
                                                   Marginals<K>& mg, const bool pairs) {
-  mg.U = mg.V = 0.f;
+  static_assert(K >= 2, "register qubits");
+  auto pidx = [](int ph, int pl) { return ph * (ph - 1) / 2 + pl; };
 #pragma unroll
-  for (int p = 0; p < K; ++p) mg.Up[p] = mg.Vp[p] = 0.f;
+  for (int g = 0; g < (1 << (K - 2)); ++g) {
+    float2 x[4];
 #pragma unroll
-  for (int q = 0; q < Marginals<K>::NP; ++q) mg.Upp[q] = mg.Vpp[q] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      const int r = 4 * g + j;
+      const float2 w = mul2(b[r], a[r]);                             // halves sum to  Re conj(b) a
+      const float2 z = mul2(b[r], make_float2(-a[r].y, a[r].x));     // halves sum to -Im conj(b) a
+      x[j] = make_float2(w.x + w.y, z.x + z.y);
+    }
+    const float2 s0 = add2(x[1], x[3]);   // register bit 0 set
+    const float2 s1 = add2(x[2], x[3]);   // register bit 1 set
+    const float2 t = add2(add2(x[0], x[1]), s1);
+    acc2(mg.T, t, g == 0);
+    acc2(mg.S[0], s0, g == 0);
+    acc2(mg.S[1], s1, g == 0);
+    if (pairs) acc2(mg.SS[pidx(1, 0)], x[3], g == 0);
 #pragma unroll
-  for (int r = 0; r < (1 << K); ++r) {
-    const float u = b[r].x * a[r].x + b[r].y * a[r].y;  // Re conj(b) a
-    const float v = b[r].x * a[r].y - b[r].y * a[r].x;  // Im conj(b) a
-    mg.U += u;
-    mg.V += v;
-#pragma unroll
-    for (int p = 0; p < K; ++p)
-      if (r & (1 << p)) { mg.Up[p] += u; mg.Vp[p] += v; }
+    for (int p = 2; p < K; ++p) {
+      if ((g >> (p - 2)) & 1) {
+        const bool first = g == (1 << (p - 2));
+        acc2(mg.S[p], t, first);
+        if (pairs) {
+          acc2(mg.SS[pidx(p, 0)], s0, first);
+          acc2(mg.SS[pidx(p, 1)], s1, first);
+        }
+      }
+    }
     if (pairs) {
 #pragma unroll
-      for (int ph = 1; ph < K; ++ph)
+      for (int ph = 3; ph < K; ++ph)
 #pragma unroll
-        for (int pl = 0; pl < ph; ++pl)
-          if ((r & (1 << ph)) && (r & (1 << pl))) {
-            mg.Upp[ph * (ph - 1) / 2 + pl] += u;
-            mg.Vpp[ph * (ph - 1) / 2 + pl] += v;
-          }
+        for (int pl = 2; pl < ph; ++pl)
+          if (((g >> (ph - 2)) & 1) && ((g >> (pl - 2)) & 1))
+            acc2(mg.SS[pidx(ph, pl)], t, g == ((1 << (ph - 2)) | (1 << (pl - 2))));
     }
   }
 }
 
+template <int N>
+__device__ __forceinline__ float2 pick2(const float2 (&v)[N], int i) {
+  float2 r = v[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) {
+    r.x = (i == k) ? v[k].x : r.x;
+    r.y = (i == k) ? v[k].y : r.y;
+  }
+  return r;
+}
+
+// Gradient of every diagonal gate of a run.  A diagonal gate with M = dG G^dagger = diag(m_sel)
+// contributes 2 Re sum_r m_sel(r) w_r = 2 sum_sel (Re m_sel U_sel - Im m_sel V_sel), U_sel + i V_sel the
+// sum of w over the amplitudes that select entry sel.
 template <int K>
 __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
                                               const PackedOp* __restrict__ ops, const int n_const, const int n_reg1,
@@ -308,6 +369,7 @@ __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const f
   OpRec nxt = load_op(ops);  // issued before the marginals so that its latency is covered
   Marginals<K> mg;
   compute_marginals<K>(a, b, mg, pairs);
+  const float2 T = mg.T;
   int i = 0;
   // gates whose qubits are all thread-constant: one selected entry times the thread totals
   for (; i < n_const; ++i) {
@@ -316,32 +378,35 @@ __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const f
     int sel = (gbase >> op.aux0) & 1;
     if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1);
     const float2 m = ldg2(coef + op.coef + 2 * sel);
-    scratch[op.gslot * nthr + tid] = 2.f * (m.x * mg.U - m.y * mg.V);
+    scratch[op.gslot * nthr + tid] = 2.f * hsum(mul2(m, T));
   }
   // one register bit (plus, for OP_GD_MIX, one thread-constant bit)
   for (; i < n_const + n_reg1; ++i) {
     const OpRec op = nxt;
     if (i + 1 < count) nxt = load_op(ops + i + 1);
     const int cb = op.type == OP_GD_MIX ? ((gbase >> op.aux0) & 1) : 0;
-    const float U1 = pick<K>(mg.Up, op.p0), V1 = pick<K>(mg.Vp, op.p0);
+    const float2 S1 = pick2<K>(mg.S, op.p0);
     const float4 m = ldg4(coef + op.coef + 4 * cb);
-    scratch[op.gslot * nthr + tid] = 2.f * (m.x * (mg.U - U1) - m.y * (mg.V - V1) + m.z * U1 - m.w * V1);
+    const float2 D = add2(T, make_float2(-S1.x, -S1.y));
+    const float2 v = fma2(make_float2(m.z, m.w), S1, mul2(make_float2(m.x, m.y), D));
+    scratch[op.gslot * nthr + tid] = 2.f * hsum(v);
   }
   // two register bits, p0 > p1
   for (; i < count; ++i) {
     const OpRec op = nxt;
     if (i + 1 < count) nxt = load_op(ops + i + 1);
     const float* e = coef + op.coef;
-    const float Uh = pick<K>(mg.Up, op.p0), Vh = pick<K>(mg.Vp, op.p0);
-    const float Ul = pick<K>(mg.Up, op.p1), Vl = pick<K>(mg.Vp, op.p1);
-    const int pi = op.p0 * (op.p0 - 1) / 2 + op.p1;
-    const float U11 = pick<Marginals<K>::NP>(mg.Upp, pi), V11 = pick<Marginals<K>::NP>(mg.Vpp, pi);
+    const float2 Sh = pick2<K>(mg.S, op.p0), Sl = pick2<K>(mg.S, op.p1);
+    const float2 S11 = pick2<Marginals<K>::NP>(mg.SS, op.p0 * (op.p0 - 1) / 2 + op.p1);
     const float4 m01 = ldg4(e), m23 = ldg4(e + 4);
-    const float val = m01.x * (mg.U - Uh - Ul + U11) - m01.y * (mg.V - Vh - Vl + V11)  // sel 0
-                      + m01.z * (Ul - U11) - m01.w * (Vl - V11)                         // sel 1: lo bit only
-                      + m23.x * (Uh - U11) - m23.y * (Vh - V11)                         // sel 2: hi bit only
-                      + m23.z * U11 - m23.w * V11;                                      // sel 3
-    scratch[op.gslot * nthr + tid] = 2.f * val;
+    const float2 n11 = make_float2(-S11.x, -S11.y);
+    const float2 Slo = add2(Sl, n11), Shi = add2(Sh, n11);                 // lo bit only / hi bit only
+    const float2 S00 = add2(add2(T, make_float2(-Sh.x, -Sh.y)), make_float2(-Slo.x, -Slo.y));
+    float2 v = mul2(make_float2(m01.x, m01.y), S00);
+    v = fma2(make_float2(m01.z, m01.w), Slo, v);
+    v = fma2(make_float2(m23.x, m23.y), Shi, v);
+    v = fma2(make_float2(m23.z, m23.w), S11, v);
+    scratch[op.gslot * nthr + tid] = 2.f * hsum(v);
   }
 }
 
@@ -495,26 +560,30 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
         F = cmul(F, ldg2(cf + 2 * sel));
       } break;
       case OP_DREG_TAB: {
+        // table entries are (re, im, -im, im): the last pair is the packed-multiply form of the constant
         const bool pending = op.aux0 != 0;  // uniform: some thread-constant factor was folded into F
+        const CK kf = make_ck(F);
 #pragma unroll
-        for (int r = 0; r < R; r += 2) {
-          const float4 t = ldg4(cf + 2 * r);
-          float2 c0 = make_float2(t.x, t.y), c1 = make_float2(t.z, t.w);
-          if (pending) { c0 = cmul(F, c0); c1 = cmul(F, c1); }
-          a[r] = cmul(a[r], c0);
-          a[r + 1] = cmul(a[r + 1], c1);
-          if constexpr (BOTH) {
-            b[r] = cmul(b[r], c0);
-            b[r + 1] = cmul(b[r + 1], c1);
+        for (int r = 0; r < R; ++r) {
+          const float4 t = ldg4(cf + 4 * r);
+          CK k;
+          k.re = t.x;
+          k.q = make_float2(t.z, t.w);
+          a[r] = cmulk(a[r], k);
+          if constexpr (BOTH) b[r] = cmulk(b[r], k);
+          if (pending) {
+            a[r] = cmulk(a[r], kf);
+            if constexpr (BOTH) b[r] = cmulk(b[r], kf);
           }
         }
         F = make_float2(1.f, 0.f);
       } break;
       case OP_DAPPLY: {
+        const CK kf = make_ck(F);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          a[r] = cmul(a[r], F);
-          if constexpr (BOTH) b[r] = cmul(b[r], F);
+          a[r] = cmulk(a[r], kf);
+          if constexpr (BOTH) b[r] = cmulk(b[r], kf);
         }
         F = make_float2(1.f, 0.f);
       } break;
@@ -580,7 +649,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
 template <int XR, bool BOTH>
 __device__ __forceinline__ void hx_apply(const float2 (&a)[16], float2 (&b)[BOTH ? 16 : 1], const float* cf,
                                          const float sgn, float& e) {
-  float acc = 0.f;
+  float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
   for (int r0 = 0; r0 < 16; r0 += 4) {
     const float4 t4 = ldg4(cf + r0);  // coefficients are read four at a time: no table in registers
@@ -589,15 +658,13 @@ __device__ __forceinline__ void hx_apply(const float2 (&a)[16], float2 (&b)[BOTH
     for (int i = 0; i < 4; ++i) {
       const int r = r0 + i, q = r ^ XR;
       if constexpr (BOTH) {
-        const float t = sgn * tab[i];
-        b[r].x = fmaf(t, a[q].x, b[r].x);
-        b[r].y = fmaf(t, a[q].y, b[r].y);
+        b[r] = fma2(bc(sgn * tab[i]), a[q], b[r]);
       } else {
-        acc = fmaf(tab[i], fmaf(a[r].x, a[q].x, a[r].y * a[q].y), acc);
+        acc = fma2(mul2(bc(tab[i]), a[r]), a[q], acc);
       }
     }
   }
-  if constexpr (!BOTH) e = fmaf(sgn, acc, e);
+  if constexpr (!BOTH) e = fmaf(sgn, hsum(acc), e);
 }
 
 // The pass works on 16 amplitudes at a time (register positions 0..3 carry the flips); with K = 5 the
@@ -833,12 +900,8 @@ __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const DevTer
         float2 p;
         if constexpr (GLOBAL) p = psi_u[(gi_tid | ka.L.moff[m0 + m]) ^ x];
         else p = s_psi[ph_tid ^ ka.L.soff[m0 + m] ^ pxor];
-        h[m].x = fmaf(c0r, p.x, h[m].x);
-        h[m].y = fmaf(c0r, p.y, h[m].y);
-        if constexpr (CPLX) {
-          h[m].x = fmaf(-c0i, p.y, h[m].x);
-          h[m].y = fmaf(c0i, p.x, h[m].y);
-        }
+        h[m] = fma2(bc(c0r), p, h[m]);
+        if constexpr (CPLX) h[m] = fma2(np_pair(c0i), swp(p), h[m]);
       }
       return;
     }
@@ -851,12 +914,8 @@ __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const DevTer
     float2 p;
     if constexpr (GLOBAL) p = psi_u[(gi_tid | ka.L.moff[m0 + m]) ^ x];
     else p = s_psi[ph_tid ^ ka.L.soff[m0 + m] ^ pxor];
-    h[m].x = fmaf(cr[m], p.x, h[m].x);
-    h[m].y = fmaf(cr[m], p.y, h[m].y);
-    if constexpr (CPLX) {
-      h[m].x = fmaf(-ci[m], p.y, h[m].x);
-      h[m].y = fmaf(ci[m], p.x, h[m].y);
-    }
+    h[m] = fma2(bc(cr[m]), p, h[m]);
+    if constexpr (CPLX) h[m] = fma2(np_pair(ci[m]), swp(p), h[m]);
   }
 }
 
@@ -922,6 +981,7 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
       const int j = orng.z;
       const float gj = want_lam ? __ldg(&ka.dgrad[(size_t)u * ka.O + j]) : 0.f;
       float ej = 0.f;
+      float2 ej2 = make_float2(0.f, 0.f);
       float2 h[MC];
       bool offdiag = false;
       if constexpr (ADJ) {
@@ -980,21 +1040,17 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
       if (offdiag) {
 #pragma unroll
         for (int m = 0; m < MC; ++m) {
-          ej = fmaf(a[m].x, h[m].x, fmaf(a[m].y, h[m].y, ej));
-          if constexpr (ADJ) {
-            lam[m].x = fmaf(gj, h[m].x, lam[m].x);
-            lam[m].y = fmaf(gj, h[m].y, lam[m].y);
-          }
+          ej2 = fma2(a[m], h[m], ej2);
+          if constexpr (ADJ) lam[m] = fma2(bc(gj), h[m], lam[m]);
         }
       }
-      ej = warp_sum(ej);
+      ej = warp_sum(ej + hsum(ej2));
       if ((tid & 31) == 0) atomicAdd(&ka.eacc[(size_t)u * ka.O + j], (double)ej);
     }
     if constexpr (ADJ) {
 #pragma unroll
       for (int m = 0; m < MC; ++m) {
-        lam[m].x = fmaf(dg[m], a[m].x, lam[m].x);
-        lam[m].y = fmaf(dg[m], a[m].y, lam[m].y);
+        lam[m] = fma2(bc(dg[m]), a[m], lam[m]);
         s_lam[ph_tid ^ ka.L.soff[m0 + m]] = lam[m];
       }
     }
@@ -1055,8 +1111,8 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
     const uint32_t basis = (uint32_t)ka.basis[u];
     active = (basis & ~ka.L.tile_mask) == goff;
     const uint32_t lb = gather_bits(basis, ka.L.runs, ka.L.n_runs);
-#pragma unroll
     const uint32_t pt = swz(tid);
+#pragma unroll
     for (int m = 0; m < R; ++m) {
       const uint32_t l = (uint32_t)m * nthr | tid;
       s_psi[pt ^ ka.L.soff[m]] = make_float2((active && l == lb) ? 1.f : 0.f, 0.f);
@@ -1175,7 +1231,15 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __res
     }
     for (int e = 0; e < 2; ++e) {
       const int v = tid + e * kPrepThreads;
-      if (v < entries) write_c(out, v, acc[e]);
+      if (v >= entries) continue;
+      if (job.b) {  // register phase table: (re, im, -im, im), the form the packed complex multiply reads
+        out[4 * v + 0] = (float)acc[e].re;
+        out[4 * v + 1] = (float)acc[e].im;
+        out[4 * v + 2] = -(float)acc[e].im;
+        out[4 * v + 3] = (float)acc[e].im;
+      } else {
+        write_c(out, v, acc[e]);
+      }
     }
     return;
   }

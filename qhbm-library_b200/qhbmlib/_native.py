@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libqhbm_b200.so")
+# QHBM_B200_LIB: development switch (A/B timing of two builds of the same C ABI); default = the in-tree build
+LIB_PATH = os.environ.get("QHBM_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libqhbm_b200.so")
 
 GATE_DTYPE = np.dtype([
     ("type", np.int32), ("q0", np.int32), ("q1", np.int32), ("nparams", np.int32),

@@ -127,7 +127,14 @@ static void prep(const HostPlan& hp, const float* symbols, int mode, std::vector
             cd d = m[sel * dim + sel];
             acc = acc * (job.a ? conj(d) : d);
           }
-          wr(job.out, v, acc);
+          if (job.b) {  // register phase table: 4 floats per entry (re, im, -im, im)
+            coef[job.out + 4 * v + 0] = (float)acc.re;
+            coef[job.out + 4 * v + 1] = (float)acc.im;
+            coef[job.out + 4 * v + 2] = -(float)acc.im;
+            coef[job.out + 4 * v + 3] = (float)acc.im;
+          } else {
+            wr(job.out, v, acc);
+          }
         }
       } break;
     }
@@ -246,7 +253,7 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
         case OP_MAT2: mat2(a, op.p0 ? 2 : 0, op.coef, nullptr, nullptr); if (both) mat2(b, op.p0 ? 2 : 0, op.coef, nullptr, nullptr); break;
         case OP_DCONST_TAB: F *= cf(c, op.coef, (gbase >> op.aux0) & op.aux1); break;
         case OP_DCONST_PAIR: { int sel = (gbase >> op.aux0) & 1; if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1); F *= cf(c, op.coef, sel); } break;
-        case OP_DREG_TAB: for (int r = 0; r < R; ++r) { cplx k = F * cf(c, op.coef, r); a[r] *= k; if (both) b[r] *= k; } F = 1; break;
+        case OP_DREG_TAB: for (int r = 0; r < R; ++r) { cplx k = F * cf(c, op.coef, 2 * r); a[r] *= k; if (both) b[r] *= k; } F = 1; break;
         case OP_DAPPLY: for (int r = 0; r < R; ++r) { a[r] *= F; if (both) b[r] *= F; } F = 1; break;
         case OP_DCROSS: { int cb = (gbase >> op.aux0) & 1; for (int r = 0; r < R; ++r) { cplx k = cf(c, op.coef, 2 * cb + ((r >> op.p0) & 1)); a[r] *= k; if (both) b[r] *= k; } } break;
         case OP_GRAD_MAT1: {

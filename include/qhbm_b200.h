@@ -234,6 +234,25 @@ int qhbm_categorical_sample(const float* d_logits, int64_t n_rows, uint64_t row_
                             int64_t n_samples, uint64_t* d_samples, void* d_workspace,
                             void* stream);
 
+/* The same sampler in two steps, for (a) many draws from unchanged logits and (b) a row range that is
+ * sharded over ranks.
+ *   qhbm_categorical_prepare: block prefix sums of exp(l - max) into d_workspace.  use_given_max != 0:
+ *     `given_max` (the GLOBAL maximum from the merged sweep statistics) replaces the local maximum, which
+ *     also saves the max pass over the logits.  The local mass sum_rows exp(l - max) is the float64 at
+ *     byte offset 256 + 8 * ceil(n_rows / 256) of the workspace.
+ *   qhbm_categorical_draw: mass_total <= 0: every sample k in [first_sample, first_sample + n_samples) is
+ *     drawn from the local rows, as qhbm_categorical_sample does.  mass_total > 0: sample k is drawn here
+ *     iff u_k * mass_total lies in [mass_begin, mass_end) -- this rank's interval of the global cumulative
+ *     mass -- and d_samples[k] is left untouched otherwise, so that the ranks' outputs (zero-initialised)
+ *     add up to exactly the samples a single GPU would draw from the whole range
+ *     (ebm.py:487-492 semantics, independent of the number of ranks). */
+int qhbm_categorical_prepare(const float* d_logits, int64_t n_rows, int32_t use_given_max, float given_max,
+                             void* d_workspace, void* stream);
+int qhbm_categorical_draw(const float* d_logits, int64_t n_rows, uint64_t row_offset, const void* d_workspace,
+                          double mass_begin, double mass_end, double mass_total, uint64_t seed0,
+                          uint64_t seed1, uint64_t first_sample, int64_t n_samples, uint64_t* d_samples,
+                          void* stream);
+
 /* Replaces tfd.Bernoulli(logits, int8).sample(N, seed) (ebm.py:559-561): packed keys,
  * bit column j lands at key bit h_shift[j]. */
 int qhbm_bernoulli_sample(const float* d_logits, int32_t n_bits, const int32_t* h_shift,
@@ -244,6 +263,20 @@ int qhbm_bernoulli_sample(const float* d_logits, int32_t n_bits, const int32_t* 
  *   d_out[w] = sum_u count[u]*vals[u,w]   (f64[width]),  d_out[width] = sum_u count[u]. */
 int qhbm_weighted_sum(const int32_t* d_counts, const float* d_vals, int64_t n_rows,
                       int32_t width, double* d_out, void* stream);
+
+/* Backward of EnergyInference._expectation (ebm.py:282-325) w.r.t. the parameters theta of a
+ * parity-feature energy E(x) = sum_t theta_t (-1)^{parity(x & mask_t)} (BernoulliEnergy, KOBE;
+ * Jacobian of energy_utils.py:97-110), over the unique rows handed in:
+ *   d_grad_theta[t] = scale * sum_u (count_u / total) f_t(x_u) (E[c] - c_u),
+ *   c_u = sum_j d_upstream[j] d_vals[u, j],  E[c] = sum_j d_upstream[j] d_average[j]
+ * i.e. E[c] E[dE/dtheta_t] - E[c dE/dtheta_t].  *d_total_count: sum of counts over ALL rows (the
+ * rows may be one rank's shard; the partial results then add up over ranks).
+ * d_workspace: n_rows + 4 floats. */
+int qhbm_score_gradient(const uint64_t* d_keys, const int32_t* d_counts, int64_t n_rows,
+                        const float* d_vals, int32_t width, const float* d_upstream,
+                        const float* d_average, const int32_t* d_masks, int32_t n_terms,
+                        const double* d_total_count, float scale, float* d_grad_theta,
+                        float* d_workspace, void* stream);
 
 #ifdef __cplusplus
 }

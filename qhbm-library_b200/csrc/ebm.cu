@@ -60,17 +60,22 @@ struct UniqueWs {
 };
 __global__ void uq_init(UniqueWs w) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < w.cap) { w.tkeys[i] = kEmptyKey; w.tfirst[i] = 0x7fffffff; w.tcount[i] = 0; }
+  if (i < w.cap) w.tkeys[i] = kEmptyKey;
+  if (i <= w.cap) { w.tfirst[i] = 0x7fffffff; w.tcount[i] = 0; }  // entry `cap`: the key equal to kEmptyKey
 }
 __global__ void uq_insert(const uint64_t* __restrict__ keys, int64_t n, UniqueWs w) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long k = keys[i];
   uint64_t h = mix64(k) & (w.cap - 1);
-  while (true) {
-    const unsigned long long old = atomicCAS(&w.tkeys[h], kEmptyKey, k);
-    if (old == kEmptyKey || old == k) break;
-    h = (h + 1) & (w.cap - 1);
+  if (k == kEmptyKey) {
+    h = w.cap;  // the one key that cannot live in the table (it marks empty slots) has its own entry
+  } else {
+    while (true) {
+      const unsigned long long old = atomicCAS(&w.tkeys[h], kEmptyKey, k);
+      if (old == kEmptyKey || old == k) break;
+      h = (h + 1) & (w.cap - 1);
+    }
   }
   atomicMin(&w.tfirst[h], (int32_t)i);
   atomicAdd(&w.tcount[h], 1);
@@ -184,6 +189,50 @@ __global__ void wsum_kernel(const int32_t* __restrict__ counts, const float* __r
       for (int64_t r = r0; r < r1; ++r) s += (double)counts[r];
     }
     atomicAdd(&out[c], s);
+  }
+}
+
+// ------------------------------------------------------------------ score-function gradient (f1)
+// EnergyInference._expectation's backward for energies E = sum_t theta_t f_t(x) with parity features
+// f_t(x) = (-1)^{parity(x & mask_t)} (Bernoulli: single-bit masks, KOBE: Z-strings; reference
+// ebm.py:282-325 with the Jacobian of energy_utils.py:97-110):
+//   d/dtheta_t = E[c] E[f_t] - E[c f_t],  c_u = sum_j upstream_j values[u, j],  E[c] = upstream . average.
+// Kernel 1: c_u for every row (+ E[c]).  Kernel 2: one CTA per term, float64 accumulation.
+__global__ void score_c_kernel(const float* __restrict__ vals, int64_t n_rows, int width,
+                               const float* __restrict__ upstream, const float* __restrict__ avg,
+                               float* __restrict__ c_out, float* __restrict__ s0_out) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u == 0) {
+    double s0 = 0.0;
+    for (int j = 0; j < width; ++j) s0 += (double)upstream[j] * (double)avg[j];
+    *s0_out = (float)s0;
+  }
+  if (u >= n_rows) return;
+  float c = 0.f;
+  for (int j = 0; j < width; ++j) c = fmaf(upstream[j], vals[u * width + j], c);
+  c_out[u] = c;
+}
+__global__ void __launch_bounds__(256) score_term_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ counts,
+                                                         int64_t n_rows, const float* __restrict__ c,
+                                                         const float* __restrict__ s0, const int32_t* __restrict__ masks,
+                                                         const double* __restrict__ total, float scale,
+                                                         float* __restrict__ out) {
+  __shared__ double s_w[8];
+  const uint64_t mask = (uint64_t)(uint32_t)masks[blockIdx.x];
+  const float e_c = *s0;
+  double acc = 0.0;
+  for (int64_t u = threadIdx.x; u < n_rows; u += blockDim.x) {
+    const float f = (__popcll(keys[u] & mask) & 1) ? -1.f : 1.f;
+    acc += (double)counts[u] * (double)(f * (e_c - c[u]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += s_w[k];
+    out[blockIdx.x] = (float)((double)scale * t / *total);
   }
 }
 
@@ -786,13 +835,21 @@ __global__ void __launch_bounds__(1024) cat_scan_kernel(double* __restrict__ bsu
 __global__ void cat_sample_kernel(const float* __restrict__ logits, int64_t n, const float* __restrict__ gmax,
                                   const double* __restrict__ bpre, int64_t nblocks, uint64_t row_offset,
                                   uint64_t seed0, uint64_t seed1, uint64_t first, int64_t n_samples,
-                                  uint64_t* __restrict__ out) {
+                                  uint64_t* __restrict__ out, double mass_begin, double mass_end, double mass_total) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_samples) return;
   const Philox ph = make_philox(seed0, seed1);
   const uint4 r = ph(first + (uint64_t)k, 0x43415453u);
-  const double total = bpre[nblocks];
-  const double target = u01_53(r.x, r.y) * total;
+  double target;
+  if (mass_total > 0.0) {
+    // one shard of a row range split over ranks: sample k belongs to the rank whose mass interval
+    // [mass_begin, mass_end) holds its point of the GLOBAL cumulative mass; the others leave out[k] alone
+    const double t = u01_53(r.x, r.y) * mass_total;
+    if (!(t >= mass_begin && t < mass_end)) return;
+    target = t - mass_begin;
+  } else {
+    target = u01_53(r.x, r.y) * bpre[nblocks];
+  }
   // largest block b with bpre[b] <= target
   int64_t lo = 0, hi = nblocks - 1;
   while (lo < hi) {
@@ -860,8 +917,8 @@ static UniqueWs carve_unique(void* ws, int64_t n) {
   const int64_t nblocks = (n + kScanBlock - 1) / kScanBlock;
   char* p = reinterpret_cast<char*>(ws);
   w.tkeys = reinterpret_cast<unsigned long long*>(p); p += align_up(w.cap * 8);
-  w.tfirst = reinterpret_cast<int32_t*>(p); p += align_up(w.cap * 4);
-  w.tcount = reinterpret_cast<int32_t*>(p); p += align_up(w.cap * 4);
+  w.tfirst = reinterpret_cast<int32_t*>(p); p += align_up((w.cap + 1) * 4);
+  w.tcount = reinterpret_cast<int32_t*>(p); p += align_up((w.cap + 1) * 4);
   w.slot = reinterpret_cast<int32_t*>(p); p += align_up((size_t)n * 4);
   w.rank = reinterpret_cast<int32_t*>(p); p += align_up((size_t)n * 4);
   w.bsum = reinterpret_cast<int32_t*>(p); p += align_up((size_t)(nblocks + 1) * 4);
@@ -913,7 +970,7 @@ int64_t qhbm_unique_workspace_bytes(int64_t n_rows) {
   if (n_rows < 0) return -1;
   const uint64_t cap = std::max<uint64_t>(1024, next_pow2((uint64_t)n_rows * 2));
   const int64_t nblocks = (n_rows + kScanBlock - 1) / kScanBlock;
-  return (int64_t)(align_up(cap * 8) + 2 * align_up(cap * 4) + 2 * align_up((size_t)n_rows * 4) +
+  return (int64_t)(align_up(cap * 8) + 2 * align_up((cap + 1) * 4) + 2 * align_up((size_t)n_rows * 4) +
                    align_up((size_t)(nblocks + 1) * 4) + 256);
 }
 
@@ -930,7 +987,7 @@ int qhbm_unique_with_counts(const uint64_t* d_keys, int64_t n_rows, uint64_t* d_
     UniqueWs w = carve_unique(d_workspace, n_rows);
     const int64_t nblocks = (n_rows + kScanBlock - 1) / kScanBlock;
     const unsigned g = (unsigned)((n_rows + 255) / 256);
-    uq_init<<<(unsigned)((w.cap + 255) / 256), 256, 0, s>>>(w);
+    uq_init<<<(unsigned)((w.cap + 256) / 256), 256, 0, s>>>(w);
     uq_insert<<<g, 256, 0, s>>>(d_keys, n_rows, w);
     uq_flag_scan<<<(unsigned)nblocks, kScanBlock, 0, s>>>(n_rows, w);
     uq_scan_blocks<<<1, 1024, 0, s>>>(nblocks, w, d_n_unique);
@@ -962,6 +1019,28 @@ int qhbm_weighted_sum(const int32_t* d_counts, const float* d_vals, int64_t n_ro
     if (n_rows <= 0) return;
     const int threads = std::min(1024, ((width + 1 + 31) / 32) * 32);
     wsum_kernel<<<(unsigned)((n_rows + kWsumStrip - 1) / kWsumStrip), threads, 0, s>>>(d_counts, d_vals, n_rows, width, d_out);
+    QHBM_CUDA(cudaGetLastError());
+  });
+}
+
+int qhbm_score_gradient(const uint64_t* d_keys, const int32_t* d_counts, int64_t n_rows, const float* d_vals,
+                        int32_t width, const float* d_upstream, const float* d_average, const int32_t* d_masks,
+                        int32_t n_terms, const double* d_total_count, float scale, float* d_grad_theta,
+                        float* d_workspace, void* stream) {
+  return guarded([&] {
+    if (n_rows < 0 || width < 1 || n_terms < 0) throw std::runtime_error("bad sizes");
+    if (!d_workspace) throw std::runtime_error("workspace is null");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_terms == 0) return;
+    if (n_rows == 0) {
+      QHBM_CUDA(cudaMemsetAsync(d_grad_theta, 0, sizeof(float) * n_terms, s));
+      return;
+    }
+    float* s0 = d_workspace;
+    float* c = d_workspace + 4;
+    score_c_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, s>>>(d_vals, n_rows, width, d_upstream, d_average, c, s0);
+    score_term_kernel<<<(unsigned)n_terms, 256, 0, s>>>(d_keys, d_counts, n_rows, c, s0, d_masks, d_total_count, scale,
+                                                        d_grad_theta);
     QHBM_CUDA(cudaGetLastError());
   });
 }
@@ -1027,26 +1106,59 @@ int64_t qhbm_sample_workspace_bytes(int64_t n_rows) {
   return 256 + 8 * (nblocks + 2);
 }
 
+static void cat_prepare(const float* d_logits, int64_t n_rows, bool use_given_max, float given_max, void* d_workspace,
+                        cudaStream_t s) {
+  if (n_rows < 1) throw std::runtime_error("n_rows must be >= 1");
+  if (!d_workspace) throw std::runtime_error("workspace is null");
+  float* gmax = reinterpret_cast<float*>(d_workspace);
+  double* bsum = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + 256);
+  const int64_t nblocks = (n_rows + kCatBlock - 1) / kCatBlock;
+  const float init = use_given_max ? given_max : -INFINITY;
+  QHBM_CUDA(cudaMemcpyAsync(gmax, &init, sizeof(float), cudaMemcpyHostToDevice, s));
+  if (!use_given_max)
+    cat_max_kernel<<<(unsigned)std::min<int64_t>((n_rows + 255) / 256, 148 * 8), 256, 0, s>>>(d_logits, n_rows, gmax);
+  cat_blocksum_kernel<<<(unsigned)nblocks, kCatBlock, 0, s>>>(d_logits, n_rows, gmax, bsum);
+  cat_scan_kernel<<<1, 1024, 0, s>>>(bsum, nblocks);
+  QHBM_CUDA(cudaGetLastError());
+}
+
+static void cat_draw(const float* d_logits, int64_t n_rows, uint64_t row_offset, const void* d_workspace,
+                     double mass_begin, double mass_end, double mass_total, uint64_t seed0, uint64_t seed1,
+                     uint64_t first_sample, int64_t n_samples, uint64_t* d_samples, cudaStream_t s) {
+  if (n_samples < 0) throw std::runtime_error("n_samples must be >= 0");
+  if (n_samples == 0) return;
+  const float* gmax = reinterpret_cast<const float*>(d_workspace);
+  const double* bsum = reinterpret_cast<const double*>(reinterpret_cast<const char*>(d_workspace) + 256);
+  const int64_t nblocks = (n_rows + kCatBlock - 1) / kCatBlock;
+  cat_sample_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, s>>>(d_logits, n_rows, gmax, bsum, nblocks, row_offset,
+                                                                       seed0, seed1, first_sample, n_samples, d_samples,
+                                                                       mass_begin, mass_end, mass_total);
+  QHBM_CUDA(cudaGetLastError());
+}
+
 int qhbm_categorical_sample(const float* d_logits, int64_t n_rows, uint64_t row_offset, uint64_t seed0,
                             uint64_t seed1, uint64_t first_sample, int64_t n_samples, uint64_t* d_samples,
                             void* d_workspace, void* stream) {
   return guarded([&] {
+    cat_prepare(d_logits, n_rows, false, 0.f, d_workspace, (cudaStream_t)stream);
+    cat_draw(d_logits, n_rows, row_offset, d_workspace, 0.0, 0.0, 0.0, seed0, seed1, first_sample, n_samples, d_samples,
+             (cudaStream_t)stream);
+  });
+}
+
+int qhbm_categorical_prepare(const float* d_logits, int64_t n_rows, int32_t use_given_max, float given_max,
+                             void* d_workspace, void* stream) {
+  return guarded([&] { cat_prepare(d_logits, n_rows, use_given_max != 0, given_max, d_workspace, (cudaStream_t)stream); });
+}
+
+int qhbm_categorical_draw(const float* d_logits, int64_t n_rows, uint64_t row_offset, const void* d_workspace,
+                          double mass_begin, double mass_end, double mass_total, uint64_t seed0, uint64_t seed1,
+                          uint64_t first_sample, int64_t n_samples, uint64_t* d_samples, void* stream) {
+  return guarded([&] {
     if (n_rows < 1) throw std::runtime_error("n_rows must be >= 1");
-    if (n_samples < 0) throw std::runtime_error("n_samples must be >= 0");
     if (!d_workspace) throw std::runtime_error("workspace is null");
-    cudaStream_t s = (cudaStream_t)stream;
-    float* gmax = reinterpret_cast<float*>(d_workspace);
-    double* bsum = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + 256);
-    const int64_t nblocks = (n_rows + kCatBlock - 1) / kCatBlock;
-    const float ninf = -INFINITY;
-    QHBM_CUDA(cudaMemcpyAsync(gmax, &ninf, sizeof(float), cudaMemcpyHostToDevice, s));
-    cat_max_kernel<<<(unsigned)std::min<int64_t>((n_rows + 255) / 256, 148 * 8), 256, 0, s>>>(d_logits, n_rows, gmax);
-    cat_blocksum_kernel<<<(unsigned)nblocks, kCatBlock, 0, s>>>(d_logits, n_rows, gmax, bsum);
-    cat_scan_kernel<<<1, 1024, 0, s>>>(bsum, nblocks);
-    if (n_samples > 0)
-      cat_sample_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, s>>>(d_logits, n_rows, gmax, bsum, nblocks, row_offset,
-                                                                           seed0, seed1, first_sample, n_samples, d_samples);
-    QHBM_CUDA(cudaGetLastError());
+    cat_draw(d_logits, n_rows, row_offset, d_workspace, mass_begin, mass_end, mass_total, seed0, seed1, first_sample,
+             n_samples, d_samples, (cudaStream_t)stream);
   });
 }
 

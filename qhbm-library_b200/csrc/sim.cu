@@ -30,6 +30,7 @@ struct DevBuf {
     if (n <= cap) return;
     if (p) QHBM_CUDA(cudaFree(p));
     p = nullptr;
+    cap = 0;  // a failed cudaMalloc below must not leave a stale capacity behind
     QHBM_CUDA(cudaMalloc(&p, n * sizeof(T)));
     cap = n;
   }
@@ -68,16 +69,52 @@ struct qhbm_plan {
   int chunk = 1;
   int sm_count = 148;
   std::mutex mu;
+  // The scratch buffers above are per plan, so device work of two calls on the same plan must not
+  // overlap: every call records `done` on its stream and the next call, if it arrives on another
+  // stream, waits for it there (calls on one stream are ordered anyway).
+  cudaEvent_t done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
+  ~qhbm_plan() { if (done) cudaEventDestroy(done); }
 };
+
+namespace {
+// Holds the plan's host lock and orders this call's device work after the previous call's.
+struct PlanUse {
+  qhbm_plan* p;
+  cudaStream_t s;
+  std::lock_guard<std::mutex> lk;
+  PlanUse(qhbm_plan* plan, cudaStream_t stream) : p(plan), s(stream), lk(plan->mu) {
+    if (!p->done) QHBM_CUDA(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+    if (p->used && p->last_stream != s) QHBM_CUDA(cudaStreamWaitEvent(s, p->done, 0));
+  }
+  ~PlanUse() {
+    cudaEventRecord(p->done, s);
+    p->last_stream = s;
+    p->used = true;
+  }
+};
+}  // namespace
 
 namespace {
 
 template <int K, bool ADJ>
 void launch_sweep(const KernelArgs& ka, int n_states, int tiles, int threads, size_t smem, cudaStream_t s) {
-  // per-device, per-function attribute; setting it on every launch keeps the library free of global state
-  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<K, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sweep_kernel<K, ADJ><<<(unsigned)(n_states * tiles), threads, smem, s>>>(ka);
   QHBM_CUDA(cudaGetLastError());
+}
+
+// Opt in to large dynamic shared memory once per plan creation (the attribute is per device and
+// function and sticky; launches then only pass the size they need).
+void allow_large_smem() {
+  int dev = 0, optin = 0;
+  QHBM_CUDA(cudaGetDevice(&dev));
+  QHBM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int dyn = optin - (int)sizeof(float4) * (kStageOps + kStageCoef / 4) - 1024;
+  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
 }
 
 void launch_any(const qhbm_plan* p, bool adj, const KernelArgs& ka, int n_states, cudaStream_t s) {
@@ -347,6 +384,7 @@ int qhbm_plan_create(const qhbm_circuit_t* c, const qhbm_ops_t* o, int32_t with_
       QHBM_CUDA(cudaGetDevice(&dev));
       QHBM_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev));
       p->chunk = default_chunk(p);
+      allow_large_smem();
     } catch (...) {
       delete p;
       throw;
@@ -374,7 +412,7 @@ int qhbm_expectation_forward(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_
                              const float* d_symbols, float* d_out, void* stream) {
   return guarded([&] {
     if (!p) throw std::runtime_error("null plan");
-    std::lock_guard<std::mutex> lk(p->mu);
+    PlanUse use(p, (cudaStream_t)stream);
     run_expectation(p, d_basis_idx, n_states, d_symbols, nullptr, d_out, nullptr, 0, QHBM_GRAD_EXACT, false,
                     (cudaStream_t)stream);
   });
@@ -387,7 +425,7 @@ int qhbm_expectation_adjoint(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_
     if (!p) throw std::runtime_error("null plan");
     if (grad_mode < 0 || grad_mode > 2) throw std::runtime_error("bad grad_mode");
     if (!d_dgrad) throw std::runtime_error("d_dgrad is null");
-    std::lock_guard<std::mutex> lk(p->mu);
+    PlanUse use(p, (cudaStream_t)stream);
     run_expectation(p, d_basis_idx, n_states, d_symbols, d_dgrad, d_out, d_grad_out, per_state, grad_mode, true,
                     (cudaStream_t)stream);
   });
@@ -398,7 +436,7 @@ int qhbm_expectation_host(qhbm_plan_t* p, const uint64_t* h_basis_idx, int64_t n
                           void* stream) {
   return guarded([&] {
     if (!p) throw std::runtime_error("null plan");
-    std::lock_guard<std::mutex> lk(p->mu);
+    PlanUse use(p, (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     const HostPlan& hp = p->hp;
     const int64_t U = n_states;
@@ -426,7 +464,7 @@ int qhbm_final_states(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_sta
                       float* d_states_out, void* stream) {
   return guarded([&] {
     if (!p) throw std::runtime_error("null plan");
-    std::lock_guard<std::mutex> lk(p->mu);
+    PlanUse use(p, (cudaStream_t)stream);
     run_states(p, d_basis_idx, n_states, d_symbols, reinterpret_cast<float2*>(d_states_out), (cudaStream_t)stream);
   });
 }
@@ -435,7 +473,7 @@ int qhbm_debug_state(qhbm_plan_t* p, uint64_t basis_idx, const float* d_symbols,
                      void* stream) {
   return guarded([&] {
     if (!p) throw std::runtime_error("null plan");
-    std::lock_guard<std::mutex> lk(p->mu);
+    PlanUse use(p, (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     p->d_basis.reserve(1);
     QHBM_CUDA(cudaMemcpyAsync(p->d_basis.p, &basis_idx, sizeof(uint64_t), cudaMemcpyHostToDevice, s));

@@ -69,6 +69,10 @@ SIGNATURES = {
     "qhbm_ebm_sweep": (ctypes.c_int, [ctypes.POINTER(EnergyDesc), _U64, _U64, _VP, _VP, _VP]),
     "qhbm_sample_workspace_bytes": (_I64, [_I64]),
     "qhbm_categorical_sample": (ctypes.c_int, [_VP, _I64, _U64, _U64, _U64, _U64, _I64, _VP, _VP, _VP]),
+    "qhbm_score_gradient": (ctypes.c_int, [_VP, _VP, _I64, _VP, _I32, _VP, _VP, _VP, _I32, _VP, ctypes.c_float, _VP, _VP, _VP]),
+    "qhbm_categorical_prepare": (ctypes.c_int, [_VP, _I64, _I32, ctypes.c_float, _VP, _VP]),
+    "qhbm_categorical_draw": (ctypes.c_int, [_VP, _I64, _U64, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                             _U64, _U64, _U64, _I64, _VP, _VP]),
     "qhbm_bernoulli_sample": (ctypes.c_int, [_VP, _I32, _VP, _U64, _U64, _U64, _I64, _VP, _VP]),
     "qhbm_weighted_sum": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _VP]),
 }

@@ -12,6 +12,8 @@ import functools
 import math
 import numbers
 
+import hashlib
+
 import numpy as np
 
 from qhbmlib import _native as nat
@@ -537,7 +539,23 @@ class OperatorTensor:
     return len(self.pauli_sums)
 
   def tables(self, qubits):
-    """(terms TERM_DTYPE[], offsets int32[O+1]) over the sorted qubit list."""
+    """(terms TERM_DTYPE[], offsets int32[O+1]) over the sorted qubit list (memoised per qubit list:
+    like a tf.string tensor, the observables do not change after conversion)."""
+    memo = self.__dict__.setdefault("_tables_memo", {})
+    key = tuple(qubits)
+    if key not in memo:
+      terms, offsets = self._build_tables(qubits)
+      digest = hashlib.sha1(terms.tobytes() + offsets.tobytes()).hexdigest()
+      memo.clear()
+      memo[key] = (terms, offsets, digest)
+    return memo[key][0], memo[key][1]
+
+  def tables_digest(self, qubits):
+    """Content hash of `tables(qubits)`: the key under which compiled plans are cached."""
+    self.tables(qubits)
+    return self._tables_memo[tuple(qubits)][2]
+
+  def _build_tables(self, qubits):
     n = len(qubits)
     qpos = {q: i for i, q in enumerate(qubits)}
     rows, offsets = [], [0]

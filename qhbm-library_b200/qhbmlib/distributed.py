@@ -8,11 +8,34 @@ follows SURVEY section 8(e):
     rebasing to the common max; sampling first splits the sample count over ranks with a
     multinomial drawn identically on every rank from the shared seed.
 """
+import contextlib
 import math
+import threading
 
 import numpy as np
 import torch
 import torch.distributed as dist
+
+_local = threading.local()
+
+
+@contextlib.contextmanager
+def local_shard():
+  """Inside this context the inference engines do NOT shard again: the caller already handed them
+  this rank's share (EnergyInference._expectation shards the unique bitstrings and then calls the
+  user's function, which usually ends in QuantumInference.expectation)."""
+  prev = getattr(_local, "depth", 0)
+  _local.depth = prev + 1
+  try:
+    yield
+  finally:
+    _local.depth = prev
+
+
+def active(group=None):
+  """True when the engines should shard their data-parallel work over the ranks of `group`."""
+  return (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and
+          getattr(_local, "depth", 0) == 0)
 
 
 def world(group=None):
@@ -114,3 +137,103 @@ def sharded_ebm_sweep(descriptor, n_bits, group=None, want_logits=True, device="
   log_z = m + math.log(s)
   masses = [tr[0] + math.log(tr[1]) if tr[1] > 0 else -math.inf for tr in triples]
   return logits, (lo, hi), log_z, log_z - t / s, masses
+
+
+# ----------------------------------------------------------------------------------------------
+# Autograd glue.  Convention ("average", the one DistributedDataParallel uses): every rank computes the
+# SAME scalar loss from all-reduced / all-gathered values, each rank's backward pass only sees its own
+# shard, and `sync_gradients` AVERAGES parameter gradients over the ranks afterwards.  For that average to
+# equal the true gradient, the backward of every collective multiplies by the world size; quantities that
+# are computed identically on all ranks (regularisers, closed-form log-partition terms) then come out
+# right as well, because their gradients are already identical on every rank.
+# ----------------------------------------------------------------------------------------------
+class _AllReduceSum(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, group):
+    ctx.world = dist.get_world_size(group)
+    y = x.detach().clone()
+    dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+    return y
+
+  @staticmethod
+  def backward(ctx, grad):
+    return grad * ctx.world, None
+
+
+def all_reduce_sum(x, group=None):
+  """Differentiable sum over ranks of a tensor of per-rank partial sums (ONE collective)."""
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    return x
+  return _AllReduceSum.apply(x, group)
+
+
+class _ScaleGrad(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, factor):
+    ctx.factor = factor
+    return x.view_as(x)
+
+  @staticmethod
+  def backward(ctx, grad):
+    return grad * ctx.factor, None
+
+
+def shard_term(x, group=None):
+  """Marks a per-rank partial term whose VALUE needs no communication (e.g. the zero-valued
+  score-function surrogates) but whose gradient is one shard of a sum over ranks."""
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    return x
+  return _ScaleGrad.apply(x, float(dist.get_world_size(group)))
+
+
+class _AllGatherRows(torch.autograd.Function):
+  """Concatenates the ranks' row blocks (sizes from shard_range) on every rank."""
+
+  @staticmethod
+  def forward(ctx, x, n_total, group):
+    rank, ws = dist.get_rank(group), dist.get_world_size(group)
+    ctx.world, ctx.range = ws, shard_range(n_total, rank, ws)
+    sizes = [shard_range(n_total, r, ws) for r in range(ws)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((width,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    pad[:x.shape[0]] = x.detach()
+    out = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(out, sizes)], 0)
+
+  @staticmethod
+  def backward(ctx, grad):
+    lo, hi = ctx.range
+    return grad[lo:hi] * ctx.world, None, None
+
+
+def all_gather_rows(x, n_total, group=None):
+  """Differentiable all-gather of contiguous row shards (x = rows shard_range(n_total, rank, world))."""
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    return x
+  return _AllGatherRows.apply(x, n_total, group)
+
+
+def sync_gradients(parameters, group=None):
+  """Averages `.grad` of the given parameters over the ranks with one all-reduce of a flat buffer
+  (call after `loss.backward()`; DistributedDataParallel does the same thing).  Parameters without a
+  gradient on this rank contribute zeros."""
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    return
+  params = [p for p in parameters if p.requires_grad]
+  if not params:
+    return
+  flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).double() for p in params])
+  dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+  flat /= dist.get_world_size(group)
+  off = 0
+  for p in params:
+    n = p.numel()
+    g = flat[off:off + n].reshape(p.shape).to(p.dtype)
+    if p.grad is None:
+      p.grad = g.clone()
+    else:
+      p.grad.copy_(g)
+    off += n

@@ -241,6 +241,24 @@ def weighted_sum(counts, vals):
   return out
 
 
+def score_gradient(keys, counts, vals, upstream, average, masks, total_count, scale=1.0):
+  """f32[T]: E[c] E[f_t] - E[c f_t] over the given unique rows (see qhbm_score_gradient)."""
+  keys = _require_cuda(keys, "keys", torch.int64)
+  counts = _require_cuda(counts, "counts", torch.int32)
+  vals = _require_cuda(vals, "vals", torch.float32)
+  upstream = _require_cuda(upstream, "upstream", torch.float32)
+  average = _require_cuda(average, "average", torch.float32)
+  masks = _require_cuda(masks, "masks", torch.int32)
+  total_count = _require_cuda(total_count, "total_count", torch.float64)
+  n_rows, width = vals.shape
+  out = torch.empty((masks.shape[0],), dtype=torch.float32, device=keys.device)
+  ws = torch.empty((n_rows + 4,), dtype=torch.float32, device=keys.device)
+  nat.check(nat.lib().qhbm_score_gradient(nat.ptr(keys), nat.ptr(counts), n_rows, nat.ptr(vals), width,
+                                          nat.ptr(upstream), nat.ptr(average), nat.ptr(masks), masks.shape[0],
+                                          nat.ptr(total_count), float(scale), nat.ptr(out), nat.ptr(ws), _stream()))
+  return out
+
+
 class EnergyDescriptor:
   """Device-side description of an energy function for the EBM kernels."""
 
@@ -294,6 +312,36 @@ def categorical_sample(logits, n_samples, seed, first_sample=0, row_offset=0):
                                               int(seed[1]), first_sample, n_samples, nat.ptr(out), nat.ptr(ws),
                                               _stream()))
   return out
+
+
+class CategoricalSampler:
+  """Prefix sums over fixed logits, prepared once and reused by every draw (the reference rebuilds the
+  tfd.Categorical only when the energy variables change, ebm.py:467-469).  `given_max`: the global
+  maximum when the logits are one shard of a range split over ranks."""
+
+  def __init__(self, logits, given_max=None):
+    self.logits = _require_cuda(logits, "logits", torch.float32)
+    n = self.logits.shape[0]
+    self.ws = torch.empty((nat.lib().qhbm_sample_workspace_bytes(n),), dtype=torch.uint8, device=logits.device)
+    nat.check(nat.lib().qhbm_categorical_prepare(nat.ptr(self.logits), n, int(given_max is not None),
+                                                 float(given_max or 0.0), nat.ptr(self.ws), _stream()))
+    self._nblocks = (n + 255) // 256
+
+  def local_mass(self):
+    """float64 device scalar: sum_rows exp(logit - max)."""
+    off = 256 + 8 * self._nblocks
+    return self.ws[off:off + 8].view(torch.float64)
+
+  def draw(self, n_samples, seed, first_sample=0, row_offset=0, mass_interval=None, out=None):
+    """int64[n_samples] row indices.  mass_interval = (begin, end, total): only the samples whose point of
+    the global cumulative mass falls in [begin, end) are written (others keep the value in `out`)."""
+    if out is None:
+      out = torch.zeros((n_samples,), dtype=torch.int64, device=self.logits.device)
+    b, e, t = mass_interval if mass_interval is not None else (0.0, 0.0, 0.0)
+    nat.check(nat.lib().qhbm_categorical_draw(nat.ptr(self.logits), self.logits.shape[0], int(row_offset),
+                                              nat.ptr(self.ws), float(b), float(e), float(t), int(seed[0]),
+                                              int(seed[1]), int(first_sample), int(n_samples), nat.ptr(out), _stream()))
+    return out
 
 
 def bernoulli_sample(logits, shifts, n_samples, seed, first_sample=0):

@@ -15,6 +15,7 @@ import secrets
 import torch
 
 from qhbmlib import _native as nat
+from qhbmlib import distributed as qd
 from qhbmlib import engine
 from qhbmlib import utils
 
@@ -28,6 +29,12 @@ def preface_inference(f):
     return f(self, *args, **kwargs)
 
   return wrapper
+
+
+def _leaves(structure):
+  out = []
+  map_structure(out.append, structure)
+  return out
 
 
 def map_structure(fn, *structures):
@@ -88,7 +95,6 @@ class EnergyInferenceBase(torch.nn.Module, abc.ABC):
       self._checkpoint = False
     else:
       self._tracked_variables_checkpoint = [v.detach().clone() for v in self._tracked_variables]
-      self._tracked_versions = [None for _ in self._tracked_variables]
       self._checkpoint = True
     self._update_seed = initial_seed is None
     self._seed = sanitize_seed(initial_seed)
@@ -120,21 +126,19 @@ class EnergyInferenceBase(torch.nn.Module, abc.ABC):
     """True iff some tracked variable differs from its checkpointed value."""
     if not self._checkpoint:
       return False
-    changed = False
-    for i, (v, vc) in enumerate(zip(self._tracked_variables, self._tracked_variables_checkpoint)):
-      stamp = (v.data_ptr(), v._version)  # in-place updates bump the version: skip the compare otherwise
-      if self._tracked_versions[i] == stamp:
-        continue
-      if vc.device != v.device or vc.shape != v.shape or not torch.equal(v.detach(), vc):
-        changed = True
-      else:
-        self._tracked_versions[i] = stamp
-    return changed
+    # Values are compared on every call, as the reference does (ebm.py:125-140): writes through `.data`
+    # change neither the storage pointer nor the version counter, so no cheaper test is safe.  All
+    # variables are compared on the device and ONE flag crosses to the host.
+    flags = []
+    for v, vc in zip(self._tracked_variables, self._tracked_variables_checkpoint):
+      if vc.device != v.device or vc.shape != v.shape:
+        return True
+      flags.append((v.detach() != vc).any())
+    return bool(torch.stack(flags).any().item()) if flags else False
 
   def _checkpoint_variables(self):
     if self._checkpoint:
       self._tracked_variables_checkpoint = [v.detach().clone() for v in self._tracked_variables]
-      self._tracked_versions = [(v.data_ptr(), v._version) for v in self._tracked_variables]
 
   def _preface_inference(self):
     if self._first_inference:
@@ -230,30 +234,99 @@ class EnergyInference(EnergyInferenceBase):
 
   def _expectation(self, function):
     """Sample average; d/dtheta = E[c]E[dE] - E[c dE] + E[d function] (reference ebm.py:282-325),
-    realised by adding a zero-valued surrogate whose gradient is the covariance term."""
+    realised by adding a zero-valued surrogate whose gradient is the covariance term.
+
+    Under torch.distributed (world size > 1) every rank draws the SAME samples (same seed) and owns a
+    contiguous shard of the unique bitstrings: `function` only sees that shard, and the count-weighted
+    partial sums of all leaves of its result travel in ONE all-reduce.  Gradients follow
+    the convention of `qhbmlib.distributed` (call `sync_gradients` after `backward`)."""
     bitstrings, _, counts = self.unique_samples(self.num_expectation_samples)
-    values = function(bitstrings)
-    average_of_values = map_structure(lambda x: utils.weighted_average(counts, x), values)
+    sharded = qd.active()
+    if sharded:
+      rank, world = qd.world()
+      lo, hi = qd.shard_range(bitstrings.shape[0], rank, world)
+      total = counts.sum()
+      bitstrings, counts = bitstrings[lo:hi].contiguous(), counts[lo:hi].contiguous()
+      with qd.local_shard():
+        values = function(bitstrings)
+      leaves = []
+      map_structure(leaves.append, values)
+      partial = [utils.weighted_sum(counts, x).reshape(-1) for x in leaves]  # sum_u c_u v_u of this shard
+      packed = qd.all_reduce_sum(torch.cat([p.double() for p in partial])) / total.double()
+      it, off = iter(leaves), [0]
+
+      def take(_):
+        x = next(it)
+        n = x[0].numel() if x.dim() > 1 else 1
+        out = packed[off[0]:off[0] + n].to(x.dtype).reshape(x.shape[1:])
+        off[0] += n
+        return out
+
+      average_of_values = map_structure(take, values)
+      weight_norm = total
+    else:
+      values = function(bitstrings)
+      average_of_values = map_structure(lambda x: utils.weighted_average(counts, x), values)
+      weight_norm = counts.sum()
     if not self._energy_needs_grad():
       return average_of_values
+    fused = self._parity_feature_tables()
+    if fused is not None and bitstrings.is_cuda and all(v.is_cuda and v.dtype == torch.float32 for v in _leaves(values)):
+      # f1: on-device score-function glue.  For parity-feature energies (Bernoulli, KOBE) the Jacobian
+      # dE/dtheta is the +-1 feature matrix, so the whole backward term is one fused kernel pair over the
+      # packed keys -- no energy evaluation, no Jacobian, no chain of small torch ops.
+      theta, masks = fused
+      n = self.energy.num_bits
+      keys = engine.pack_bits(bitstrings, utils._natural_shifts(n))
+      total = weight_norm.double().reshape(1)
+      scale = float(qd.world()[1]) if sharded else 1.0
+      return map_structure(
+          lambda avg, val: utils.score_function_term(avg, theta, val, keys, counts, total, masks, scale),
+          average_of_values, values)
     energies = self.energy(bitstrings)
-    weights = counts.to(energies.dtype) / counts.sum().to(energies.dtype)
+    weights = counts.to(energies.dtype) / weight_norm.to(energies.dtype)
     weighted_energies = weights * energies
 
     def add_score_term(avg, val):
       centered = (avg.detach().unsqueeze(0) - val.detach()).to(weighted_energies.dtype)
       surrogate = torch.tensordot(weighted_energies, centered, dims=([0], [0]))
+      if sharded:
+        surrogate = qd.shard_term(surrogate)  # its value is zero anyway; its gradient is one shard of the sum
       return avg + (surrogate - surrogate.detach()).to(avg.dtype)
 
     return map_structure(add_score_term, average_of_values, values)
 
+  def _parity_feature_tables(self):
+    """(theta parameter, int32 masks on the device) when the energy is sum_t theta_t x parity feature
+    (BernoulliEnergy, KOBE) and theta is trainable; else None."""
+    if not hasattr(self.energy, "kernel_descriptor"):
+      return None
+    _, masks, theta = self.energy.kernel_descriptor()
+    if not (isinstance(theta, torch.nn.Parameter) and theta.requires_grad and theta.is_cuda and
+            theta.dtype == torch.float32):
+      return None
+    cache = self.__dict__.setdefault("_mask_cache", {})
+    key = (tuple(masks), theta.device)
+    if key not in cache:
+      cache.clear()
+      cache[key] = torch.tensor(masks, dtype=torch.int64, device=theta.device).to(torch.int32)
+    return theta, cache[key]
+
   def _log_partition(self):
     """Forward value from the subclass; gradient -E_{x~p}[dE/dtheta] from fresh samples
-    (reference ebm.py:331-343, 396-415)."""
+    (reference ebm.py:331-343, 396-415).  Sharded like `_expectation` when torch.distributed is active."""
     result = self._log_partition_forward_pass().detach()
     if not self._energy_needs_grad():
       return result
     unique_samples, _, counts = self.unique_samples(self.num_expectation_samples)
+    if qd.active():
+      rank, world = qd.world()
+      lo, hi = qd.shard_range(unique_samples.shape[0], rank, world)
+      total = counts.sum()
+      e = self.energy(unique_samples[lo:hi].contiguous())
+      w = counts[lo:hi].to(e.dtype) / total.to(e.dtype)
+      surrogate = qd.shard_term(-(w * e).sum())
+      return result + (surrogate - surrogate.detach())
     unique_energies = self.energy(unique_samples)
     surrogate = -utils.weighted_average(counts, unique_energies)
     return result + (surrogate - surrogate.detach())
@@ -277,10 +350,10 @@ class Categorical:
     self._owner = owner
 
   def logits_parameter(self):
-    return self._owner._logits
+    return self._owner._full_logits()
 
   def probs_parameter(self):
-    return torch.softmax(self._owner._logits.double(), 0).float()
+    return torch.softmax(self._owner._full_logits().double(), 0).float()
 
   def entropy(self):
     m, s, t = self._owner._stats.tolist()
@@ -288,7 +361,7 @@ class Categorical:
 
   def sample(self, num_samples, seed=None):
     seed = self._owner.seed if seed is None else sanitize_seed(seed)
-    return engine.categorical_sample(self._owner._logits, int(num_samples), seed)
+    return self._owner._draw_keys(int(num_samples), seed)
 
 
 def _mlp_layers(energy):
@@ -350,6 +423,8 @@ class AnalyticEnergyInference(EnergyInference):
     self._all_bitstrings = None
     self._logits = None
     self._stats = None
+    self._sampler = None
+    self._row_range = (0, 1 << input_energy.num_bits)
     self._distribution = Categorical(self)
 
   @property
@@ -370,8 +445,21 @@ class AnalyticEnergyInference(EnergyInference):
     return self._distribution
 
   def _ready_inference(self):
+    """logits = -E(all rows), plus (max, sum exp, sum exp * l) for log Z and the entropy (reference
+    ebm.py:467-469).  Under torch.distributed every rank sweeps its contiguous share of the 2^n rows and
+    keeps only those logits; the statistics merge through one all-gather of three doubles per rank."""
     n = self.energy.num_bits
     desc = energy_descriptor(self.energy)
+    self._sampler = None
+    self._row_range = (0, 1 << n)
+    rank, world = qd.world()
+    if desc is not None and world > 1:
+      lo, hi = qd.shard_range(1 << n, rank, world)
+      self._logits, stats = desc.sweep(lo, hi, device=self.device)
+      m, sm, t = qd.merge_log_stats(qd.all_gather_stats(stats))
+      self._stats = torch.tensor([m, sm, t], dtype=torch.float64)
+      self._row_range = (lo, hi)
+      return
     if desc is not None:
       self._logits, self._stats = desc.sweep(0, 1 << n, device=self.device)
       self._stats = self._stats.cpu()
@@ -390,6 +478,48 @@ class AnalyticEnergyInference(EnergyInference):
     w = torch.exp(l64 - m)
     self._stats = torch.stack([m, w.sum(), (w * l64).sum()]).cpu()
 
+  def _sharded(self):
+    return self._row_range != (0, 1 << self.energy.num_bits)
+
+  def _full_logits(self):
+    """f32[2^n] on every rank (the local shard otherwise stays where it was computed)."""
+    if not self._sharded():
+      return self._logits
+    rank, world = qd.world()
+    n = self.energy.num_bits
+    sizes = [qd.shard_range(1 << n, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros(width, dtype=torch.float32, device=self._logits.device)
+    pad[:self._logits.shape[0]] = self._logits
+    out = [torch.empty_like(pad) for _ in range(world)]
+    torch.distributed.all_gather(out, pad)
+    return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(out, sizes)])
+
+  def _draw_keys(self, num_samples, seed):
+    """Row indices (= packed bitstring keys) of `num_samples` samples.  The prefix sums over the logits
+    are prepared once per parameter change, with the maximum taken from the sweep statistics.  Sharded:
+    sample k is drawn by the rank whose interval of the global cumulative mass holds its uniform, the
+    others leave a zero, and one all-reduce(sum) of the int64 sample vector gives every rank the full
+    draw -- the samples a single GPU would have drawn, whatever the number of ranks."""
+    if self._sampler is None:
+      self._sampler = engine.CategoricalSampler(self._logits, given_max=float(self._stats[0]))
+      self._mass_interval = None
+      if self._sharded():
+        rank, world = qd.world()
+        mass = self._sampler.local_mass().clone()
+        masses = [torch.zeros_like(mass) for _ in range(world)]
+        torch.distributed.all_gather(masses, mass)
+        cum = [0.0]
+        for m in masses:
+          cum.append(cum[-1] + float(m.item()))
+        self._mass_interval = (cum[rank], cum[rank + 1] if rank + 1 < world else math.inf, cum[-1])
+    if not self._sharded():
+      return self._sampler.draw(num_samples, seed)
+    out = torch.zeros((num_samples,), dtype=torch.int64, device=self._logits.device)
+    self._sampler.draw(num_samples, seed, row_offset=self._row_range[0], mass_interval=self._mass_interval, out=out)
+    torch.distributed.all_reduce(out)
+    return out
+
   def _call(self, inputs, *args, **kwargs):
     if inputs is None:
       return self.distribution
@@ -403,7 +533,7 @@ class AnalyticEnergyInference(EnergyInference):
     return torch.tensor(m + math.log(s), dtype=torch.float32, device=self.device)
 
   def _sample_keys(self, num_samples):
-    return engine.categorical_sample(self._logits, int(num_samples), self.seed)  # row index IS the key
+    return self._draw_keys(int(num_samples), self.seed)  # row index IS the key
 
   def _sample(self, num_samples):
     n = self.energy.num_bits

@@ -6,6 +6,7 @@ with the adjoint-gradient kernels wired into torch autograd (the reference wires
 differentiator into TF autodiff, qnn.py:87-139).
 """
 import abc
+import collections
 import math
 import os
 
@@ -14,10 +15,34 @@ import torch
 
 from qhbmlib import _native as nat
 from qhbmlib import circuits as cq
+from qhbmlib import distributed as qd
 from qhbmlib import engine
 from qhbmlib import utils
 from qhbmlib.models import energy as energy_lib
 from qhbmlib.models import hamiltonian as hamiltonian_lib
+
+
+class _LRU:
+  """Small least-recently-used map.  Compiled plans own device tables and grow-only workspaces, so the
+  caches that hold them are keyed by CONTENT (an observable or circuit rebuilt inside a training loop hits
+  the same entry) and bounded (an evicted plan frees its device memory when it is collected)."""
+
+  def __init__(self, maxsize=8):
+    self.maxsize = maxsize
+    self._d = collections.OrderedDict()
+
+  def get(self, key, make):
+    if key in self._d:
+      self._d.move_to_end(key)
+      return self._d[key]
+    value = make()
+    self._d[key] = value
+    while len(self._d) > self.maxsize:
+      self._d.popitem(last=False)
+    return value
+
+  def __len__(self):
+    return len(self._d)
 
 
 class _ExpectationOp(torch.autograd.Function):
@@ -104,17 +129,26 @@ class QuantumInference(torch.nn.Module, abc.ABC):
       total_circuit = self.circuit
     else:
       total_circuit = self._total_circuit(observables)
-    circuits = total_circuit(unique_states)
-    unique_expectations = self._expectation(circuits, total_circuit.symbol_names, total_circuit.symbol_values,
-                                            observables)
+    if qd.active():
+      # one process per GPU: this rank simulates its contiguous share of the unique states; the rows are
+      # all-gathered so that every rank returns the full [batch, n_ops] result
+      rank, world = qd.world()
+      n_unique = unique_states.shape[0]
+      lo, hi = qd.shard_range(n_unique, rank, world)
+      circuits = total_circuit(unique_states[lo:hi].contiguous())
+      local = self._expectation(circuits, total_circuit.symbol_names, total_circuit.symbol_values, observables)
+      unique_expectations = qd.all_gather_rows(local, n_unique)
+    else:
+      circuits = total_circuit(unique_states)
+      unique_expectations = self._expectation(circuits, total_circuit.symbol_names, total_circuit.symbol_values,
+                                              observables)
     return utils.expand_unique_results(unique_expectations, idx)
 
   def _total_circuit(self, observables):
-    cache = self.__dict__.setdefault("_total_cache", {})
-    key = id(observables)
-    if key not in cache:
-      cache[key] = (observables, self.circuit + observables.circuit_dagger)
-    return cache[key][1]
+    """circuit + observables.circuit_dagger (reference qnn.py:69-72), kept for the few Hamiltonians in
+    use (the entries hold their key objects alive, so ids cannot be recycled while cached)."""
+    cache = self.__dict__.setdefault("_total_cache", _LRU(4))
+    return cache.get(id(observables), lambda: (observables, self.circuit + observables.circuit_dagger))[1]
 
   @abc.abstractmethod
   def _expectation(self, circuits, symbol_names, symbol_values, observables):
@@ -130,20 +164,21 @@ class AnalyticQuantumInference(QuantumInference):
     super().__init__(input_circuit, name)
     self.grad_mode = grad_mode
     self._tile_qubits, self._reg_qubits = tile_qubits, reg_qubits
-    self._plans = {}
+    self._plans = _LRU(8)
 
   def _plan_for(self, circuit, ops_tensor):
-    key = (id(circuit), id(ops_tensor))
-    hit = self._plans.get(key)
-    if hit is None:
+    """Compiled plan for (gate table, Pauli tables), cached by content."""
+
+    def make():
       terms, offsets = ops_tensor.tables(circuit.qubits)
       args = (circuit.gate_table(), len(circuit.qubits), len(circuit.symbol_names), terms, offsets)
       plan = engine.ExpectationPlan(*args, True, self._tile_qubits, self._reg_qubits)
-      make_fwd = lambda: engine.ExpectationPlan(*args, False, 0, 0)
-      hit = (circuit, ops_tensor, _PlanHolder(plan, self.grad_mode, make_fwd))  # keep the keys alive
-      self._plans[key] = hit
-    hit[2].grad_mode = self.grad_mode
-    return hit[2]
+      return _PlanHolder(plan, self.grad_mode, lambda: engine.ExpectationPlan(*args, False, 0, 0))
+
+    key = (circuit.gate_table_digest(), ops_tensor.tables_digest(circuit.qubits))
+    holder = self._plans.get(key, make)
+    holder.grad_mode = self.grad_mode
+    return holder
 
   def _expectation(self, circuits, symbol_names, symbol_values, observables):
     del symbol_names
@@ -282,7 +317,7 @@ class SampledQuantumInference(QuantumInference):
     if initial_seed is None:
       initial_seed = int.from_bytes(os.urandom(8), "little")
     self._seed_state = int(initial_seed) & ((1 << 64) - 1)
-    self._plans = {}
+    self._plans = _LRU(8)
 
   def _next_seed(self):
     """A fresh (seed0, seed1) per measurement (splitmix64 stream)."""
@@ -299,18 +334,17 @@ class SampledQuantumInference(QuantumInference):
   def _compiled(self, circuit, key_obj, term_ops):
     """(occurrence table, plan) for `circuit`; the plan measures `term_ops` (an OperatorTensor with
     one Pauli string per entry) or, when None, is used for final states only."""
-    key = (id(circuit), id(key_obj))
-    hit = self._plans.get(key)
-    if hit is None:
+    qubits = circuit.qubits
+    if term_ops is None:
+      term_ops = cq.convert_to_tensor([cq.PauliSum.from_pauli_strings(cq.Z(qubits[0]))])
+    del key_obj
+
+    def make():
       occ = _Occurrences(circuit.gate_table(), len(circuit.symbol_names))
-      qubits = circuit.qubits
-      if term_ops is None:
-        term_ops = cq.convert_to_tensor([cq.PauliSum.from_pauli_strings(cq.Z(qubits[0]))])
       terms, offsets = term_ops.tables(qubits)
-      plan = engine.ExpectationPlan(occ.table, len(qubits), occ.total_symbols, terms, offsets, False)
-      hit = (circuit, key_obj, occ, plan)
-      self._plans[key] = hit
-    return hit[2], hit[3]
+      return occ, engine.ExpectationPlan(occ.table, len(qubits), occ.total_symbols, terms, offsets, False)
+
+    return self._plans.get((circuit.gate_table_digest(), term_ops.tables_digest(qubits)), make)
 
   @staticmethod
   def _split_terms(ops, qubits):
@@ -335,11 +369,10 @@ class SampledQuantumInference(QuantumInference):
 
   # ------------------------------------------------------------------ estimators
   def _pauli_estimator(self, circuits, ops):
-    key = (id(circuits.circuit), id(ops))
-    cache = self.__dict__.setdefault("_split_cache", {})
-    if key not in cache:
-      cache[key] = (ops,) + self._split_terms(ops, circuits.circuit.qubits)
-    _, term_ops, mix, offsets = cache[key]
+    qubits = circuits.circuit.qubits
+    cache = self.__dict__.setdefault("_split_cache", _LRU(8))
+    term_ops, mix, offsets = cache.get((ops.tables_digest(qubits), len(qubits)),
+                                       lambda: self._split_terms(ops, qubits))
     occ, plan = self._compiled(circuits.circuit, ops, term_ops)
     basis_idx = circuits.basis_idx
     dev = basis_idx.device

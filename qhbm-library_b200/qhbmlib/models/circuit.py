@@ -112,6 +112,16 @@ class QuantumCircuit(torch.nn.Module):
       self._gate_table = cq.gate_table(self._pqc, self._qubits, self._symbol_names)
     return self._gate_table
 
+  def gate_table_digest(self):
+    """Content hash of the gate table (+ qubit and symbol counts): the key under which compiled plans
+    are cached, so that an equal circuit built again reuses the plan instead of compiling a new one."""
+    if getattr(self, "_gate_digest", None) is None:
+      import hashlib  # pylint: disable=import-outside-toplevel
+      h = hashlib.sha1(self.gate_table().tobytes())
+      h.update(f"|{len(self._qubits)}|{len(self._symbol_names)}".encode())
+      self._gate_digest = h.hexdigest()
+    return self._gate_digest
+
   def basis_indices(self, bitstrings):
     """int8 [N, n] -> int64 basis index per row, with the reference's column -> qubit map."""
     if bitstrings.shape[1] != len(self._qubits):

@@ -47,11 +47,64 @@ class _WeightedSum(torch.autograd.Function):
 
 
 def weighted_average(counts, values):
-  """Mean of `values` over axis 0 weighted by integer `counts` (reference utils.py:43-58)."""
-  if values.is_cuda and values.shape[0] > 0 and values.dtype in (torch.float32, torch.float64):
+  """Mean of `values` over axis 0 weighted by integer `counts` (reference utils.py:43-58).
+  float32 values on the GPU go through the float64-accumulating kernel; float64 values keep their
+  precision on the torch path."""
+  if values.is_cuda and values.shape[0] > 0 and values.dtype == torch.float32:
     return _WeightedSum.apply(counts.to(torch.int32), values)
   fc = counts.to(values.dtype)
   return torch.tensordot(fc, values, dims=([0], [0])) / fc.sum()
+
+
+class _WeightedPartialSum(torch.autograd.Function):
+  """sum_u counts[u] * values[u, ...] (no normalisation): one rank's share of a weighted average."""
+
+  @staticmethod
+  def forward(ctx, counts, values):
+    flat = values.reshape(values.shape[0], -1).contiguous().float()
+    acc = engine.weighted_sum(counts, flat)
+    ctx.save_for_backward(counts)
+    ctx.shape = values.shape
+    return acc[:-1].reshape(values.shape[1:])  # float64
+
+  @staticmethod
+  def backward(ctx, grad_out):
+    (counts,) = ctx.saved_tensors
+    g = counts.double().reshape((-1,) + (1,) * (len(ctx.shape) - 1)) * grad_out.unsqueeze(0)
+    return None, g.float()
+
+
+def weighted_sum(counts, values):
+  """float64 sum over axis 0 of counts[u] * values[u, ...] (differentiable w.r.t. values)."""
+  if values.is_cuda and values.shape[0] > 0 and values.dtype == torch.float32:
+    return _WeightedPartialSum.apply(counts.to(torch.int32), values)
+  return torch.tensordot(counts.double(), values.double(), dims=([0], [0]))
+
+
+class _ScoreTerm(torch.autograd.Function):
+  """Identity on `average` whose backward adds the score-function gradient of
+  EnergyInference._expectation w.r.t. the parameters theta of a parity-feature energy
+  (reference ebm.py:282-325): d/dtheta_t = E[c] E[f_t] - E[c f_t], computed by one fused kernel pair
+  from the packed keys of the unique bitstrings instead of an energy Jacobian."""
+
+  @staticmethod
+  def forward(ctx, average, theta, values, keys, counts, total, masks, scale):
+    ctx.save_for_backward(average.detach(), values.detach(), keys, counts, total, masks)
+    ctx.scale, ctx.theta_shape, ctx.theta_dtype = scale, theta.shape, theta.dtype
+    return average.view_as(average)
+
+  @staticmethod
+  def backward(ctx, grad):
+    average, values, keys, counts, total, masks = ctx.saved_tensors
+    flat = values.reshape(values.shape[0], -1).contiguous().float()
+    g_theta = engine.score_gradient(keys, counts, flat, grad.reshape(-1).contiguous().float(),
+                                    average.reshape(-1).contiguous().float(), masks, total, ctx.scale)
+    return grad, g_theta.reshape(ctx.theta_shape).to(ctx.theta_dtype), None, None, None, None, None, None
+
+
+def score_function_term(average, theta, values, keys, counts, total, masks, scale=1.0):
+  """`average` with the score-function gradient path to `theta` attached (see _ScoreTerm)."""
+  return _ScoreTerm.apply(average, theta, values, keys, counts.to(torch.int32), total, masks, scale)
 
 
 def _natural_shifts(n):

@@ -241,7 +241,8 @@ class Compiler {
     const int n = hp_.n_eff, K = hp_.K;
     std::vector<char> done(atoms.size(), 0);
     size_t remaining = atoms.size();
-    const int max_slots = std::min(4 * (1 << K), 255);  // gradient scratch = the two dead smem tiles
+    // gradient scratch: kScratchFloats floats of shared memory, one per (slot, thread)
+    const int max_slots = std::min(kScratchFloats >> (std::min(hp_.T, n) - K), 255);
     while (remaining > 0) {
       SweepOut sw;
       sw.tile_bits = choose_tile(atoms, done);
@@ -326,10 +327,29 @@ class Compiler {
         run.grp_list.assign((n + kConstGroupBits - 1) / kConstGroupBits, {});
         size_t executed = 0;
         Block blk(n);
+        // A pass's program (op descriptors + coefficients) is staged in a fixed shared-memory buffer: the
+        // pass is closed before the next atom could overflow it (headroom = the largest single atom, the
+        // tables the pending diagonal run will emit when flushed, and the merged-rotation tables).
+        int n_rot = 0;
+        auto fits = [&](const Atom& a) {
+          int rops = 0, rcoef = 0;
+          if (run.any) {
+            if (!run.gd_ops.empty()) rops += 1 + (int)run.gd_ops.size();
+            for (const auto& g : run.grp_list) if (!g.empty()) { ++rops; rcoef += 2 << kConstGroupBits; }
+            rops += (int)run.pair_ops.size() + (int)run.cross_ops.size() + 1;
+            rcoef += 4 << K;
+          }
+          const int ng = (int)a.gates.size();
+          const int ops_now = (int)hp_.ops.size() - ps.op_begin + rops;
+          const int coef_now = hp_.ncoef - ps.coef_begin + rcoef + n_rot * (4 * K + 4);
+          return ops_now + 6 * ng + 4 <= kStageOps &&
+                 coef_now + 136 * ng + (2 << kConstGroupBits) + (4 << K) + (4 * K + 4) <= kStageCoef;
+        };
         for (size_t ai = 0; ai < atoms.size(); ++ai) {
           if (done[ai]) continue;
           const Atom& a = atoms[ai];
           if (!blk.ready(a)) { blk.block(a); continue; }
+          if (!fits(a)) break;
           bool ok = true;
           int ngrads = 0;
           if (backward) {
@@ -364,7 +384,7 @@ class Compiler {
                   const qhbm_gate_t& g = hp_.gates[x.gates[0]];
                   for (int k = 0; k < g.nparams; ++k) ng += g.sym[k] >= 0;
                 }
-                if (ps.ngrad + ng > max_slots) { b2.block(x); continue; }
+                if (ps.ngrad + ng > max_slots || !fits(x)) { b2.block(x); continue; }
                 emit_diag(x, backward, regpos, ps, run);
                 done[aj] = 1;
                 --remaining;
@@ -373,6 +393,7 @@ class Compiler {
               flush_diag(run, backward);
             }
             emit_nondiag(a, backward, regpos, ps);
+            ++n_rot;
           }
           done[ai] = 1;
           --remaining;
@@ -383,6 +404,8 @@ class Compiler {
         merge_rotations(ps);
         ps.op_end = (int)hp_.ops.size();
         ps.coef_end = hp_.ncoef;
+        if (ps.op_end - ps.op_begin > kStageOps || ps.coef_end - ps.coef_begin > kStageCoef)
+          throw std::runtime_error("internal: a pass program exceeds the staging buffer");
         hp_.passes.push_back(ps);
         executed_in_sweep += executed;
         if (!have_nondiag && remaining > 0) {
@@ -964,6 +987,14 @@ class Compiler {
           if (std::find(zouts.begin(), zouts.end(), zo) == zouts.end()) zouts.push_back(zo);
         }
         for (uint32_t zo : zouts) {
+          if ((int)hp_.ops.size() - ps.op_begin + 1 > kStageOps || hp_.ncoef - ps.coef_begin + R > kStageCoef) {
+            // the staging buffer is full: continue in another pass over the same register set
+            ps.op_end = (int)hp_.ops.size();
+            ps.coef_end = hp_.ncoef;
+            hp_.passes.push_back(ps);
+            ps.op_begin = (int)hp_.ops.size();
+            ps.coef_begin = hp_.ncoef;
+          }
           std::vector<int32_t> tab(R, 0);
           for (int r = 0; r < R; ++r) {
             float v = 0.f;
@@ -1134,6 +1165,31 @@ HostPlan compile_plan(const CircuitIR& c, const OpsIR& o, bool with_gradient, in
   hp.gates = c.gates;
   Compiler comp(hp);
   comp.compile(c, o);
+  // Prefetch links and gradient-slot ranges.  Inside a launch's pass range the programs are consecutive
+  // (pass i + 1 starts where pass i ends), which is what lets the kernel prefetch the next program from
+  // the staged descriptor of the current one.
+  for (size_t i = 0; i < hp.passes.size(); ++i) {
+    const bool has_next = i + 1 < hp.passes.size();
+    hp.passes[i].next_op_end = has_next ? hp.passes[i + 1].op_end : hp.passes[i].op_end;
+    hp.passes[i].next_coef_end = has_next ? hp.passes[i + 1].coef_end : hp.passes[i].coef_end;
+  }
+  auto check_range = [&](int b, int e) {
+    for (int i = b; i + 1 < e; ++i)
+      if (hp.passes[i + 1].op_begin != hp.passes[i].op_end || hp.passes[i + 1].coef_begin != hp.passes[i].coef_end)
+        throw std::runtime_error("internal: pass programs of a launch range are not consecutive");
+  };
+  for (LaunchDesc& L : hp.launches) {
+    check_range(L.pass_a_begin, L.pass_a_end);
+    check_range(L.pass_h_begin, L.pass_h_end);
+    check_range(L.pass_b_begin, L.pass_b_end);
+    L.gslot_begin = L.gslot_count = 0;
+    if (L.pass_b_end > L.pass_b_begin) {
+      const DevPass& first = hp.passes[L.pass_b_begin];
+      const DevPass& last = hp.passes[L.pass_b_end - 1];
+      L.gslot_begin = first.gsym_off;
+      L.gslot_count = last.gsym_off + std::max(last.ngrad, 0) - first.gsym_off;
+    }
+  }
   return hp;
 }
 

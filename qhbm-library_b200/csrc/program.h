@@ -21,8 +21,10 @@ constexpr int kMaxTileQubits = 14;
 constexpr int kMaxQubits = 30;
 constexpr int kConstGroupBits = 7;  // width of one "thread-constant" phase table
 constexpr int kMaxRuns = 16;
-constexpr int kStageOps = 192;     // ops of one pass staged in shared memory (else read from global)
-constexpr int kStageCoef = 1792;   // floats of one pass's coefficients staged in shared memory
+constexpr int kStageOps = 192;     // ops of one pass: the compiler closes a pass before its program exceeds the
+constexpr int kStageCoef = 1792;   // shared-memory staging buffer (op descriptors / coefficient floats)
+constexpr int kScratchFloats = 4096;  // gradient scratch of a pass: slots x threads (adjoint kernel)
+constexpr int kGaccSlots = 512;       // gradient slots of one launch accumulated in shared memory
 
 enum OpType : int32_t {
   OP_NOP = 0,
@@ -89,7 +91,7 @@ inline PackedOp pack_op(const DevOp& o) {
   return q;
 }
 
-struct DevPass {  // 128 bytes
+struct DevPass {  // 144 bytes
   int32_t regbit[kMaxRegQubits];     // tile-local bit of register position j
   int32_t sorted[kMaxRegQubits];     // the same bits in ascending order
   int32_t op_begin, op_end;
@@ -97,6 +99,8 @@ struct DevPass {  // 128 bytes
                                      // ngrad == -1 marks an observable pass (OP_HX / OP_HD only)
   int32_t coef_begin, coef_end;      // float range of the coefficient buffer this pass reads
   uint16_t eoff[1 << kMaxRegQubits]; // swizzled smem offset of register amplitude r (XOR with the thread base)
+  int32_t next_op_end, next_coef_end;  // ends of the NEXT pass's ranges (they start where this pass's end):
+  int32_t pad[2];                      // what the kernel needs to prefetch that program while this pass runs
 };
 
 // Contiguous run of tile-local bits mapped to contiguous state-index bits.
@@ -127,6 +131,7 @@ struct LaunchDesc {
   uint32_t tile_mask;                // state-index bits covered by the tile
   int32_t pass_h_begin, pass_h_end;  // observable passes run at the start of the expectation phase
   int32_t expect_stage;              // LF_EXPECT: which stage's tables this launch uses
+  int32_t gslot_begin, gslot_count;  // gradient slots (indices into gsym) of all passes of this launch
   int32_t rng_begin, rng_end;        // its slice of the observable ranges (DevOpRange)
   int32_t grp_begin, grp_end;        // that stage's slice of the group / term tables (staged in shared memory)
   int32_t term_begin, term_end;

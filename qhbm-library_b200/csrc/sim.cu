@@ -110,11 +110,15 @@ void allow_large_smem() {
   int dev = 0, optin = 0;
   QHBM_CUDA(cudaGetDevice(&dev));
   QHBM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const int dyn = optin - (int)sizeof(float4) * (kStageOps + kStageCoef / 4) - 1024;
-  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-  QHBM_CUDA(cudaFuncSetAttribute(sweep_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+  auto allow = [&](const void* fn) {
+    cudaFuncAttributes attr;
+    QHBM_CUDA(cudaFuncGetAttributes(&attr, fn));
+    QHBM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)attr.sharedSizeBytes));
+  };
+  allow(reinterpret_cast<const void*>(sweep_kernel<4, true>));
+  allow(reinterpret_cast<const void*>(sweep_kernel<4, false>));
+  allow(reinterpret_cast<const void*>(sweep_kernel<5, true>));
+  allow(reinterpret_cast<const void*>(sweep_kernel<5, false>));
 }
 
 void launch_any(const qhbm_plan* p, bool adj, const KernelArgs& ka, int n_states, cudaStream_t s) {

@@ -11,6 +11,7 @@
 // layout is nibble-XOR swizzled so that every pass is bank-conflict free for any
 // contiguous choice of register bits.  No tensor cores: there is no dense contraction.
 #pragma once
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -414,61 +415,118 @@ __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const f
 // One pass: smem tile -> registers -> ops -> smem tile.
 // BOTH = false: forward (psi only).  BOTH = true: adjoint (psi and lambda, gradients).
 // ---------------------------------------------------------------------------------
+// Shared-memory state of a CTA besides the tiles.
+//   stage   : two program buffers (pass descriptor + op descriptors + coefficients); while a pass runs from
+//             one, the next pass's program streams into the other with cp.async (LDGSTS), so no pass waits
+//             for global memory except the first of a range
+//   scratch : per-thread gradient values of the running pass, [slot][thread] (adjoint kernel)
+//   gacc    : the launch's gradient sums of this CTA, flushed to the float64 accumulators once at the end
+struct PassCtx {
+  float4* stage;
+  float* scratch;
+  float* gacc;
+  int buf;
+  bool dbuf;  // two program buffers (adjoint kernel); the forward-only kernel keeps one, to fit three CTAs per SM
+};
+constexpr int kPassF4 = (int)(sizeof(DevPass) / 16);
+constexpr int kStageF4 = kPassF4 + kStageOps + kStageCoef / 4;  // float4 per program buffer
+static_assert(sizeof(DevPass) % 16 == 0, "DevPass is copied in 16-byte pieces");
+
+// Copies pass p's program into stage buffer `buf`.  ASYNC: cp.async, completed by stage_wait().
+template <bool ASYNC>
+__device__ __forceinline__ void stage_program(const KernelArgs& ka, float4* buf, const int p, const int op_begin,
+                                              const int op_end, const int cb, const int ce) {
+  const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
+  const float4* g_ps = reinterpret_cast<const float4*>(ka.passes + p);
+  const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
+  const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);  // coefficient slots are 16-byte aligned
+  float4* s_ops = buf + kPassF4;
+  float4* s_cf = buf + kPassF4 + kStageOps;
+  const int n_ops = op_end - op_begin, n_cf = (ce - cb + 3) / 4;
+  if constexpr (ASYNC) {
+    if (tid < kPassF4) __pipeline_memcpy_async(buf + tid, g_ps + tid, 16);
+    for (int i = tid; i < n_ops; i += nthr) __pipeline_memcpy_async(s_ops + i, g_ops + i, 16);
+    for (int i = tid; i < n_cf; i += nthr) __pipeline_memcpy_async(s_cf + i, g_cf + i, 16);
+    __pipeline_commit();
+  } else {
+    if (tid < kPassF4) buf[tid] = __ldg(g_ps + tid);
+    for (int i = tid; i < n_ops; i += nthr) s_ops[i] = __ldg(g_ops + i);
+    for (int i = tid; i < n_cf; i += nthr) s_cf[i] = __ldg(g_cf + i);
+  }
+}
+
+// Start of a pass: makes pass p's program current (staging it now if it is the first of its range, else
+// waiting for the prefetch), starts the prefetch of pass p + 1, and returns the views into the buffer.
+struct PassView {
+  const DevPass* ps;      // in shared memory
+  const PackedOp* ops;    // indexed by absolute op number
+  const float* coef;      // indexed by absolute float offset
+  int op_begin, op_end;
+};
+__device__ __forceinline__ PassView begin_pass(const KernelArgs& ka, PassCtx& cx, const int p, const bool first,
+                                               const bool last) {
+  if (first || !cx.dbuf) {
+    __syncthreads();  // the previous phase is done with the tiles and the stage buffers
+    const DevPass* gp = ka.passes + p;
+    stage_program<false>(ka, cx.stage + cx.buf * kStageF4, p, __ldg(&gp->op_begin), __ldg(&gp->op_end),
+                         __ldg(&gp->coef_begin), __ldg(&gp->coef_end));
+  } else {
+    __pipeline_wait_prior(0);
+  }
+  __syncthreads();  // program visible; the previous pass's tile stores and gradient reduction are complete
+  float4* buf = cx.stage + cx.buf * kStageF4;
+  PassView v;
+  v.ps = reinterpret_cast<const DevPass*>(buf);
+  v.op_begin = v.ps->op_begin;
+  v.op_end = v.ps->op_end;
+  const int cb = v.ps->coef_begin;
+  v.ops = reinterpret_cast<const PackedOp*>(buf + kPassF4) - v.op_begin;
+  v.coef = reinterpret_cast<const float*>(buf + kPassF4 + kStageOps) - cb;
+  if (cx.dbuf) {
+    if (!last)  // passes of a range are consecutive: the next program starts where this one ends
+      stage_program<true>(ka, cx.stage + (cx.buf ^ 1) * kStageF4, p + 1, v.op_end, v.ps->next_op_end, v.ps->coef_end,
+                          v.ps->next_coef_end);
+    cx.buf ^= 1;
+  }
+  return v;
+}
+
 template <int K, bool BOTH>
-__device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __restrict__ ps, float2* s_psi,
-                                         float2* s_lam, float4* s_stage, uint32_t goff, uint32_t u) {
+__device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, const int p, const bool first,
+                                         const bool last, float2* s_psi, float2* s_lam, uint32_t goff, uint32_t u) {
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-  // Stage this pass's op descriptors and coefficients in shared memory: every later access is then an
-  // LDS broadcast with a short fixed latency instead of a dependent global load per op.
-  const int op_begin = __ldg(&ps->op_begin), op_end = __ldg(&ps->op_end);
-  const int cb = __ldg(&ps->coef_begin), ce = __ldg(&ps->coef_end);
-  const bool staged = (op_end - op_begin) <= kStageOps && (ce - cb) <= kStageCoef;
-  const PackedOp* ops_base = ka.ops;    // indexed by absolute op number
-  const float* coef_base = ka.coef;     // indexed by absolute float offset
-  __syncthreads();  // the previous pass (its tile stores and its staged program) is finished everywhere
-  if (staged) {
-    float4* s_ops = s_stage;                       // kStageOps float4 (one per op)
-    float4* s_cf = s_stage + kStageOps;            // kStageCoef / 4 float4
-    const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
-    for (int i = (int)tid; i < (op_end - op_begin); i += (int)nthr) s_ops[i] = __ldg(g_ops + i);
-    const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);  // coefficient slots are 16-byte aligned
-    for (int i = (int)tid; i < (ce - cb + 3) / 4; i += (int)nthr) s_cf[i] = __ldg(g_cf + i);
-    ops_base = reinterpret_cast<const PackedOp*>(s_ops) - op_begin;
-    coef_base = reinterpret_cast<const float*>(s_cf) - cb;
-  }
+  const PassView pv = begin_pass(ka, cx, p, first, last);
+  const DevPass* ps = pv.ps;
+  const int op_begin = pv.op_begin, op_end = pv.op_end;
+  const PackedOp* ops_base = pv.ops;
+  const float* coef_base = pv.coef;
   uint32_t base = tid;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    const int sp = __ldg(&ps->sorted[j]);
+    const int sp = ps->sorted[j];
     base = ((base >> sp) << (sp + 1)) | (base & ((1u << sp) - 1u));
   }
   const uint32_t B = swz(base);
   const uint32_t gbase = goff | scatter_bits(base, ka.L.runs, ka.L.n_runs);
-  uint32_t eo[R];
+  float2 a[R];
+  float2 b[BOTH ? R : 1];
   {
     const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
 #pragma unroll
     for (int i = 0; i < R / 8; ++i) {
-      const uint4 w = __ldg(ep + i);
-      eo[8 * i + 0] = w.x & 0xffffu; eo[8 * i + 1] = w.x >> 16;
-      eo[8 * i + 2] = w.y & 0xffffu; eo[8 * i + 3] = w.y >> 16;
-      eo[8 * i + 4] = w.z & 0xffffu; eo[8 * i + 5] = w.z >> 16;
-      eo[8 * i + 6] = w.w & 0xffffu; eo[8 * i + 7] = w.w >> 16;
+      const uint4 w = ep[i];
+      const uint32_t eo[8] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16,
+                              w.z & 0xffffu, w.z >> 16, w.w & 0xffffu, w.w >> 16};
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        a[8 * i + r] = s_psi[B ^ eo[r]];
+        if constexpr (BOTH) b[8 * i + r] = s_lam[B ^ eo[r]];
+      }
     }
   }
-  __syncthreads();  // staged program visible
-
-  float2 a[R];
-  float2 b[BOTH ? R : 1];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    a[r] = s_psi[B ^ eo[r]];
-    if constexpr (BOTH) b[r] = s_lam[B ^ eo[r]];
-  }
-  const int ngrad = BOTH ? __ldg(&ps->ngrad) : 0;
-  float* scratch = reinterpret_cast<float*>(s_psi);
-  if (ngrad > 0) __syncthreads();  // every amplitude is in registers: the tiles become scratch
+  const int ngrad = BOTH ? ps->ngrad : 0;
+  float* scratch = cx.scratch;
 
   float2 F = make_float2(1.f, 0.f);
   int oi = op_begin;
@@ -620,22 +678,35 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, const DevPass* __
   }
 
   if (ngrad > 0) {
-    __syncthreads();
+    __syncthreads();  // every thread's gradient values of this pass are in the scratch
     const uint32_t w = tid >> 5, lane = tid & 31, nw = nthr >> 5;
-    const int gs0 = __ldg(&ps->gsym_off);
+    const int gs0 = ps->gsym_off;
+    const bool in_smem = ka.L.gslot_count <= kGaccSlots;
     double* grow = ka.gacc + (size_t)(ka.per_state ? (ka.grow0 + (int)u) : 0) * ka.P;
     for (int g = w; g < ngrad; g += nw) {
-      float s = 0.f;
-      for (uint32_t i = lane; i < nthr; i += 32) s += scratch[g * nthr + i];
-      s = warp_sum(s);
-      if (lane == 0) atomicAdd(grow + __ldg(&ka.gsym[gs0 + g]), (double)s);
+      float sum = 0.f;
+      for (uint32_t i = lane; i < nthr; i += 32) sum += scratch[g * nthr + i];
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        if (in_smem) cx.gacc[gs0 + g - ka.L.gslot_begin] = sum;  // each slot belongs to exactly one pass
+        else atomicAdd(grow + __ldg(&ka.gsym[gs0 + g]), (double)sum);
+      }
     }
-    __syncthreads();
+    // no barrier here: the scratch is next written after the next pass's entry barrier
   }
+  {
+    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    s_psi[B ^ eo[r]] = a[r];
-    if constexpr (BOTH) s_lam[B ^ eo[r]] = b[r];
+    for (int i = 0; i < R / 8; ++i) {
+      const uint4 w = ep[i];
+      const uint32_t eo[8] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16,
+                              w.z & 0xffffu, w.z >> 16, w.w & 0xffffu, w.w >> 16};
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        s_psi[B ^ eo[r]] = a[8 * i + r];
+        if constexpr (BOTH) s_lam[B ^ eo[r]] = b[8 * i + r];
+      }
+    }
   }
 }
 
@@ -671,35 +742,24 @@ __device__ __forceinline__ void hx_apply(const float2 (&a)[16], float2 (&b)[BOTH
 // fifth register position only selects the half, so the forward-only kernel never holds 32 complex
 // registers here.
 template <int K, bool BOTH>
-__device__ __forceinline__ void run_hpass(const KernelArgs& ka, const DevPass* __restrict__ ps, const float2* s_psi,
-                                          float2* s_lam, float4* s_stage, uint32_t goff, uint32_t u) {
+__device__ __forceinline__ void run_hpass(const KernelArgs& ka, PassCtx& cx, const int p, const bool first,
+                                          const bool last, const float2* s_psi, float2* s_lam, uint32_t goff,
+                                          uint32_t u) {
   constexpr int R = 1 << K;
-  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-  const int op_begin = __ldg(&ps->op_begin), op_end = __ldg(&ps->op_end);
-  const int cb = __ldg(&ps->coef_begin), ce = __ldg(&ps->coef_end);
-  const bool staged = (op_end - op_begin) <= kStageOps && (ce - cb) <= kStageCoef;
-  const PackedOp* ops_base = ka.ops;
-  const float* coef_base = ka.coef;
-  __syncthreads();  // previous pass done (tile stores, staged program)
-  if (staged) {
-    float4* s_ops = s_stage;
-    float4* s_cf = s_stage + kStageOps;
-    const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
-    for (int i = (int)tid; i < (op_end - op_begin); i += (int)nthr) s_ops[i] = __ldg(g_ops + i);
-    const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);
-    for (int i = (int)tid; i < (ce - cb + 3) / 4; i += (int)nthr) s_cf[i] = __ldg(g_cf + i);
-    ops_base = reinterpret_cast<const PackedOp*>(s_ops) - op_begin;
-    coef_base = reinterpret_cast<const float*>(s_cf) - cb;
-  }
+  const uint32_t tid = threadIdx.x;
+  const PassView pv = begin_pass(ka, cx, p, first, last);
+  const DevPass* ps = pv.ps;
+  const int op_begin = pv.op_begin, op_end = pv.op_end;
+  const PackedOp* ops_base = pv.ops;
+  const float* coef_base = pv.coef;
   uint32_t base = tid;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    const int sp = __ldg(&ps->sorted[j]);
+    const int sp = ps->sorted[j];
     base = ((base >> sp) << (sp + 1)) | (base & ((1u << sp) - 1u));
   }
   const uint32_t B = swz(base);
   const uint32_t gbase = goff | scatter_bits(base, ka.L.runs, ka.L.n_runs);
-  __syncthreads();  // staged program visible
   float e = 0.f;
 #pragma unroll 1
   for (int half = 0; half < R / 16; ++half) {
@@ -708,7 +768,7 @@ __device__ __forceinline__ void run_hpass(const KernelArgs& ka, const DevPass* _
       const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff) + 2 * half;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint4 w = __ldg(ep + i);
+        const uint4 w = ep[i];
         eo[8 * i + 0] = w.x & 0xffffu; eo[8 * i + 1] = w.x >> 16;
         eo[8 * i + 2] = w.y & 0xffffu; eo[8 * i + 3] = w.y >> 16;
         eo[8 * i + 4] = w.z & 0xffffu; eo[8 * i + 5] = w.z >> 16;
@@ -1092,7 +1152,9 @@ constexpr int sweep_max_threads() { return ADJ ? (1 << (13 - K)) : 512; }
 template <int K, bool ADJ>
 __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(const __grid_constant__ KernelArgs ka) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float4 s_stage[kStageOps + kStageCoef / 4];
+  __shared__ float4 s_stage[(ADJ ? 2 : 1) * kStageF4];
+  __shared__ float s_scratch[ADJ ? kScratchFloats : 1];
+  __shared__ float s_gacc[ADJ ? kGaccSlots : 1];
   float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float2* s_lam = s_psi + (ADJ ? (1u << ka.T) : 0u);
   constexpr int R = 1 << K;
@@ -1105,6 +1167,17 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
   float2* lam_u = ka.lam ? ka.lam + ((size_t)u << ka.n) : nullptr;
   const uint32_t flags = ka.L.flags;
   const float2 one = make_float2(1.f, 0.f);
+  PassCtx cx;
+  cx.stage = s_stage;
+  cx.scratch = s_scratch;
+  cx.gacc = s_gacc;
+  cx.buf = 0;
+  cx.dbuf = ADJ;
+  const bool flush_gacc = ADJ && ka.L.gslot_count > 0 && ka.L.gslot_count <= kGaccSlots;
+  if constexpr (ADJ) {
+    if (flush_gacc)
+      for (int g = (int)tid; g < ka.L.gslot_count; g += (int)nthr) s_gacc[g] = 0.f;
+  }
 
   bool active = true;
   if (flags & LF_INIT_BASIS) {
@@ -1126,7 +1199,7 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
 
   if (active) {
     for (int p = ka.L.pass_a_begin; p < ka.L.pass_a_end; ++p)
-      run_pass<K, false>(ka, ka.passes + p, s_psi, s_lam, s_stage, goff, u);
+      run_pass<K, false>(ka, cx, p, p == ka.L.pass_a_begin, p + 1 == ka.L.pass_a_end, s_psi, s_lam, goff, u);
   }
   if (flags & LF_WRITE_STATE) {
     __syncthreads();
@@ -1142,19 +1215,29 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
         for (int m = 0; m < (1 << K); ++m) s_lam[pz ^ ka.L.soff[m]] = make_float2(0.f, 0.f);
       }
       for (int p = ka.L.pass_h_begin; p < ka.L.pass_h_end; ++p)
-        run_hpass<K, ADJ>(ka, ka.passes + p, s_psi, s_lam, s_stage, goff, u);
+        run_hpass<K, ADJ>(ka, cx, p, p == ka.L.pass_h_begin, p + 1 == ka.L.pass_h_end, s_psi, s_lam, goff, u);
     }
     expect_phase<K, ADJ>(ka, s_psi, s_lam, s_stage, goff, u, psi_u, hpasses);
   }
   if constexpr (ADJ) {
     for (int p = ka.L.pass_b_begin; p < ka.L.pass_b_end; ++p)
-      run_pass<K, true>(ka, ka.passes + p, s_psi, s_lam, s_stage, goff, u);
+      run_pass<K, true>(ka, cx, p, p == ka.L.pass_b_begin, p + 1 == ka.L.pass_b_end, s_psi, s_lam, goff, u);
   }
   if (flags & (LF_STORE_PSI | LF_STORE_LAM)) {
     __syncthreads();
     if (flags & LF_STORE_PSI) store_tile<K>(s_psi, ka.psi_out + ((size_t)u << ka.n), goff, ka, one);
     if constexpr (ADJ) {
       if (flags & LF_STORE_LAM) store_tile<K>(s_lam, lam_u, goff, ka, one);
+    }
+  }
+  if constexpr (ADJ) {
+    if (flush_gacc) {
+      __syncthreads();  // the last pass's sums are in s_gacc
+      double* grow = ka.gacc + (size_t)(ka.per_state ? (ka.grow0 + (int)u) : 0) * ka.P;
+      for (int g = (int)tid; g < ka.L.gslot_count; g += (int)nthr) {
+        const float v = s_gacc[g];
+        if (v != 0.f) atomicAdd(grow + __ldg(&ka.gsym[ka.L.gslot_begin + g]), (double)v);
+      }
     }
   }
 }

@@ -587,8 +587,15 @@ def convert_to_tensor(pauli_sums):
 # ----------------------------------------------------------------------------- cirq adapter
 
 
-def from_cirq(obj):  # pragma: no cover - cirq is not installed in this environment
-  """Converts a cirq.Circuit / cirq.PauliSum into this module's types (needs cirq)."""
+def from_cirq(obj):
+  """Converts a cirq.Circuit / cirq.PauliSum into this module's types (needs cirq).
+
+  cirq is not installable in this image: tests/test_adapters_fake_modules.py runs this function against
+  a minimal stand-in `cirq` module.  Gate set = what TFQ 0.6.1 serialises.  Controlled
+  operations (`op.controlled_by(...)`, TFQ's control_qubits / control_values) are accepted where they are
+  one of the native two-qubit gates -- a singly-controlled X**t is CNOT**t and a singly-controlled Z**t is
+  CZ**t (control value 1, zero global shift); any other controlled gate is rejected with a ValueError that
+  asks for a decomposition, because the gate table has no control field."""
   import cirq  # pylint: disable=import-outside-toplevel
 
   def qubit(q):
@@ -599,10 +606,23 @@ def from_cirq(obj):  # pragma: no cover - cirq is not installed in this environm
   kinds = [(cirq.XPowGate, 1), (cirq.YPowGate, 2), (cirq.ZPowGate, 3), (cirq.HPowGate, 4),
            (cirq.CZPowGate, 5), (cirq.CNotPowGate, 6), (cirq.SwapPowGate, 7), (cirq.ISwapPowGate, 8),
            (cirq.XXPowGate, 9), (cirq.YYPowGate, 10), (cirq.ZZPowGate, 11)]
+  controlled_gate = getattr(cirq, "ControlledGate", ())
   out = Circuit()
   for op in obj.all_operations():
     g = op.gate
     qs = [qubit(q) for q in op.qubits]
+    if controlled_gate and isinstance(g, controlled_gate):
+      sub = g.sub_gate
+      values = [tuple(v) for v in getattr(g, "control_values", [(1,)])]
+      simple = g.num_controls() == 1 and values == [(1,)] and getattr(sub, "global_shift", 0) == 0
+      if simple and isinstance(sub, cirq.XPowGate):
+        out.append(Gate(6, (sub.exponent,), 0.0).on(*qs))  # CNotPow: control first
+        continue
+      if simple and isinstance(sub, cirq.ZPowGate):
+        out.append(Gate(5, (sub.exponent,), 0.0).on(*qs))  # CZPow
+        continue
+      raise ValueError(f"controlled gate {g!r} has no entry in the gate table (no control_qubits field): "
+                       "decompose it into the TFQ-serialisable one- and two-qubit gates first")
     if isinstance(g, cirq.IdentityGate):
       out.append(I.on(qs[0]))
       continue

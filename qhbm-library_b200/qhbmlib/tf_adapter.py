@@ -1,18 +1,26 @@
-"""TensorFlow binding of the engine (import-guarded: TensorFlow is not installable in this image, so
-this module is exercised only where TF >= 2.7 with GPU support exists).
+"""TensorFlow binding of the engine.  EXPERIMENTAL: TensorFlow is not installable in this image, so the
+module has never run under a real TensorFlow; tests/test_adapters_fake_modules.py executes every line of
+it against a minimal stand-in `tensorflow` module (DLPack hand-over, custom_gradient wiring, shapes), and
+INTEGRATION.md describes what a maintainer has to check on a TF >= 2.7 GPU install.
 
 `expectation(plan, basis_idx, symbol_values)` is the drop-in for the `tfq.layers.Expectation()` call at
 /root/reference/qhbmlib/inference/qnn.py:134-138: a `tf.custom_gradient` whose forward is
-`qhbm_expectation_forward` and whose backward is `qhbm_expectation_adjoint`, with tensors handed over
-as raw device pointers through DLPack.
-"""
-import ctypes
+`qhbm_expectation_forward` and whose backward is `qhbm_expectation_adjoint`.
 
-from qhbmlib import _native as nat
+Memory and ordering rules (the points a raw-pointer binding gets wrong):
+  * inputs cross as DLPack capsules that are CONSUMED (`torch.utils.dlpack.from_dlpack`), so TF's buffers
+    stay alive for the duration of the call and are only read;
+  * outputs are allocated by this side (never written into a TF tensor, which may be a shared constant) and
+    handed to TF with `tf.experimental.dlpack.from_dlpack`;
+  * the engine runs on torch's current stream; before TF sees an output the stream is synchronised, because
+    TF's compute stream is not reachable from Python and no cross-framework event exists.
+"""
+import torch
+from torch.utils import dlpack as torch_dlpack
 
 try:
   import tensorflow as tf  # pylint: disable=import-error
-except Exception:  # pragma: no cover
+except Exception:  # TensorFlow absent: `available()` is False and `expectation` raises
   tf = None
 
 
@@ -20,38 +28,35 @@ def available():
   return tf is not None
 
 
-def _dev_ptr(t):  # pragma: no cover - needs TensorFlow
-  cap = tf.experimental.dlpack.to_dlpack(t)
-  get = ctypes.pythonapi.PyCapsule_GetPointer
-  get.restype = ctypes.c_void_p
-  get.argtypes = [ctypes.py_object, ctypes.c_char_p]
-  managed = get(cap, b"dltensor")
-  return ctypes.cast(managed, ctypes.POINTER(ctypes.c_void_p))[0]  # DLTensor.data is the first field
+def _to_torch(t):
+  """TF tensor -> torch view of the same device memory (the capsule is consumed)."""
+  return torch_dlpack.from_dlpack(tf.experimental.dlpack.to_dlpack(t))
 
 
-def expectation(plan, basis_idx, symbol_values, grad_mode="tfq_fd"):  # pragma: no cover - needs TensorFlow
+def _to_tf(t):
+  """torch tensor -> TF tensor owning a reference to the same memory, after the producing stream finished."""
+  if t.is_cuda:
+    torch.cuda.current_stream(t.device).synchronize()
+  return tf.experimental.dlpack.from_dlpack(torch_dlpack.to_dlpack(t))
+
+
+def expectation(plan, basis_idx, symbol_values, grad_mode="tfq_fd"):
   """f32[U, O] expectations, differentiable w.r.t. `symbol_values` (f32[P]) under tf.GradientTape.
   `plan` is a qhbmlib.engine.ExpectationPlan; `basis_idx` an int64 GPU tensor [U]."""
   if tf is None:
     raise ImportError("TensorFlow is required for qhbmlib.tf_adapter")
-  from qhbmlib import engine
-  lib = nat.lib()
-  mode = engine.GRAD_MODES[grad_mode]
+  basis = _to_torch(basis_idx)
 
   @tf.custom_gradient
   def op(values):
-    u = int(basis_idx.shape[0])
-    out = tf.zeros([u, plan.n_ops], tf.float32)
-    nat.check(lib.qhbm_expectation_forward(plan._plan, _dev_ptr(basis_idx), u, _dev_ptr(values), _dev_ptr(out),
-                                           None))
+    vals = _to_torch(values).to(torch.float32).contiguous()
+    out = plan.forward(basis, vals)
 
     def grad(upstream):
-      g = tf.zeros_like(values)
-      e = tf.zeros([u, plan.n_ops], tf.float32)
-      nat.check(lib.qhbm_expectation_adjoint(plan._plan, _dev_ptr(basis_idx), u, _dev_ptr(values),
-                                             _dev_ptr(tf.identity(upstream)), _dev_ptr(e), _dev_ptr(g), 0, mode, None))
-      return g
+      up = _to_torch(tf.identity(upstream)).to(torch.float32).contiguous()
+      _, g = plan.forward_adjoint(basis, vals, up, per_state=False, grad_mode=grad_mode)
+      return _to_tf(g)
 
-    return out, grad
+    return _to_tf(out), grad
 
   return op(symbol_values)

@@ -25,7 +25,8 @@ h = cq.convert_to_tensor([arch.tfim_ring(qubits)])
 beta = torch.tensor(1.0, device="cuda")
 params = qhbm.trainable_variables
 opt = torch.optim.Adam(params, lr=1e-2)
-for it in range(8):
+times = []
+for it in range(30):
   torch.cuda.synchronize()
   t0 = time.perf_counter()
   opt.zero_grad()
@@ -33,5 +34,8 @@ for it in range(8):
   loss.backward()
   opt.step()
   torch.cuda.synchronize()
-  dt = time.perf_counter() - t0
-  print(f"step {it}: loss {float(loss):.5f}  {dt * 1e3:.2f} ms  ({num_samples} samples, n={n})", flush=True)
+  times.append(time.perf_counter() - t0)
+times = sorted(times[10:])
+print(f"VQT step (sample, unique, expectation, backward, Adam), n={n}, {num_samples} samples: "
+      f"median {times[len(times) // 2] * 1e3:.2f} ms, min {times[0] * 1e3:.2f} ms, last loss {float(loss.detach()):.5f}",
+      flush=True)

@@ -268,3 +268,40 @@ def test_sampled_split_terms():
   only_identity = cq.convert_to_tensor([cq.PauliSum.from_pauli_strings(cq.PauliString(0.7, {}))])
   term_ops, mix, offsets = qnn.SampledQuantumInference._split_terms(only_identity, q)
   assert len(term_ops) == 1 and float(mix.abs().sum()) == 0.0 and offsets.tolist() == pytest.approx([0.7])
+
+
+def test_variables_updated_sees_writes_through_dot_data():
+  """`p.data.add_()` changes neither the storage pointer nor the version counter; the preface
+  must still notice it (the reference compares values on every call, ebm.py:125-140)."""
+  from qhbmlib import inference
+  energy = models.BernoulliEnergy([0, 1, 2], energy_utils.Constant(0.3) if hasattr(energy_utils, "Constant") else None)
+  inf = inference.BernoulliEnergyInference(energy, 10, initial_seed=1)
+  kernel = energy.post_process[0].kernel
+  with torch.no_grad():
+    kernel.copy_(torch.tensor([0.3, -0.2, 0.5]))
+  with torch.no_grad():  # (with gradients the log-partition draws samples: CUDA only)
+    lp0 = float(inf.log_partition())
+  assert not inf.variables_updated
+  ptr, version = kernel.data_ptr(), kernel._version
+  kernel.data.add_(1.0)
+  assert (kernel.data_ptr(), kernel._version) == (ptr, version)   # the cheap test would have missed it
+  assert inf.variables_updated
+  with torch.no_grad():
+    lp1 = float(inf.log_partition())
+  t = np.array([1.3, 0.8, 1.5])
+  np.testing.assert_allclose(lp1, np.sum(np.log(2 * np.cosh(t))), rtol=1e-6)
+  assert abs(lp1 - lp0) > 0.5
+
+
+def test_plan_cache_lru_is_bounded_and_content_keyed():
+  from qhbmlib.inference import qnn
+  lru = qnn._LRU(3)
+  made = []
+  for key in ["a", "b", "a", "c", "d", "a", "b"]:
+    lru.get(key, lambda k=key: made.append(k) or k.upper())
+  assert made == ["a", "b", "c", "d", "b"] and len(lru) == 3   # "b" was evicted by "d", "a" stayed hot
+  qubits = cq.GridQubit.rect(1, 3)
+  h1 = cq.convert_to_tensor([cq.Z(qubits[0]) * cq.Z(qubits[1]) + 0.5 * cq.X(qubits[2])])
+  h2 = cq.convert_to_tensor([cq.Z(qubits[0]) * cq.Z(qubits[1]) + 0.5 * cq.X(qubits[2])])
+  h3 = cq.convert_to_tensor([cq.Z(qubits[0]) * cq.Z(qubits[1]) + 0.25 * cq.X(qubits[2])])
+  assert h1 is not h2 and h1.tables_digest(qubits) == h2.tables_digest(qubits) != h3.tables_digest(qubits)

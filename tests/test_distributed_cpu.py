@@ -114,3 +114,122 @@ def test_merge_log_stats_matches_logsumexp():
   np.testing.assert_allclose(m + math.log(s), orc.logsumexp(l), rtol=1e-13)
   pr = np.exp(l - orc.logsumexp(l))
   np.testing.assert_allclose(m + math.log(s) - t / s, -(pr * np.log(pr)).sum(), rtol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------
+# Sharding behind the API (host logic on CPU): EnergyInference._expectation / _log_partition with the
+# differentiable collectives of qhbmlib.distributed.  The sampler is replaced by fixed unique bitstrings so
+# that no CUDA kernel is needed; values and gradients at world size 2 must equal the single-process ones.
+# ------------------------------------------------------------------------------------------------
+def _make_inference():
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  for p in (root, os.path.join(root, "qhbm-library_b200")):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  from qhbmlib import models
+  from qhbmlib.inference import ebm
+  from qhbmlib.models import energy_utils
+
+  class FixedSamples(ebm.EnergyInference):
+    """EnergyInference whose `unique_samples` returns a fixed dedup result (identical on every rank)."""
+
+    def __init__(self, energy):
+      super().__init__(energy, 100, initial_seed=5)
+      rng = np.random.default_rng(9)
+      rows = rng.choice(1 << 5, 13, replace=False)
+      self.bits = torch.tensor(((rows[:, None] >> (4 - np.arange(5))[None, :]) & 1).astype(np.int8))
+      self.counts = torch.tensor(rng.integers(1, 30, 13).astype(np.int32))
+
+    def unique_samples(self, num_samples):
+      return self.bits, None, self.counts
+
+    def _ready_inference(self):
+      pass
+
+    def _call(self, inputs, *a, **k):
+      raise NotImplementedError
+
+    def _sample(self, n):
+      raise NotImplementedError
+
+    def _log_partition_forward_pass(self):
+      return torch.tensor(0.25)
+
+  energy = models.KOBE(list(range(5)), 2, energy_utils.RandomNormal(0.0, 0.5, 3))
+  inf = FixedSamples(energy)
+  w = torch.nn.Parameter(torch.tensor([0.3, -0.7, 1.1, 0.2, -0.4], dtype=torch.float32))
+
+  def function(bits):
+    x = bits.to(torch.float32)
+    return {"a": torch.stack([x @ w, (x * x) @ (w * w)], 1), "b": [torch.sin(x @ w)]}
+
+  return inf, energy, w, function
+
+
+def _loss_and_grads():
+  from qhbmlib import distributed as qd
+  inf, energy, w, function = _make_inference()
+  out = inf.expectation(function)
+  loss = (out["a"] * torch.tensor([1.0, -2.0])).sum() + 3.0 * out["b"][0] + 0.5 * inf.log_partition()
+  loss = loss + 0.1 * (w * w).sum()  # a replicated (unsharded) term must survive the gradient averaging
+  loss.backward()
+  params = [w] + list(energy.parameters())
+  qd.sync_gradients(params)
+  return np.concatenate([[float(loss)]] + [p.grad.detach().double().reshape(-1).numpy() for p in params])
+
+
+def _api_worker(rank, world_size, port, out_dir):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world_size)
+  try:
+    np.save(os.path.join(out_dir, f"api{rank}.npy"), _loss_and_grads())
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world_size", [2, 3])
+def test_sharded_expectation_and_log_partition_match_single_process(tmp_path, world_size):
+  single = _loss_and_grads()
+  mp.spawn(_api_worker, args=(world_size, _free_port(), str(tmp_path)), nprocs=world_size, join=True)
+  outs = [np.load(tmp_path / f"api{r}.npy") for r in range(world_size)]
+  for o in outs[1:]:
+    np.testing.assert_array_equal(outs[0], o)           # every rank holds the same loss and gradients
+  np.testing.assert_allclose(outs[0], single, rtol=2e-6, atol=2e-7)
+
+
+def _collective_worker(rank, world_size, port, out_dir):
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  for p in (root, os.path.join(root, "qhbm-library_b200")):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  from qhbmlib import distributed as qd
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world_size)
+  try:
+    x = torch.nn.Parameter(torch.arange(7, dtype=torch.float64) + 1.0)
+    lo, hi = qd.shard_range(7, rank, world_size)
+    rows = (x[lo:hi] ** 2).unsqueeze(1)                 # this rank's rows of a [7, 1] result
+    full = qd.all_gather_rows(rows, 7)                  # [7, 1] on every rank
+    total = qd.all_reduce_sum((x[lo:hi] ** 3).sum().reshape(1))
+    with qd.local_shard():
+      assert not qd.active()
+    assert qd.active()
+    loss = (full[:, 0] * torch.arange(7, dtype=torch.float64)).sum() + 2.0 * total[0]
+    loss.backward()
+    qd.sync_gradients([x])
+    np.save(os.path.join(out_dir, f"c{rank}.npy"), np.concatenate([[float(loss)], x.grad.numpy()]))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_differentiable_collectives_give_the_single_process_gradient(tmp_path):
+  mp.spawn(_collective_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+  r0, r1 = np.load(tmp_path / "c0.npy"), np.load(tmp_path / "c1.npy")
+  np.testing.assert_array_equal(r0, r1)
+  x = np.arange(7) + 1.0
+  np.testing.assert_allclose(r0[0], (x**2 * np.arange(7)).sum() + 2 * (x**3).sum(), rtol=1e-14)
+  np.testing.assert_allclose(r0[1:], 2 * x * np.arange(7) + 6 * x**2, rtol=1e-14)

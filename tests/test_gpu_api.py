@@ -475,10 +475,13 @@ def test_config2_12q_vqt_kobe2_analytic():
   f = 0.8 * e_h[:, 0] - energies
   all_e = orc.kobe_energy(orc.all_bitstrings(n), 2, th)
   ref_loss = float(w @ f) - orc.analytic_log_partition(all_e)
-  np.testing.assert_allclose(float(loss), ref_loss, rtol=1e-5, atol=1e-5)
-  np.testing.assert_allclose(g_phi.cpu(), g_h.sum(0), rtol=1e-4, atol=2e-5)
+  # tolerances: 1e-5 relative with the absolute floor 1e-6 * (scale of the summed terms): the TFIM ring has
+  # sum|coeff| = 2n = 24, weighted by beta = 0.8
+  floor = 1e-6 * 0.8 * 24
+  np.testing.assert_allclose(float(loss), ref_loss, rtol=1e-5, atol=floor)
+  np.testing.assert_allclose(g_phi.cpu(), g_h.sum(0), rtol=1e-5, atol=floor)
   ref_gth = orc.expectation_score_gradient(counts, f, orc.parity_features(y, 2), np.zeros(len(th)), 1.0)
-  np.testing.assert_allclose(g_theta.cpu(), ref_gth, rtol=1e-4, atol=2e-5)
+  np.testing.assert_allclose(g_theta.cpu(), ref_gth, rtol=1e-5, atol=floor + 1e-6 * np.abs(energies).max())
 
 
 def test_single_observable_jacobian_in_forward_matches_resimulation():

@@ -1,8 +1,10 @@
 """GPU parity tests of the state-vector path, through the C ABI (libqhbm_b200.so).
 
 Oracle: oracle/qhbm_oracle.py (complex128).  Tolerance: north_star asks 1e-5 relative for
-complex64 results; here every comparison uses rtol 1e-5 with an absolute floor of
-1e-5 * sum|coeff| (expectations of many cancelling terms)."""
+complex64 results; every comparison uses rtol 1e-5 with the absolute floor SURVEY section 7 item 6
+prescribes for sums of cancelling Pauli terms, 1e-6 * sum|coeff| (times the upstream weights for
+gradients).  `_check` prints the worst error / tolerance ratio it saw, so the margin is visible in
+`pytest -s` output and in the per-round pytest log."""
 import numpy as np
 import pytest
 import torch
@@ -13,6 +15,17 @@ import helpers as hp
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
+FLOOR = 1e-6  # x sum|coeff| (x upstream weight)
+WORST = {"ratio": 0.0}
+
+
+def _check(got, ref, floor, what):
+  """|got - ref| <= RTOL |ref| + floor element-wise (floor broadcastable)."""
+  got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+  ratio = np.abs(got - ref) / (RTOL * np.abs(ref) + floor)
+  worst = float(ratio.max()) if ratio.size else 0.0
+  WORST["ratio"] = max(WORST["ratio"], worst)
+  assert worst <= 1.0, f"{what}: error / tolerance = {worst:.3g} (worst so far {WORST['ratio']:.3g})"
 
 
 def _plan(gates, n, nsym, ops, grad=True, T=0, K=0):
@@ -34,20 +47,19 @@ def _compare(gates, n, nsym, ops, rng, n_states, T=0, K=0, mode="exact", check_s
   d_basis = torch.tensor(basis, device="cuda")
   d_dg = torch.tensor(dg, device="cuda")
   e_ref, g_ref = orc.batch_expectation_and_gradient(gates, n, phi, basis, ops, dg, mode)
-  scale = _scale(ops)
+  scale = _scale(ops)  # sum|coeff| per observable
   # forward only
   e_fwd = plan.forward(d_basis, d_phi).cpu().numpy()
-  np.testing.assert_allclose(e_fwd, e_ref, rtol=RTOL, atol=RTOL * scale.max())
+  _check(e_fwd, e_ref, FLOOR * scale[None, :], "forward expectations")
   # forward + adjoint, reduced gradient
   e, g = plan.forward_adjoint(d_basis, d_phi, d_dg, grad_mode=mode)
-  np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=RTOL, atol=RTOL * scale.max())
-  # absolute floor: a gradient that vanishes analytically still carries complex64 rounding of O(|coeff|)
-  gscale = max(np.abs(g_ref).sum(0).max(), scale.max() * len(basis))
-  np.testing.assert_allclose(g.cpu().numpy(), g_ref.sum(0), rtol=RTOL, atol=RTOL * gscale)
+  _check(e.cpu().numpy(), e_ref, FLOOR * scale[None, :], "expectations of the adjoint call")
+  # a gradient that vanishes analytically still carries complex64 rounding of O(|upstream| sum|coeff|)
+  gfloor_state = FLOOR * (np.abs(dg) * scale[None, :]).sum(1)  # per state
+  _check(g.cpu().numpy(), g_ref.sum(0), gfloor_state.sum(), "reduced gradient")
   # un-reduced gradient (the TFQ op's own output shape)
   _, gp = plan.forward_adjoint(d_basis, d_phi, d_dg, per_state=True, grad_mode=mode)
-  np.testing.assert_allclose(gp.cpu().numpy(), g_ref, rtol=RTOL,
-                             atol=RTOL * max(np.abs(g_ref).max(), scale.max()) * 3)
+  _check(gp.cpu().numpy(), g_ref, gfloor_state[:, None], "per-state gradient")
   if check_state:
     st = plan.state(int(basis[0]), d_phi).cpu().numpy()
     np.testing.assert_allclose(st, orc.simulate(gates, n, phi, basis[0]), atol=3e-6)
@@ -132,7 +144,7 @@ def test_forward_only_expectation_stages_and_passes(n, T, K, ham, monkeypatch):
   basis = rng.choice(1 << n, 6, replace=False).astype(np.int64)
   e = plan.forward(torch.tensor(basis, device="cuda"), torch.tensor(phi, device="cuda")).cpu().numpy()
   e_ref = orc.expectations(gates, n, phi, basis, ops)
-  np.testing.assert_allclose(e, e_ref, rtol=RTOL, atol=RTOL * _scale(ops).max())
+  _check(e, e_ref, FLOOR * _scale(ops)[None, :], "expectations")
 
 
 @pytest.mark.parametrize("n,T,K", [(4, 0, 4), (11, 9, 4)])
@@ -155,20 +167,19 @@ def test_many_diagonal_shards_walsh_hadamard_path(n, T, K, grad):
   basis = rng.choice(1 << n, 4, replace=False).astype(np.int64)
   plan = _plan(gates, n, len(names), ops, grad, T, K)
   d_phi, d_basis = torch.tensor(phi, device="cuda"), torch.tensor(basis, device="cuda")
-  scale = _scale(ops).max()
+  scale = _scale(ops)[None, :]
   if not grad:
     e = plan.forward(d_basis, d_phi).cpu().numpy()
     e_ref = orc.expectations(gates, n, phi, basis, ops)
-    np.testing.assert_allclose(e, e_ref, rtol=RTOL, atol=RTOL * scale)
+    _check(e, e_ref, FLOOR * scale, "WHT forward expectations")
     return
   dg = rng.uniform(-1, 1, (len(basis), len(ops))).astype(np.float32)
   e_ref, g_ref = orc.batch_expectation_and_gradient(gates, n, phi, basis, ops, dg)
   e, g = plan.forward_adjoint(d_basis, d_phi, torch.tensor(dg, device="cuda"), grad_mode="exact")
-  np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=RTOL, atol=RTOL * scale)
-  gs = g_ref.sum(0)
-  np.testing.assert_allclose(g.cpu().numpy(), gs, rtol=RTOL, atol=RTOL * np.abs(g_ref).sum(0).max())
+  _check(e.cpu().numpy(), e_ref, FLOOR * scale, "WHT expectations")
+  _check(g.cpu().numpy(), g_ref.sum(0), FLOOR * (np.abs(dg) * scale).sum(), "WHT reduced gradient")
   e2 = plan.forward(d_basis, d_phi).cpu().numpy()   # forward-only call on an adjoint plan
-  np.testing.assert_allclose(e2, e_ref, rtol=RTOL, atol=RTOL * scale)
+  _check(e2, e_ref, FLOOR * scale, "WHT forward-only call on an adjoint plan")
 
 
 def test_config1_4q_tfim_bernoulli_samples():
@@ -186,8 +197,8 @@ def test_config1_4q_tfim_bernoulli_samples():
   plan = _plan(gates, n, len(names), ops)
   basis = torch.tensor(orc.bitstrings_to_index(y), device="cuda")
   vals = plan.forward(basis, torch.tensor(phi, device="cuda")).cpu().numpy()
-  np.testing.assert_allclose(vals, ref_vals, rtol=RTOL, atol=RTOL * 8)
-  np.testing.assert_allclose(orc.weighted_average(counts, vals), ref_avg, rtol=RTOL, atol=RTOL * 8)
+  np.testing.assert_allclose(vals, ref_vals, rtol=RTOL, atol=FLOOR * 8)
+  np.testing.assert_allclose(orc.weighted_average(counts, vals), ref_avg, rtol=RTOL, atol=FLOOR * 8)
 
 
 def test_config3_16q_xxz_adjoint_sample_against_oracle():
@@ -243,7 +254,7 @@ def test_config4_20q_tfim_forward_sample_and_properties():
   basis = rng.choice(1 << n, 64, replace=False).astype(np.int64)
   e = plan.forward(torch.tensor(basis, device="cuda"), d_phi).cpu().numpy()
   e_ref = orc.expectations(gates, n, phi, basis[:2], ops)
-  np.testing.assert_allclose(e[:2], e_ref, rtol=RTOL, atol=RTOL * 2 * n)
+  np.testing.assert_allclose(e[:2], e_ref, rtol=RTOL, atol=FLOOR * 2 * n)
   np.testing.assert_allclose(e[:, 1], 1.0, atol=3e-6)
   e_a = plan.forward(torch.tensor(basis[:23], device="cuda"), d_phi).cpu().numpy()
   e_b = plan.forward(torch.tensor(basis[23:], device="cuda"), d_phi).cpu().numpy()
@@ -316,11 +327,12 @@ def test_host_buffer_entry_point():
   dg = rng.uniform(-1, 1, (7, 2)).astype(np.float32)
   e, g = plan.run_host(basis, phi, dg)
   e_ref, g_ref = orc.batch_expectation_and_gradient(gates, n, phi, basis, ops, dg)
-  np.testing.assert_allclose(e, e_ref, rtol=RTOL, atol=RTOL * 12)
-  np.testing.assert_allclose(g, g_ref.sum(0), rtol=RTOL, atol=RTOL * np.abs(g_ref).sum(0).max())
+  scale = _scale(ops)[None, :]
+  _check(e, e_ref, FLOOR * scale, "host-buffer expectations")
+  _check(g, g_ref.sum(0), FLOOR * (np.abs(dg) * scale).sum(), "host-buffer reduced gradient")
   e2, g2 = plan.run_host(basis, phi)
   assert g2 is None
-  np.testing.assert_allclose(e2, e_ref, rtol=RTOL, atol=RTOL * 12)
+  _check(e2, e_ref, FLOOR * scale, "host-buffer forward expectations")
 
 
 def test_errors_are_reported():
@@ -409,5 +421,5 @@ def test_adjoint_in_small_chunks_matches_one_chunk(n, ham, monkeypatch):
   np.testing.assert_allclose(gr1.cpu().numpy(), gr0.cpu().numpy(), rtol=1e-5, atol=1e-6)
   e_ref, g_ref = orc.batch_expectation_and_gradient(gates, n, phi.cpu().numpy(), basis.cpu().numpy(), ops,
                                                     dg.cpu().numpy())
-  np.testing.assert_allclose(e1.cpu().numpy(), e_ref, rtol=RTOL, atol=RTOL * _scale(ops).max())
-  np.testing.assert_allclose(g1.cpu().numpy(), g_ref, rtol=RTOL, atol=RTOL * _scale(ops).max() * 3)
+  _check(e1.cpu().numpy(), e_ref, FLOOR * _scale(ops)[None, :], "chunked expectations")
+  _check(g1.cpu().numpy(), g_ref, FLOOR * np.abs(dg.cpu().numpy()) * _scale(ops).max(), "chunked per-state gradient")

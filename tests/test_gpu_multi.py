@@ -102,3 +102,86 @@ def test_two_gpu_sharded_expectation_and_ebm_sweep(tmp_path):
   obs = r0["hist"].reshape(64, -1).sum(1)
   exp = p.reshape(64, -1).sum(1) * 200000
   assert np.sum((obs - exp)**2 / exp) < 2.5 * 64
+
+
+# ------------------------------------------------------------------------------------------------
+# Sharding behind the API: vqt / qmhl losses, their gradients and the analytic sampler must be the same at
+# world size 1 and 2 (north_star: "the API stays intact").
+# ------------------------------------------------------------------------------------------------
+def _api_results(dev):
+  """VQT and QMHL losses + gradients and a sample draw, built from fixed seeds on device `dev`.
+  Under an initialised process group the inference engines shard by themselves."""
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  for p in (root, os.path.join(root, "qhbm-library_b200")):
+    if p not in sys.path:
+      sys.path.insert(0, p)
+  from qhbmlib import architectures as arch
+  from qhbmlib import circuits as cq
+  from qhbmlib import data as qdata
+  from qhbmlib import distributed as qd
+  from qhbmlib import inference
+  from qhbmlib import models
+  from qhbmlib.models import energy_utils
+  n, num_samples = 12, 3000
+  qubits = cq.GridQubit.rect(1, n)
+  out = {}
+
+  def make_qhbm(tag, seed):
+    energy = models.KOBE(list(range(n)), 2, energy_utils.RandomNormal(0.0, 0.3, seed))
+    e_inf = inference.AnalyticEnergyInference(energy, num_samples, initial_seed=[seed, seed + 1])
+    circ = models.DirectQuantumCircuit(arch.get_hardware_efficient_model_unitary(qubits, 2, tag),
+                                       energy_utils.RandomUniform(-1, 1, seed + 2))
+    return inference.QHBM(e_inf, inference.AnalyticQuantumInference(circ, grad_mode="exact")), energy, circ
+
+  # --- VQT
+  qhbm, energy, circ = make_qhbm("v", 21)
+  loss = inference.vqt(qhbm, cq.convert_to_tensor([arch.tfim_ring(qubits)]), torch.tensor(0.7, device=dev))
+  params = [energy.post_process[0].kernel, circ.trainable_variables[0]]
+  loss.backward()
+  qd.sync_gradients(params)
+  out["vqt_loss"] = np.array([float(loss)])
+  out["vqt_g_theta"], out["vqt_g_phi"] = [p.grad.detach().double().cpu().numpy() for p in params]
+  out["samples"] = qhbm.e_inference.sample(20000).to(torch.int64).sum(1).cpu().numpy()  # popcount per sample
+  out["entropy"] = np.array([float(qhbm.e_inference.entropy())])
+  # --- QMHL: data QHBM (fixed) against a model QHBM
+  data_qhbm, _, _ = make_qhbm("d", 31)
+  model, m_energy, m_circ = make_qhbm("m", 41)
+  loss = inference.qmhl(qdata.QHBMData(data_qhbm), model)
+  params = [m_energy.post_process[0].kernel, m_circ.trainable_variables[0]]
+  loss.backward()
+  qd.sync_gradients(params)
+  out["qmhl_loss"] = np.array([float(loss)])
+  out["qmhl_g_theta"], out["qmhl_g_phi"] = [p.grad.detach().double().cpu().numpy() for p in params]
+  return out
+
+
+def _api_worker(rank, world_size, port, out_dir):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=torch.device("cuda", rank))
+  try:
+    np.savez(os.path.join(out_dir, f"api{rank}.npz"), **_api_results(torch.device("cuda", rank)))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_vqt_and_qmhl_equal_single_gpu(tmp_path):
+  world_size = 2
+  mp.spawn(_api_worker, args=(world_size, _free_port(), str(tmp_path)), nprocs=world_size, join=True)
+  r0, r1 = np.load(tmp_path / "api0.npz"), np.load(tmp_path / "api1.npz")
+  torch.cuda.set_device(0)
+  single = _api_results(torch.device("cuda", 0))
+  for key in single:
+    np.testing.assert_array_equal(r0[key], r1[key])              # all ranks agree exactly
+  # the sharded analytic sampler reproduces the single-GPU draw (same seed, any number of ranks)
+  assert int((r0["samples"] != single["samples"]).sum()) <= 2
+  np.testing.assert_allclose(r0["entropy"], single["entropy"], rtol=1e-6)
+  for key in ("vqt_loss", "qmhl_loss"):
+    np.testing.assert_allclose(r0[key], single[key], rtol=2e-6, atol=2e-6)
+  for key in ("vqt_g_theta", "vqt_g_phi", "qmhl_g_theta", "qmhl_g_phi"):
+    scale = np.abs(single[key]).max()
+    np.testing.assert_allclose(r0[key], single[key], rtol=1e-5, atol=2e-6 * max(scale, 1.0))
+    assert scale > 1e-3

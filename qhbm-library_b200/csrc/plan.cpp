@@ -241,8 +241,7 @@ class Compiler {
     const int n = hp_.n_eff, K = hp_.K;
     std::vector<char> done(atoms.size(), 0);
     size_t remaining = atoms.size();
-    // gradient scratch: kScratchFloats floats of shared memory, one per (slot, thread)
-    const int max_slots = std::min(kScratchFloats >> (std::min(hp_.T, n) - K), 255);
+    const int max_slots = std::min(4 * (1 << K), 255);  // gradient scratch = the two dead smem tiles
     while (remaining > 0) {
       SweepOut sw;
       sw.tile_bits = choose_tile(atoms, done);
@@ -384,7 +383,8 @@ class Compiler {
                   const qhbm_gate_t& g = hp_.gates[x.gates[0]];
                   for (int k = 0; k < g.nparams; ++k) ng += g.sym[k] >= 0;
                 }
-                if (ps.ngrad + ng > max_slots || !fits(x)) { b2.block(x); continue; }
+                // (the block that closes the run, atom `a`, still needs its own `ngrads` slots)
+                if (ps.ngrad + ng + ngrads > max_slots || !fits(x)) { b2.block(x); continue; }
                 emit_diag(x, backward, regpos, ps, run);
                 done[aj] = 1;
                 --remaining;
@@ -406,6 +406,7 @@ class Compiler {
         ps.coef_end = hp_.ncoef;
         if (ps.op_end - ps.op_begin > kStageOps || ps.coef_end - ps.coef_begin > kStageCoef)
           throw std::runtime_error("internal: a pass program exceeds the staging buffer");
+        if (ps.ngrad > max_slots) throw std::runtime_error("internal: a pass has more gradient slots than scratch");
         hp_.passes.push_back(ps);
         executed_in_sweep += executed;
         if (!have_nondiag && remaining > 0) {
@@ -1007,7 +1008,21 @@ class Compiler {
           DevOp op = make_op(type);
           op.p0 = xr;
           op.aux0 = (int32_t)zo;
+          // table shape (see hx_apply): 1 = uniform, 2 = zero on even flip parity and uniform elsewhere
           op.aux1 = 0;
+          {
+            std::vector<float> tv(R);
+            std::memcpy(tv.data(), tab.data(), sizeof(float) * R);
+            bool uniform = true, flip = xr != 0;
+            const float odd = tv[xr & -xr];
+            for (int r = 0; r < R; ++r) {
+              uniform = uniform && tv[r] == tv[0];
+              const bool oddp = __builtin_popcount(r & xr) & 1;
+              flip = flip && (oddp ? tv[r] == odd : tv[r] == 0.f);
+            }
+            if (uniform) op.aux1 = 1;
+            else if (flip) op.aux1 = 2;
+          }
           op.coef = alloc_coef(R);
           add_job(PJ_CONST, op.coef, 0, 0, 0, 0, tab);
           hp_.ops.push_back(op);

@@ -23,7 +23,6 @@ constexpr int kConstGroupBits = 7;  // width of one "thread-constant" phase tabl
 constexpr int kMaxRuns = 16;
 constexpr int kStageOps = 192;     // ops of one pass: the compiler closes a pass before its program exceeds the
 constexpr int kStageCoef = 1792;   // shared-memory staging buffer (op descriptors / coefficient floats)
-constexpr int kScratchFloats = 4096;  // gradient scratch of a pass: slots x threads (adjoint kernel)
 constexpr int kGaccSlots = 512;       // gradient slots of one launch accumulated in shared memory
 
 enum OpType : int32_t {

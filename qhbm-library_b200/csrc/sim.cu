@@ -119,11 +119,23 @@ void allow_large_smem() {
   allow(reinterpret_cast<const void*>(sweep_kernel<4, false>));
   allow(reinterpret_cast<const void*>(sweep_kernel<5, true>));
   allow(reinterpret_cast<const void*>(sweep_kernel<5, false>));
+  allow(reinterpret_cast<const void*>(sweep_kernel<4, false, true>));
 }
 
 void launch_any(const qhbm_plan* p, bool adj, const KernelArgs& ka, int n_states, cudaStream_t s) {
   const HostPlan& hp = p->hp;
   const int threads = 1 << (hp.T - hp.K);
+  // forward sweeps of an adjoint plan (psi only, no expectation phase, no backward passes) run on the dense
+  // forward kernel: one tile of shared memory and ~80 registers instead of two tiles and 128
+  const bool psi_only = !(ka.L.flags & (LF_EXPECT | LF_LOAD_LAM | LF_STORE_LAM | LF_WRITE_STATE)) &&
+                        ka.L.pass_b_end == ka.L.pass_b_begin;
+  static const bool no_dense = std::getenv("QHBM_NO_DENSE_FWD") != nullptr;
+  if (adj && psi_only && hp.K == 4 && threads <= 256 && hp.tiles() > 1 && !no_dense) {
+    const size_t smem1 = (size_t)8u * (1u << hp.T);
+    sweep_kernel<4, false, true><<<(unsigned)(n_states * hp.tiles()), threads, smem1, s>>>(ka);
+    QHBM_CUDA(cudaGetLastError());
+    return;
+  }
   // psi tile (+ lambda tile for the adjoint kernel; forward-only WHT needs a float scratch tile)
   const size_t smem = (size_t)(adj ? 2 : 1) * 8u * (1u << hp.T) + ((!adj && !hp.dterms.empty()) ? 4u * (1u << hp.T) : 0u);
   const int tiles = hp.tiles();
@@ -176,6 +188,10 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
   ka.O = hp.O;
   ka.P = hp.P;
   ka.phase_coef = hp.phase_coef;
+  // cp.async tile loads: measured 17.38 -> 17.04 ms per 4096 bitstrings on config 3
+  // (profiles/r2_tile_copy_experiment.md); QHBM_SYNC_TILE=1 restores the register-staged copy
+  static const bool sync_tile = std::getenv("QHBM_SYNC_TILE") != nullptr;
+  ka.async_tile = sync_tile ? 0 : 1;
 }
 
 // Coefficient jobs + clearing of the call's float64 accumulators in one launch.

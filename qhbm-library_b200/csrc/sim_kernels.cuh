@@ -44,6 +44,7 @@ struct KernelArgs {
   int32_t grow0;          // accumulator row of this chunk's first state (per-state gradients)
   int32_t per_state;
   int32_t phase_coef;     // coef offset of the dropped global phase (debug state output), or -1
+  int32_t async_tile;     // tiles are loaded with cp.async (default; QHBM_SYNC_TILE=1 turns it off)
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t x) {
@@ -103,13 +104,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
+// One op descriptor in registers: the 16-byte PackedOp as loaded.  type / p0 / p1 / gslot stay packed in
+// w0 and are extracted where they are used (one instruction each), which keeps the interpreter's live
+// state at 4 registers per descriptor instead of 7 -- the kernel runs at the 128-register cap.
 struct OpRec {
-  int type, p0, p1, coef, gslot, aux0, aux1;
+  uint32_t w0;
+  int coef, aux0, aux1;
+  __device__ __forceinline__ int type() const { return (int)(w0 & 0xffu); }
+  __device__ __forceinline__ int p0() const { return (int)((w0 >> 8) & 0xffu); }
+  __device__ __forceinline__ int p1() const { return (int)((w0 >> 16) & 0xffu); }
+  __device__ __forceinline__ int gslot() const { return (int)(w0 >> 24); }
 };
 __device__ __forceinline__ OpRec load_op(const PackedOp* op) {
   const int4 a = *reinterpret_cast<const int4*>(op);
   OpRec r;
-  r.type = a.x & 0xff; r.p0 = (a.x >> 8) & 0xff; r.p1 = (a.x >> 16) & 0xff; r.gslot = (int)((uint32_t)a.x >> 24);
+  r.w0 = (uint32_t)a.x;
   r.coef = a.y; r.aux0 = a.z; r.aux1 = a.w;
   return r;
 }
@@ -367,38 +376,34 @@ __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const f
                                               const PackedOp* __restrict__ ops, const int n_const, const int n_reg1,
                                               const int count, const bool pairs, const float* __restrict__ coef,
                                               float* scratch, uint32_t gbase, uint32_t tid, uint32_t nthr) {
-  OpRec nxt = load_op(ops);  // issued before the marginals so that its latency is covered
   Marginals<K> mg;
   compute_marginals<K>(a, b, mg, pairs);
   const float2 T = mg.T;
   int i = 0;
   // gates whose qubits are all thread-constant: one selected entry times the thread totals
   for (; i < n_const; ++i) {
-    const OpRec op = nxt;
-    if (i + 1 < count) nxt = load_op(ops + i + 1);
+    const OpRec op = load_op(ops + i);  // shared memory: no prefetch needed
     int sel = (gbase >> op.aux0) & 1;
     if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1);
     const float2 m = ldg2(coef + op.coef + 2 * sel);
-    scratch[op.gslot * nthr + tid] = 2.f * hsum(mul2(m, T));
+    scratch[op.gslot() * nthr + tid] = 2.f * hsum(mul2(m, T));
   }
   // one register bit (plus, for OP_GD_MIX, one thread-constant bit)
   for (; i < n_const + n_reg1; ++i) {
-    const OpRec op = nxt;
-    if (i + 1 < count) nxt = load_op(ops + i + 1);
-    const int cb = op.type == OP_GD_MIX ? ((gbase >> op.aux0) & 1) : 0;
-    const float2 S1 = pick2<K>(mg.S, op.p0);
+    const OpRec op = load_op(ops + i);  // shared memory: no prefetch needed
+    const int cb = op.type() == OP_GD_MIX ? ((gbase >> op.aux0) & 1) : 0;
+    const float2 S1 = pick2<K>(mg.S, op.p0());
     const float4 m = ldg4(coef + op.coef + 4 * cb);
     const float2 D = add2(T, make_float2(-S1.x, -S1.y));
     const float2 v = fma2(make_float2(m.z, m.w), S1, mul2(make_float2(m.x, m.y), D));
-    scratch[op.gslot * nthr + tid] = 2.f * hsum(v);
+    scratch[op.gslot() * nthr + tid] = 2.f * hsum(v);
   }
   // two register bits, p0 > p1
   for (; i < count; ++i) {
-    const OpRec op = nxt;
-    if (i + 1 < count) nxt = load_op(ops + i + 1);
+    const OpRec op = load_op(ops + i);  // shared memory: no prefetch needed
     const float* e = coef + op.coef;
-    const float2 Sh = pick2<K>(mg.S, op.p0), Sl = pick2<K>(mg.S, op.p1);
-    const float2 S11 = pick2<Marginals<K>::NP>(mg.SS, op.p0 * (op.p0 - 1) / 2 + op.p1);
+    const float2 Sh = pick2<K>(mg.S, op.p0()), Sl = pick2<K>(mg.S, op.p1());
+    const float2 S11 = pick2<Marginals<K>::NP>(mg.SS, op.p0() * (op.p0() - 1) / 2 + op.p1());
     const float4 m01 = ldg4(e), m23 = ldg4(e + 4);
     const float2 n11 = make_float2(-S11.x, -S11.y);
     const float2 Slo = add2(Sl, n11), Shi = add2(Sh, n11);                 // lo bit only / hi bit only
@@ -407,7 +412,7 @@ __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const f
     v = fma2(make_float2(m01.z, m01.w), Slo, v);
     v = fma2(make_float2(m23.x, m23.y), Shi, v);
     v = fma2(make_float2(m23.z, m23.w), S11, v);
-    scratch[op.gslot * nthr + tid] = 2.f * hsum(v);
+    scratch[op.gslot() * nthr + tid] = 2.f * hsum(v);
   }
 }
 
@@ -419,11 +424,9 @@ __device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const f
 //   stage   : two program buffers (pass descriptor + op descriptors + coefficients); while a pass runs from
 //             one, the next pass's program streams into the other with cp.async (LDGSTS), so no pass waits
 //             for global memory except the first of a range
-//   scratch : per-thread gradient values of the running pass, [slot][thread] (adjoint kernel)
 //   gacc    : the launch's gradient sums of this CTA, flushed to the float64 accumulators once at the end
 struct PassCtx {
   float4* stage;
-  float* scratch;
   float* gacc;
   int buf;
   bool dbuf;  // two program buffers (adjoint kernel); the forward-only kernel keeps one, to fit three CTAs per SM
@@ -470,6 +473,7 @@ __device__ __forceinline__ PassView begin_pass(const KernelArgs& ka, PassCtx& cx
     const DevPass* gp = ka.passes + p;
     stage_program<false>(ka, cx.stage + cx.buf * kStageF4, p, __ldg(&gp->op_begin), __ldg(&gp->op_end),
                          __ldg(&gp->coef_begin), __ldg(&gp->coef_end));
+    if (ka.async_tile) __pipeline_wait_prior(0);  // cp.async tile loads of this thread (experiment switch)
   } else {
     __pipeline_wait_prior(0);
   }
@@ -526,27 +530,28 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
     }
   }
   const int ngrad = BOTH ? ps->ngrad : 0;
-  float* scratch = cx.scratch;
+  // Gradient scratch [slot][thread] = the psi and lambda tiles themselves, which are dead while every
+  // amplitude sits in registers (dedicated scratch was measured: it costs 16 KB of shared memory per CTA,
+  // which shrinks L1 to ~20 KB and turns the kernel's few register spills into L2 round trips).
+  float* scratch = reinterpret_cast<float*>(s_psi);
+  if (ngrad > 0) __syncthreads();  // every thread has read its amplitudes: the tiles become scratch
 
   float2 F = make_float2(1.f, 0.f);
   int oi = op_begin;
-  OpRec nxt;
-  if (oi < op_end) nxt = load_op(ops_base + oi);
   while (oi < op_end) {
-    const OpRec op = nxt;
+    const OpRec op = load_op(ops_base + oi);  // one LDS.128 from the staged program
     const float* cf = coef_base + op.coef;
     int step = 1;
-    if (op.type == OP_GD_BEGIN) step += op.aux0;
-    if (oi + step < op_end) nxt = load_op(ops_base + oi + step);  // prefetch the next descriptor
-    switch (op.type) {
+    if (op.type() == OP_GD_BEGIN) step += op.aux0;
+    switch (op.type()) {
       case OP_XROTM: {
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
-          if (op.p0 & (1 << P)) {
+          if (op.p0() & (1 << P)) {
             const float4 cs = ldg4(cf + 4 * P);  // (c, s, kappa, -)
             if constexpr (BOTH) {
               if (op.aux0 & (1 << P)) {
-                const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1;
+                const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1();
                 scratch[slot * nthr + tid] = cs.z * im_bxa<K, P>(a, b);
               }
             }
@@ -562,7 +567,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
           const float4 cs = ldg4(cf + 4 * P);  // identity at inactive positions
           if constexpr (BOTH) {
             if (op.aux0 & (1 << P)) {
-              const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1;
+              const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1();
               scratch[slot * nthr + tid] = cs.z * im_bxa<K, P>(a, b);
             }
           }
@@ -578,11 +583,11 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
       case OP_YROTM: {
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
-          if (op.p0 & (1 << P)) {
+          if (op.p0() & (1 << P)) {
             const float4 cs = ldg4(cf + 4 * P);
             if constexpr (BOTH) {
               if (op.aux0 & (1 << P)) {
-                const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1;
+                const int slot = P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1();
                 scratch[slot * nthr + tid] = cs.z * im_bya<K, P>(a, b);
               }
             }
@@ -593,14 +598,14 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
       } break;
       case OP_MAT1: {
         const float4 m0 = ldg4(cf), m1 = ldg4(cf + 4);
-        dispatch_pos<K>(op.p0, [&](auto pc) {
+        dispatch_pos<K>(op.p0(), [&](auto pc) {
           constexpr int P = decltype(pc)::value;
           mat1<K, P>(a, m0, m1);
           if constexpr (BOTH) mat1<K, P>(b, m0, m1);
         });
       } break;
       case OP_MAT2: {
-        if (op.p0 == 0) {
+        if (op.p0() == 0) {
           mat2<K, 0, false>(a, a, cf);
           if constexpr (BOTH) mat2<K, 0, false>(b, b, cf);
         } else {
@@ -651,7 +656,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
         const float2 e0 = make_float2(e.x, e.y), e1 = make_float2(e.z, e.w);
         const bool id0 = e.x == 1.f && e.y == 0.f, id1 = e.z == 1.f && e.w == 0.f;
         if (!(id0 && id1)) {
-          dispatch_pos<K>(op.p0, [&](auto pc) {
+          dispatch_pos<K>(op.p0(), [&](auto pc) {
             constexpr int P = decltype(pc)::value;
             mul_sel<K, P>(a, e0, e1, id0, id1);
             if constexpr (BOTH) mul_sel<K, P>(b, e0, e1, id0, id1);
@@ -660,16 +665,16 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
       } break;
       default:
         if constexpr (BOTH) {
-          if (op.type == OP_GRAD_MAT1) {
+          if (op.type() == OP_GRAD_MAT1) {
             const float4 m0 = ldg4(cf), m1 = ldg4(cf + 4);
             float v = 0.f;
-            dispatch_pos<K>(op.p0, [&](auto pc) { v = grad_mat1<K, decltype(pc)::value>(a, b, m0, m1); });
-            scratch[op.gslot * nthr + tid] = v;
-          } else if (op.type == OP_GRAD_MAT2) {
-            const float g = op.p0 == 0 ? mat2<K, 0, true>(a, b, cf) : mat2<K, 2, true>(a, b, cf);
-            scratch[op.gslot * nthr + tid] = g;
-          } else if (op.type == OP_GD_BEGIN) {
-            grad_diag_run<K>(a, b, ops_base + oi + 1, op.p0, op.p1, op.aux0, op.aux1 != 0, coef_base, scratch, gbase, tid, nthr);
+            dispatch_pos<K>(op.p0(), [&](auto pc) { v = grad_mat1<K, decltype(pc)::value>(a, b, m0, m1); });
+            scratch[op.gslot() * nthr + tid] = v;
+          } else if (op.type() == OP_GRAD_MAT2) {
+            const float g = op.p0() == 0 ? mat2<K, 0, true>(a, b, cf) : mat2<K, 2, true>(a, b, cf);
+            scratch[op.gslot() * nthr + tid] = g;
+          } else if (op.type() == OP_GD_BEGIN) {
+            grad_diag_run<K>(a, b, ops_base + oi + 1, op.p0(), op.p1(), op.aux0, op.aux1 != 0, coef_base, scratch, gbase, tid, nthr);
           }
         }
         break;
@@ -683,16 +688,38 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
     const int gs0 = ps->gsym_off;
     const bool in_smem = ka.L.gslot_count <= kGaccSlots;
     double* grow = ka.gacc + (size_t)(ka.per_state ? (ka.grow0 + (int)u) : 0) * ka.P;
-    for (int g = w; g < ngrad; g += nw) {
-      float sum = 0.f;
-      for (uint32_t i = lane; i < nthr; i += 32) sum += scratch[g * nthr + i];
-      sum = warp_sum(sum);
+    // two slots per warp at a time, two partial sums each: 4 independent load/add chains and two
+    // interleaved shuffle trees instead of one latency-bound chain per slot
+    for (int g0 = (int)w; g0 < ngrad; g0 += 2 * (int)nw) {
+      const int g1 = g0 + (int)nw;
+      const bool two = g1 < ngrad;
+      const float* r0 = scratch + (size_t)g0 * nthr;
+      const float* r1 = scratch + (size_t)(two ? g1 : g0) * nthr;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 4
+      for (uint32_t i = lane; i < nthr; i += 64) {
+        const bool hi = i + 32 < nthr;
+        acc0 += r0[i];
+        acc2 += r1[i];
+        if (hi) { acc1 += r0[i + 32]; acc3 += r1[i + 32]; }
+      }
+      float sum0 = acc0 + acc1, sum1 = acc2 + acc3;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, o);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, o);
+      }
       if (lane == 0) {
-        if (in_smem) cx.gacc[gs0 + g - ka.L.gslot_begin] = sum;  // each slot belongs to exactly one pass
-        else atomicAdd(grow + __ldg(&ka.gsym[gs0 + g]), (double)sum);
+        if (in_smem) {  // each slot belongs to exactly one pass
+          cx.gacc[gs0 + g0 - ka.L.gslot_begin] = sum0;
+          if (two) cx.gacc[gs0 + g1 - ka.L.gslot_begin] = sum1;
+        } else {
+          atomicAdd(grow + __ldg(&ka.gsym[gs0 + g0]), (double)sum0);
+          if (two) atomicAdd(grow + __ldg(&ka.gsym[gs0 + g1]), (double)sum1);
+        }
       }
     }
-    // no barrier here: the scratch is next written after the next pass's entry barrier
+    __syncthreads();  // the scratch is the tile: reductions must finish before amplitudes are stored back
   }
   {
     const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
@@ -717,25 +744,42 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
 // BOTH = true (adjoint kernel): h = H psi accumulates in the lambda tile (unscaled; the expectation phase
 // finishes E and lambda from it).  BOTH = false: E is accumulated directly.  Single observable only.
 // ---------------------------------------------------------------------------------
-template <int XR, bool BOTH>
+// MODE 0: per-amplitude coefficient table.  MODE 1: the table is uniform (e.g. a bare X or XX string: no
+// Z dressing inside the registers).  MODE 2: the table is zero where the flipped register bits have even
+// parity and uniform elsewhere (XX + YY with equal coefficients only connects |01> and |10>): half of the
+// amplitudes are skipped.  The host sets the mode (DevOp::aux1) from the table it built.
+template <int XR, bool BOTH, int MODE>
 __device__ __forceinline__ void hx_apply(const float2 (&a)[16], float2 (&b)[BOTH ? 16 : 1], const float* cf,
                                          const float sgn, float& e) {
   float2 acc = make_float2(0.f, 0.f);
+  if constexpr (MODE == 0) {
 #pragma unroll
-  for (int r0 = 0; r0 < 16; r0 += 4) {
-    const float4 t4 = ldg4(cf + r0);  // coefficients are read four at a time: no table in registers
-    const float tab[4] = {t4.x, t4.y, t4.z, t4.w};
+    for (int r0 = 0; r0 < 16; r0 += 4) {
+      const float4 t4 = ldg4(cf + r0);  // coefficients are read four at a time: no table in registers
+      const float tab[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + i, q = r ^ XR;
-      if constexpr (BOTH) {
-        b[r] = fma2(bc(sgn * tab[i]), a[q], b[r]);
-      } else {
-        acc = fma2(mul2(bc(tab[i]), a[r]), a[q], acc);
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + i, q = r ^ XR;
+        if constexpr (BOTH) {
+          b[r] = fma2(bc(sgn * tab[i]), a[q], b[r]);
+        } else {
+          acc = fma2(mul2(bc(tab[i]), a[r]), a[q], acc);
+        }
       }
     }
+    if constexpr (!BOTH) e = fmaf(sgn, hsum(acc), e);
+  } else {
+    constexpr int kFirst = MODE == 2 ? (XR & -XR) : 0;  // first entry of the table that carries the value
+    const float t = sgn * cf[kFirst];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (MODE == 2 && !(__builtin_popcount(r & XR) & 1)) continue;
+      const int q = r ^ XR;
+      if constexpr (BOTH) b[r] = fma2(bc(t), a[q], b[r]);
+      else acc = fma2(a[r], a[q], acc);
+    }
+    if constexpr (!BOTH) e = fmaf(t, hsum(acc), e);
   }
-  if constexpr (!BOTH) e = fmaf(sgn, hsum(acc), e);
 }
 
 // The pass works on 16 amplitudes at a time (register positions 0..3 carry the flips); with K = 5 the
@@ -786,19 +830,27 @@ __device__ __forceinline__ void run_hpass(const KernelArgs& ka, PassCtx& cx, con
       const OpRec op = load_op(ops_base + oi);
       const float* cf = coef_base + op.coef + 16 * half;
       const float sgn = (__popc(gbase & (uint32_t)op.aux0) & 1) ? -1.f : 1.f;
-      if (op.type == OP_HD) {
-        hx_apply<0, BOTH>(a, b, cf, sgn, e);
-      } else {
-        // register xor masks with one or two of the low four bits set
-        for_each_pos<4>([&](auto ph) {
-          constexpr int PH = decltype(ph)::value;
-          for_each_pos<4>([&](auto pl) {
-            constexpr int PL = decltype(pl)::value;
-            if constexpr (PL <= PH) {
-              if (op.p0 == ((1 << PH) | (1 << PL))) hx_apply<(1 << PH) | (1 << PL), BOTH>(a, b, cf, sgn, e);
-            }
-          });
-        });
+      const int mode = op.aux1;
+      auto apply = [&](auto xc) {
+        constexpr int XR = decltype(xc)::value;
+        if (mode == 1) hx_apply<XR, BOTH, 1>(a, b, cf, sgn, e);
+        else if (mode == 2 && XR != 0) hx_apply<XR, BOTH, (XR != 0 ? 2 : 0)>(a, b, cf, sgn, e);
+        else hx_apply<XR, BOTH, 0>(a, b, cf, sgn, e);
+      };
+      // register xor mask: 0 for diagonal strings (OP_HD), else one or two of the low four bits
+      switch (op.type() == OP_HD ? 0 : op.p0()) {
+        case 0: apply(IntC<0>{}); break;
+        case 1: apply(IntC<1>{}); break;
+        case 2: apply(IntC<2>{}); break;
+        case 3: apply(IntC<3>{}); break;
+        case 4: apply(IntC<4>{}); break;
+        case 5: apply(IntC<5>{}); break;
+        case 6: apply(IntC<6>{}); break;
+        case 8: apply(IntC<8>{}); break;
+        case 9: apply(IntC<9>{}); break;
+        case 10: apply(IntC<10>{}); break;
+        case 12: apply(IntC<12>{}); break;
+        default: break;
       }
     }
     if constexpr (BOTH) {
@@ -1123,6 +1175,16 @@ __device__ __forceinline__ void load_tile(float2* s, const float2* __restrict__ 
   const uint32_t tid = threadIdx.x;
   const uint32_t gt = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
   const uint32_t pt = swz(tid);
+  if (ka.async_tile) {
+    // Measured in profiles/r2_tile_copy_experiment.md: global -> shared without the register round trip,
+    // 8-byte cp.async per amplitude (the nibble-XOR swizzle permutes amplitudes inside 128-byte groups, so a
+    // larger copy unit -- 16-byte cp.async or a TMA box -- would land in the wrong order).  The copies
+    // complete at the first pass's program wait (cp.async.wait_all) + barrier.
+#pragma unroll
+    for (int m = 0; m < R; ++m) __pipeline_memcpy_async(s + (pt ^ ka.L.soff[m]), g + (gt | ka.L.moff[m]), 8);
+    __pipeline_commit();
+    return;
+  }
   float2 v[R];
 #pragma unroll
   for (int m = 0; m < R; ++m) v[m] = g[gt | ka.L.moff[m]];
@@ -1149,11 +1211,15 @@ template <int K, bool ADJ>
 constexpr int sweep_max_threads() { return ADJ ? (1 << (13 - K)) : 512; }
 
 // grid = chunk * 2^(n-T) CTAs, block = 2^(T-K) threads, dynamic smem = (ADJ ? 2 : 1) * 8 * 2^T bytes.
-template <int K, bool ADJ>
-__global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(const __grid_constant__ KernelArgs ka) {
+// DENSE (forward kernel, K = 4, <= 256 threads): compiled for three resident CTAs per SM with two program
+// buffers; it runs the forward sweeps of ADJOINT plans, which hold one 32 KiB psi tile each and would
+// otherwise occupy the SM with the two-CTA, 128-register adjoint kernel.
+template <int K, bool ADJ, bool DENSE = false>
+__global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DENSE ? 3 : 1)
+    sweep_kernel(const __grid_constant__ KernelArgs ka) {
+  static_assert(!(DENSE && ADJ), "the dense variant is forward-only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float4 s_stage[(ADJ ? 2 : 1) * kStageF4];
-  __shared__ float s_scratch[ADJ ? kScratchFloats : 1];
+  __shared__ float4 s_stage[((ADJ || DENSE) ? 2 : 1) * kStageF4];
   __shared__ float s_gacc[ADJ ? kGaccSlots : 1];
   float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float2* s_lam = s_psi + (ADJ ? (1u << ka.T) : 0u);
@@ -1169,10 +1235,9 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
   const float2 one = make_float2(1.f, 0.f);
   PassCtx cx;
   cx.stage = s_stage;
-  cx.scratch = s_scratch;
   cx.gacc = s_gacc;
   cx.buf = 0;
-  cx.dbuf = ADJ;
+  cx.dbuf = ADJ || DENSE;
   const bool flush_gacc = ADJ && ka.L.gslot_count > 0 && ka.L.gslot_count <= kGaccSlots;
   if constexpr (ADJ) {
     if (flush_gacc)
@@ -1201,6 +1266,8 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
     for (int p = ka.L.pass_a_begin; p < ka.L.pass_a_end; ++p)
       run_pass<K, false>(ka, cx, p, p == ka.L.pass_a_begin, p + 1 == ka.L.pass_a_end, s_psi, s_lam, goff, u);
   }
+  if (ka.async_tile) __pipeline_wait_prior(0);  // (experiment switch) tile copies that no pass has waited for
+  if constexpr (!DENSE) {  // (the dense forward variant only ever runs plain forward sweeps)
   if (flags & LF_WRITE_STATE) {
     __syncthreads();
     const float2 phase = ka.phase_coef >= 0 ? ldg2(ka.coef + ka.phase_coef) : one;
@@ -1218,6 +1285,7 @@ __global__ void __launch_bounds__(sweep_max_threads<K, ADJ>()) sweep_kernel(cons
         run_hpass<K, ADJ>(ka, cx, p, p == ka.L.pass_h_begin, p + 1 == ka.L.pass_h_end, s_psi, s_lam, goff, u);
     }
     expect_phase<K, ADJ>(ka, s_psi, s_lam, s_stage, goff, u, psi_u, hpasses);
+  }
   }
   if constexpr (ADJ) {
     for (int p = ka.L.pass_b_begin; p < ka.L.pass_b_end; ++p)

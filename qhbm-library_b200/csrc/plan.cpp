@@ -69,7 +69,8 @@ struct DiagRun {
   std::vector<std::vector<int32_t>> grp_list;
   std::vector<DevOp> pair_ops, cross_ops, gd_ops;
   bool any = false, any_const = false;
-  uint32_t bits = 0;  // state-index bits some pending diagonal gate acts on
+  uint32_t bits = 0;   // state-index bits some pending diagonal gate acts on
+  uint32_t vmask = 0;  // marginal vectors the run's gradient ops read (OP_GD_BEGIN)
 };
 
 DevOp make_op(int type) {
@@ -241,7 +242,9 @@ class Compiler {
     const int n = hp_.n_eff, K = hp_.K;
     std::vector<char> done(atoms.size(), 0);
     size_t remaining = atoms.size();
-    const int max_slots = std::min(4 * (1 << K), 255);  // gradient scratch = the two dead smem tiles
+    // Gradient scratch = the two dead smem tiles = 4 * 2^K units of one float per thread.  A rotation /
+    // matrix-block gradient takes one unit, every marginal vector of a diagonal run two (complex).
+    const int max_units = std::min(4 * (1 << K), 255);
     while (remaining > 0) {
       SweepOut sw;
       sw.tile_bits = choose_tile(atoms, done);
@@ -326,10 +329,36 @@ class Compiler {
         run.grp_list.assign((n + kConstGroupBits - 1) / kConstGroupBits, {});
         size_t executed = 0;
         Block blk(n);
+        units_ = 0;
+        tasks_bound_ = 0;
+        // marginal vectors the gradient of diagonal atom x reads (see OP_GD_BEGIN), 0 if it has no symbol
+        auto atom_vmask = [&](const Atom& x) -> uint32_t {
+          if (!backward || !x.diag) return 0u;
+          uint32_t m = 0;
+          for (int gi : x.gates) {
+            const qhbm_gate_t& g = hp_.gates[gi];
+            bool any = false;
+            for (int k = 0; k < g.nparams; ++k) any = any || g.sym[k] >= 0;
+            if (!any) continue;
+            const int pa = regpos[x.bit[0]], pb = x.nq == 2 ? regpos[x.bit[1]] : -1;
+            m |= 1u;
+            if (pa >= 0) m |= 2u << pa;
+            if (pb >= 0) m |= 2u << pb;
+            if (pa >= 0 && pb >= 0) {
+              const int ph = std::max(pa, pb), pl = std::min(pa, pb);
+              m |= 1u << (1 + K + ph * (ph - 1) / 2 + pl);
+            }
+          }
+          return m;
+        };
+        auto units_with = [&](uint32_t extra_vmask, int extra_float) {
+          return units_ + 2 * __builtin_popcount(run.vmask | extra_vmask) + extra_float;
+        };
         // A pass's program (op descriptors + coefficients) is staged in a fixed shared-memory buffer: the
         // pass is closed before the next atom could overflow it (headroom = the largest single atom, the
         // tables the pending diagonal run will emit when flushed, and the merged-rotation tables).
         int n_rot = 0;
+        const int stage_ops = backward ? kStageOpsAdj : kStageOps;
         auto fits = [&](const Atom& a) {
           int rops = 0, rcoef = 0;
           if (run.any) {
@@ -341,7 +370,8 @@ class Compiler {
           const int ng = (int)a.gates.size();
           const int ops_now = (int)hp_.ops.size() - ps.op_begin + rops;
           const int coef_now = hp_.ncoef - ps.coef_begin + rcoef + n_rot * (4 * K + 4);
-          return ops_now + 6 * ng + 4 <= kStageOps &&
+          // (a gradient pass also stages its reduction tasks: <= 1 per float slot, <= 3 + 1 per diagonal op)
+          return ops_now + 6 * ng + 4 + (backward ? tasks_bound_ + 4 * ng + 1 : 0) <= stage_ops &&
                  coef_now + 136 * ng + (2 << kConstGroupBits) + (4 << K) + (4 * K + 4) <= kStageCoef;
         };
         for (size_t ai = 0; ai < atoms.size(); ++ai) {
@@ -354,7 +384,8 @@ class Compiler {
           if (backward) {
             const qhbm_gate_t& g = hp_.gates[a.gates[0]];
             for (int k = 0; k < g.nparams; ++k) ngrads += g.sym[k] >= 0;
-            if (ps.ngrad + ngrads > max_slots) ok = false;
+            if (ps.ngrad + ngrads > 255) ok = false;
+            if (a.diag ? units_with(atom_vmask(a), 0) > max_units : units_with(0, ngrads) > max_units) ok = false;
           }
           if (ok && !a.diag) {
             for (int i = 0; i < a.nq; ++i) ok = ok && regpos[a.bit[i]] >= 0;
@@ -383,8 +414,11 @@ class Compiler {
                   const qhbm_gate_t& g = hp_.gates[x.gates[0]];
                   for (int k = 0; k < g.nparams; ++k) ng += g.sym[k] >= 0;
                 }
-                // (the block that closes the run, atom `a`, still needs its own `ngrads` slots)
-                if (ps.ngrad + ng + ngrads > max_slots || !fits(x)) { b2.block(x); continue; }
+                // (the block that closes the run, atom `a`, still needs its own `ngrads` units)
+                if (ps.ngrad + ng + ngrads > 255 || units_with(atom_vmask(x), ngrads) > max_units || !fits(x)) {
+                  b2.block(x);
+                  continue;
+                }
                 emit_diag(x, backward, regpos, ps, run);
                 done[aj] = 1;
                 --remaining;
@@ -404,9 +438,9 @@ class Compiler {
         merge_rotations(ps);
         ps.op_end = (int)hp_.ops.size();
         ps.coef_end = hp_.ncoef;
-        if (ps.op_end - ps.op_begin > kStageOps || ps.coef_end - ps.coef_begin > kStageCoef)
+        if (ps.op_end - ps.op_begin > stage_ops || ps.coef_end - ps.coef_begin > kStageCoef)
           throw std::runtime_error("internal: a pass program exceeds the staging buffer");
-        if (ps.ngrad > max_slots) throw std::runtime_error("internal: a pass has more gradient slots than scratch");
+        if (units_ > max_units) throw std::runtime_error("internal: a pass needs more gradient scratch than the tiles hold");
         hp_.passes.push_back(ps);
         executed_in_sweep += executed;
         if (!have_nondiag && remaining > 0) {
@@ -491,6 +525,8 @@ class Compiler {
       if (backward) {
         if (g.sym[0] >= 0) {  // gradient inner product fused into the un-rotation (gslot >= 0)
           o.gslot = ps.ngrad++;
+          ++units_;
+          ++tasks_bound_;
           hp_.gsym.push_back(g.sym[0]);
           add_job(PJ_KAPPA, o.coef + 2, 0, is_y ? 1 : 0, 0, 0, {gi});
         }
@@ -509,6 +545,8 @@ class Compiler {
           o.p0 = p;
           o.coef = alloc_coef(8);
           o.gslot = ps.ngrad++;
+          ++units_;
+          ++tasks_bound_;
           hp_.gsym.push_back(g.sym[k]);
           add_job(PJ_GRAD1, o.coef, 0, 0, k, 0, {gi});
           hp_.ops.push_back(o);
@@ -532,6 +570,8 @@ class Compiler {
           o.p0 = pair;
           o.coef = alloc_coef(32);
           o.gslot = ps.ngrad++;
+          ++units_;
+          ++tasks_bound_;
           hp_.gsym.push_back(g.sym[k]);
           add_job(PJ_GRAD2, o.coef, 0, swap, k, 0, {gi});
           hp_.ops.push_back(o);
@@ -580,6 +620,14 @@ class Compiler {
           o.gslot = ps.ngrad++;
           hp_.gsym.push_back(g.sym[k]);
           add_job(PJ_GDIAG, o.coef, 0, swap, k, 0, {gi});
+          tasks_bound_ += run.gd_ops.empty() ? 4 : 3;
+          run.vmask |= 1u;
+          if (reg_a) run.vmask |= 2u << pa;
+          if (reg_b) run.vmask |= 2u << pb;
+          if (reg_a && reg_b) {
+            const int ph = std::max(pa, pb), pl = std::min(pa, pb);
+            run.vmask |= 1u << (1 + hp_.K + ph * (ph - 1) / 2 + pl);
+          }
           run.gd_ops.push_back(o);
         }
       }
@@ -654,6 +702,7 @@ class Compiler {
       hp_.ops.push_back(make_op(OP_DAPPLY));
     }
     for (auto& o : run.cross_ops) hp_.ops.push_back(o);
+    units_ += 2 * __builtin_popcount(run.vmask);
     const size_t ng = run.grp_list.size();
     run = DiagRun();
     run.grp_list.assign(ng, {});
@@ -1149,7 +1198,240 @@ class Compiler {
   std::vector<std::vector<int>> stage_bits_;  // tile map of every expectation stage
   std::vector<StageRange> stage_ranges_;
   bool no_hpass_ = std::getenv("QHBM_NO_HPASS") != nullptr;  // development switch: generic tables only
+  int units_ = 0;        // gradient scratch units committed by the pass being scheduled (flushed runs + float slots)
+  int tasks_bound_ = 0;  // upper bound on the reduction tasks that pass will stage
 };
+
+}  // namespace
+
+
+// ---------------------------------------------------------------------------------
+// Device program.  The kernels execute `dev_passes` / `dev_ops`: the schedule above with the gradient
+// bookkeeping of a pass turned into (i) scratch UNITS (one float per thread each) that the per-thread
+// ops write, (ii) reduction TASKS staged behind the pass's ops, which sum those units over the CTA
+// (complex marginal vectors: also over the subset of threads whose index has given bits set), and
+// (iii) DESCRIPTORS, evaluated once per CTA at the end of a flush window, that combine the reduced sums
+// into one float64 atomic per gradient slot.  A diagonal gate therefore costs no per-thread work
+// beyond the run's shared marginal vectors: its 2 or 4 selected sums come from inclusion-exclusion
+// over the task results (DevGradDesc).
+// ---------------------------------------------------------------------------------
+namespace {
+
+struct BitRef {
+  int kind;  // 0: register position, 1: thread-index bit, 2: state-index bit outside the tile
+  int v;
+};
+struct Marg {
+  int vec;        // marginal vector: 0 = T, 1 + p = S[p], 1 + K + pi = SS[pi]
+  uint32_t mask;  // thread-index bits that must be set
+  int cond_a, cond_b;
+};
+
+void lower_device_program(HostPlan& hp) {
+  const int K = hp.K;
+  const int npass = (int)hp.passes.size();
+  std::vector<int> launch_of(npass, -1);
+  for (size_t li = 0; li < hp.launches.size(); ++li)
+    for (int p = hp.launches[li].pass_b_begin; p < hp.launches[li].pass_b_end; ++p) launch_of[p] = (int)li;
+  hp.dev_passes = hp.passes;
+  hp.dev_ops.clear();
+  hp.gdescs.clear();
+  std::vector<int> pass_floats(npass, 0);                 // reduced floats the pass's tasks produce
+  std::vector<std::pair<int, int>> pass_descs(npass, {0, 0});
+  for (int p = 0; p < npass; ++p) {
+    const DevPass& ps = hp.passes[p];
+    DevPass& dp = hp.dev_passes[p];
+    dp.op_begin = (int32_t)hp.dev_ops.size();
+    dp.gd_flush_begin = dp.gd_flush_end = 0;
+    pass_descs[p] = {(int)hp.gdescs.size(), (int)hp.gdescs.size()};
+    if (ps.ngrad <= 0 || launch_of[p] < 0) {
+      for (int i = ps.op_begin; i < ps.op_end; ++i) hp.dev_ops.push_back(pack_op(hp.ops[i]));
+      dp.exec_end = dp.op_end = (int32_t)hp.dev_ops.size();
+      continue;
+    }
+    const LaunchDesc& L = hp.launches[launch_of[p]];
+    std::vector<int> local_of(32, -1);
+    for (int r = 0; r < L.n_runs; ++r)
+      for (int i = 0; i < L.runs[r].len; ++i) local_of[L.runs[r].global_start + i] = L.runs[r].local_start + i;
+    uint32_t regmask = 0;
+    for (int j = 0; j < K; ++j) regmask |= 1u << ps.regbit[j];
+    auto ref_of = [&](int state_bit) -> BitRef {
+      const int l = local_of[state_bit];
+      if (l < 0) return {2, state_bit};
+      if ((regmask >> l) & 1) throw std::runtime_error("internal: a thread-constant bit is a register bit");
+      return {1, l - __builtin_popcount(regmask & ((1u << l) - 1u))};
+    };
+    auto marg1 = [&](const BitRef& a) -> Marg {
+      if (a.kind == 0) return {1 + a.v, 0u, -1, -1};
+      if (a.kind == 1) return {0, 1u << a.v, -1, -1};
+      return {0, 0u, a.v, -1};
+    };
+    auto marg2 = [&](const BitRef& a, const BitRef& b) -> Marg {
+      Marg m{0, 0u, -1, -1};
+      if (a.kind == 0 && b.kind == 0) {
+        const int ph = std::max(a.v, b.v), pl = std::min(a.v, b.v);
+        m.vec = 1 + K + ph * (ph - 1) / 2 + pl;
+      } else if (a.kind == 0) m.vec = 1 + a.v;
+      else if (b.kind == 0) m.vec = 1 + b.v;
+      if (a.kind == 1) m.mask |= 1u << a.v;
+      if (b.kind == 1) m.mask |= 1u << b.v;
+      if (a.kind == 2) m.cond_a = a.v;
+      if (b.kind == 2) m.cond_b = b.v;
+      return m;
+    };
+    int units = 0, floats = 0;
+    std::vector<PackedOp> tasks;
+    auto float_task = [&](int sym) {  // one float per thread in the next unit -> gacc[floats]
+      const int unit = units++;
+      DevOp t = make_op(OP_TASK_F);
+      t.p0 = unit;
+      t.coef = floats;
+      t.aux0 = t.aux1 = 0;
+      tasks.push_back(pack_op(t));
+      DevGradDesc d;
+      std::memset(&d, 0, sizeof(d));
+      d.kind = 0;
+      d.sym = sym;
+      d.coef = -1;
+      d.i_tot = (int16_t)floats;
+      d.i_a = d.i_b = d.i_ab = 0;
+      d.cond_a = d.cond_b = -1;
+      hp.gdescs.push_back(d);
+      floats += 1;
+      return unit;
+    };
+    for (int i = ps.op_begin; i < ps.op_end; ++i) {
+      DevOp o = hp.ops[i];
+      switch (o.type) {
+        case OP_XROTM: case OP_YROTM: case OP_XROTF: {
+          int aux1 = 0, p1 = o.p1;
+          for (int P = 0; P < K; ++P) {
+            if (!(o.aux0 & (1 << P))) continue;
+            const int slot = P < 4 ? ((o.aux1 >> (8 * P)) & 0xff) : o.p1;
+            const int unit = float_task(hp.gsym[ps.gsym_off + slot]);
+            if (P < 4) aux1 |= unit << (8 * P);
+            else p1 = unit;
+          }
+          if (o.aux0) { o.aux1 = aux1; o.p1 = p1; }
+          hp.dev_ops.push_back(pack_op(o));
+        } break;
+        case OP_XROT: case OP_YROT: case OP_GRAD_X: case OP_GRAD_Y:
+          throw std::runtime_error("internal: unmerged rotation op in a device program");
+        case OP_GRAD_MAT1: case OP_GRAD_MAT2:
+          o.gslot = float_task(hp.gsym[ps.gsym_off + o.gslot]);
+          hp.dev_ops.push_back(pack_op(o));
+          break;
+        case OP_GD_BEGIN: {
+          const int count = o.aux0;
+          uint32_t vmask = 1u;
+          std::vector<std::pair<int, std::pair<BitRef, BitRef>>> gates;  // (kind, (A, B))
+          for (int q = 1; q <= count; ++q) {
+            const DevOp& g = hp.ops[i + q];
+            BitRef a{0, 0}, b{0, 0};
+            int kind = 2;
+            switch (g.type) {
+              case OP_GD_CONST:
+                a = ref_of(g.aux0);
+                if (g.aux1 >= 0) b = ref_of(g.aux1); else kind = 1;
+                break;
+              case OP_GD_REG1: a = {0, g.p0}; kind = 1; break;
+              case OP_GD_REG2: a = {0, g.p0}; b = {0, g.p1}; break;
+              case OP_GD_MIX: a = ref_of(g.aux0); b = {0, g.p0}; break;
+              default: throw std::runtime_error("internal: malformed diagonal-gradient run");
+            }
+            gates.push_back({kind, {a, b}});
+            vmask |= 1u << marg1(a).vec;
+            if (kind == 2) { vmask |= 1u << marg1(b).vec; vmask |= 1u << marg2(a, b).vec; }
+          }
+          const int unit0 = units;
+          units += 2 * __builtin_popcount(vmask);
+          std::vector<std::pair<std::pair<int, uint32_t>, int>> seen;  // (vector, mask) -> gacc offset
+          auto task_of = [&](const Marg& m) {
+            for (const auto& s : seen) if (s.first.first == m.vec && s.first.second == m.mask) return s.second;
+            DevOp t = make_op(OP_TASK_C);
+            t.p0 = unit0 + 2 * __builtin_popcount(vmask & ((1u << m.vec) - 1u));
+            t.coef = floats;
+            t.aux0 = (int32_t)m.mask;
+            t.aux1 = 0;
+            tasks.push_back(pack_op(t));
+            seen.push_back({{m.vec, m.mask}, floats});
+            floats += 2;
+            return floats - 2;
+          };
+          for (int q = 1; q <= count; ++q) {
+            const DevOp& g = hp.ops[i + q];
+            const auto& gt = gates[q - 1];
+            DevGradDesc d;
+            std::memset(&d, 0, sizeof(d));
+            d.kind = gt.first;
+            d.sym = hp.gsym[ps.gsym_off + g.gslot];
+            d.coef = g.coef;
+            d.i_tot = (int16_t)task_of(Marg{0, 0u, -1, -1});
+            const Marg ma = marg1(gt.second.first);
+            d.i_a = (int16_t)task_of(ma);
+            d.cond_a = (int8_t)ma.cond_a;
+            d.cond_b = -1;
+            if (gt.first == 2) {
+              const Marg mb = marg1(gt.second.second);
+              const Marg mab = marg2(gt.second.first, gt.second.second);
+              d.i_b = (int16_t)task_of(mb);
+              d.i_ab = (int16_t)task_of(mab);
+              d.cond_b = (int8_t)mb.cond_a;
+            }
+            hp.gdescs.push_back(d);
+          }
+          o.coef = (int32_t)vmask;
+          o.gslot = unit0;
+          hp.dev_ops.push_back(pack_op(o));
+          for (int q = 1; q <= count; ++q) hp.dev_ops.push_back(pack_op(hp.ops[i + q]));  // skipped by the kernel
+          i += count;
+        } break;
+        default:
+          hp.dev_ops.push_back(pack_op(o));
+          break;
+      }
+    }
+    if (units > std::min(4 * (1 << K), 255))
+      throw std::runtime_error("internal: a pass needs more gradient scratch than the tiles hold");
+    dp.exec_end = (int32_t)hp.dev_ops.size();
+    hp.dev_ops.insert(hp.dev_ops.end(), tasks.begin(), tasks.end());
+    dp.op_end = (int32_t)hp.dev_ops.size();
+    if (dp.op_end - dp.op_begin > kStageOpsAdj)
+      throw std::runtime_error("internal: a gradient pass program exceeds the staging buffer");
+    if (floats > kGaccFloats) throw std::runtime_error("internal: a pass reduces more sums than the flush window holds");
+    pass_floats[p] = floats;
+    pass_descs[p].second = (int)hp.gdescs.size();
+  }
+  for (int p = 0; p < npass; ++p) {
+    const bool has_next = p + 1 < npass;
+    hp.dev_passes[p].next_op_end = has_next ? hp.dev_passes[p + 1].op_end : hp.dev_passes[p].op_end;
+  }
+  // Flush windows: consecutive gradient passes of a launch share the shared-memory sums until they would
+  // overflow; the last pass of a window evaluates the window's descriptors.
+  for (const LaunchDesc& L : hp.launches) {
+    int p = L.pass_b_begin;
+    while (p < L.pass_b_end) {
+      int e = p, used = 0;
+      while (e < L.pass_b_end && used + pass_floats[e] <= kGaccFloats) {
+        // rebase pass e's task outputs and descriptor indices into the window
+        DevPass& dp = hp.dev_passes[e];
+        for (int t = dp.exec_end; t < dp.op_end; ++t) hp.dev_ops[t].coef += used;
+        for (int d = pass_descs[e].first; d < pass_descs[e].second; ++d) {
+          DevGradDesc& g = hp.gdescs[d];
+          g.i_tot = (int16_t)(g.i_tot + used);
+          if (g.kind >= 1) g.i_a = (int16_t)(g.i_a + used);
+          if (g.kind == 2) { g.i_b = (int16_t)(g.i_b + used); g.i_ab = (int16_t)(g.i_ab + used); }
+        }
+        used += pass_floats[e];
+        ++e;
+      }
+      DevPass& last = hp.dev_passes[e - 1];
+      last.gd_flush_begin = pass_descs[p].first;
+      last.gd_flush_end = pass_descs[e - 1].second;
+      p = e;
+    }
+  }
+}
 
 }  // namespace
 
@@ -1205,6 +1487,7 @@ HostPlan compile_plan(const CircuitIR& c, const OpsIR& o, bool with_gradient, in
       L.gslot_count = last.gsym_off + std::max(last.ngrad, 0) - first.gsym_off;
     }
   }
+  lower_device_program(hp);
   return hp;
 }
 

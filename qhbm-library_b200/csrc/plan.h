@@ -49,6 +49,13 @@ struct HostPlan {
   std::vector<DevOpRange> opranges;
   std::vector<DevDiagTerm> dterms;        // diagonal terms routed through the WHT path (may be empty)
 
+  // Device program (lower_device_program): the passes / ops the kernels execute.  Same schedule as
+  // `passes` / `ops`; gradient passes additionally carry their reduction tasks, scratch-unit numbers
+  // instead of gradient slots, and the flush windows of the gradient descriptors.
+  std::vector<DevPass> dev_passes;
+  std::vector<PackedOp> dev_ops;
+  std::vector<DevGradDesc> gdescs;
+
   int tiles() const { return 1 << (n_eff - T); }
 };
 

@@ -23,7 +23,8 @@ constexpr int kConstGroupBits = 7;  // width of one "thread-constant" phase tabl
 constexpr int kMaxRuns = 16;
 constexpr int kStageOps = 192;     // ops of one pass: the compiler closes a pass before its program exceeds the
 constexpr int kStageCoef = 1792;   // shared-memory staging buffer (op descriptors / coefficient floats)
-constexpr int kGaccSlots = 512;       // gradient slots of one launch accumulated in shared memory
+constexpr int kStageOpsAdj = 256;  // the same for a gradient pass of the adjoint kernel (ops + reduction tasks)
+constexpr int kGaccFloats = 1024;  // reduced gradient sums (one flush window) kept in shared memory
 
 enum OpType : int32_t {
   OP_NOP = 0,
@@ -53,7 +54,10 @@ enum OpType : int32_t {
   OP_GRAD_Y,      // kappa * Im <lam| Y_p0 |psi>; coef -> kappa
   OP_GD_BEGIN,    // starts a run of aux0 diagonal-gradient ops (they share conj(lam)*psi), sorted by kind:
                   //     p0 OP_GD_CONST, then p1 OP_GD_REG1 / OP_GD_MIX, then the OP_GD_REG2;
-                  //     aux1 != 0: pair marginals are needed (some OP_GD_REG2 in the run)
+                  //     aux1 != 0: pair marginals are needed (some OP_GD_REG2 in the run).
+                  //     Device form (lower_device_program): coef = mask of the marginal vectors the run needs
+                  //     (bit 0: T, bit 1 + p: S[p], bit 1 + K + pi: SS[pi]); gslot = first scratch unit.  The
+                  //     thread stores those vectors and skips the aux0 descriptors, which only the host reads
   OP_GD_CONST,    // entries M[sel] at coef (complex); sel = 2*bit(aux0)+bit(aux1) (aux1<0: bit(aux0))
   OP_GD_REG1,     // sel = register bit p0; coef -> 2 complex
   OP_GD_REG2,     // sel = 2*regbit(p0) + regbit(p1); coef -> 4 complex
@@ -63,6 +67,10 @@ enum OpType : int32_t {
   OP_HX,          // h[r] += s * tab[r] * psi[r ^ p0]: p0 = register xor mask with one or two bits set,
                   //     coef -> 2^K real coefficients, s = (-1)^{parity(gbase & aux0)} (aux0 = 0: +1)
   OP_HD,          // h[r] += s * tab[r] * psi[r]  (diagonal terms), same fields
+  // reduction tasks of a gradient pass (device program only; they follow the pass's executed ops)
+  OP_TASK_F,      // gacc[coef] = sum over the CTA's threads of the float vector in scratch unit p0
+  OP_TASK_C,      // gacc[coef], gacc[coef + 1] = sum over the threads with (tid & aux0) == aux0 of the complex
+                  //     vector in scratch units p0, p0 + 1
 };
 
 struct DevOp {  // 32 bytes
@@ -90,7 +98,27 @@ inline PackedOp pack_op(const DevOp& o) {
   return q;
 }
 
-struct DevPass {  // 144 bytes
+// One gradient value of a flush window: how to combine reduced sums into d<H>/d(symbol).
+//   kind 0: the float sum gacc[i_tot] (rotation / matrix-block gradients are complete per thread)
+//   kind 1: one-qubit diagonal gate, M = diag(m0, m1) at coef: U1 = A, U0 = tot - A
+//   kind 2: two-qubit diagonal gate, M entries indexed 2 * bitA + bitB: U11 = AB, U10 = A - AB,
+//           U01 = B - AB, U00 = tot - A - B + AB
+// tot / A / B / AB are complex sums (u, -v) of w = conj(lam) psi = u + i v at gacc[i_*], taken over the
+// tile (tot), over the amplitudes with bit A set, with bit B set, with both set.  A bit outside the tile
+// is a condition on the CTA's tile offset instead (cond_*: state-index bit, -1: none): the marginal is
+// the sum named by the index if the bit is set in goff and zero otherwise.
+// value = 2 sum_sel (Re m_sel * U_sel.x + Im m_sel * U_sel.y)
+struct DevGradDesc {  // 32 bytes
+  int32_t kind;
+  int32_t sym;
+  int32_t coef;
+  int16_t i_tot, i_a, i_b, i_ab;
+  int8_t cond_a, cond_b;
+  int8_t pad0[2];
+  int32_t pad1[2];
+};
+
+struct DevPass {  // 160 bytes
   int32_t regbit[kMaxRegQubits];     // tile-local bit of register position j
   int32_t sorted[kMaxRegQubits];     // the same bits in ascending order
   int32_t op_begin, op_end;
@@ -99,7 +127,11 @@ struct DevPass {  // 144 bytes
   int32_t coef_begin, coef_end;      // float range of the coefficient buffer this pass reads
   uint16_t eoff[1 << kMaxRegQubits]; // swizzled smem offset of register amplitude r (XOR with the thread base)
   int32_t next_op_end, next_coef_end;  // ends of the NEXT pass's ranges (they start where this pass's end):
-  int32_t pad[2];                      // what the kernel needs to prefetch that program while this pass runs
+                                       // what the kernel needs to prefetch that program while this pass runs
+  // device program only (HostPlan::dev_passes):
+  int32_t exec_end;                    // ops [op_begin, exec_end) run per thread, [exec_end, op_end) are tasks
+  int32_t gd_flush_begin, gd_flush_end;  // gradient descriptors evaluated (and added to the float64
+  int32_t pad[3];                        // accumulators) after this pass: the end of a flush window
 };
 
 // Contiguous run of tile-local bits mapped to contiguous state-index bits.
@@ -130,7 +162,7 @@ struct LaunchDesc {
   uint32_t tile_mask;                // state-index bits covered by the tile
   int32_t pass_h_begin, pass_h_end;  // observable passes run at the start of the expectation phase
   int32_t expect_stage;              // LF_EXPECT: which stage's tables this launch uses
-  int32_t gslot_begin, gslot_count;  // gradient slots (indices into gsym) of all passes of this launch
+  int32_t gslot_begin, gslot_count;  // gradient slots (indices into gsym) of all passes of this launch (host view)
   int32_t rng_begin, rng_end;        // its slice of the observable ranges (DevOpRange)
   int32_t grp_begin, grp_end;        // that stage's slice of the group / term tables (staged in shared memory)
   int32_t term_begin, term_end;

@@ -51,7 +51,7 @@ struct qhbm_plan {
   HostPlan hp;
   DevBuf<DevPass> d_passes;
   DevBuf<PackedOp> d_ops;
-  DevBuf<int32_t> d_gsym;
+  DevBuf<DevGradDesc> d_gdescs;
   DevBuf<PrepJob> d_jobs;
   DevBuf<int32_t> d_lists;
   DevBuf<qhbm_gate_t> d_gates;
@@ -175,7 +175,7 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
   ka.passes = p->d_passes.p;
   ka.ops = p->d_ops.p;
   ka.coef = p->d_coef.p;
-  ka.gsym = p->d_gsym.p;
+  ka.gdescs = p->d_gdescs.p;
   ka.terms = p->d_terms.p;
   ka.groups = p->d_groups.p;
   ka.opranges = p->d_opranges.p;
@@ -385,13 +385,9 @@ int qhbm_plan_create(const qhbm_circuit_t* c, const qhbm_ops_t* o, int32_t with_
     try {
       p->hp = compile_plan(c->ir, o->ir, with_gradient != 0, tile_qubits, reg_qubits);
       const HostPlan& hp = p->hp;
-      p->d_passes.upload(hp.passes);
-      {
-        std::vector<PackedOp> packed(hp.ops.size());
-        for (size_t i = 0; i < hp.ops.size(); ++i) packed[i] = pack_op(hp.ops[i]);
-        p->d_ops.upload(packed);
-      }
-      p->d_gsym.upload(hp.gsym);
+      p->d_passes.upload(hp.dev_passes);
+      p->d_ops.upload(hp.dev_ops);
+      p->d_gdescs.upload(hp.gdescs);
       p->d_jobs.upload(hp.jobs);
       p->d_lists.upload(hp.lists);
       p->d_gates.upload(hp.gates);

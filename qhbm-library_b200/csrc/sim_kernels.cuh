@@ -25,7 +25,7 @@ struct KernelArgs {
   const DevPass* passes;
   const PackedOp* ops;
   const float* coef;
-  const int32_t* gsym;
+  const DevGradDesc* gdescs;  // gradient descriptors (flush windows of the gradient passes)
   const DevTerm* terms;
   const DevTermGroup* groups;
   const DevOpRange* opranges;
@@ -368,51 +368,34 @@ __device__ __forceinline__ float2 pick2(const float2 (&v)[N], int i) {
   return r;
 }
 
-// Gradient of every diagonal gate of a run.  A diagonal gate with M = dG G^dagger = diag(m_sel)
-// contributes 2 Re sum_r m_sel(r) w_r = 2 sum_sel (Re m_sel U_sel - Im m_sel V_sel), U_sel + i V_sel the
-// sum of w over the amplitudes that select entry sel.
+// Diagonal-gate gradients of a run.  A diagonal gate with M = dG G^dagger = diag(m_sel) contributes
+// 2 Re sum_i m_sel(i) w_i, i.e. it only needs the sums of w over the amplitudes that select each entry.
+// The thread stores the marginal vectors the run's gates read (`vmask`: bit 0 T, bit 1 + p S[p], bit
+// 1 + K + pi SS[pi]; complex, two scratch units each, in mask order from unit `unit0`); the pass's
+// reduction tasks sum them over the CTA -- for gates on thread-index bits over the threads that have
+// the bit set -- and the flush combines the sums per gate (DevGradDesc).  No per-gate work per thread.
 template <int K>
-__device__ __forceinline__ void grad_diag_run(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
-                                              const PackedOp* __restrict__ ops, const int n_const, const int n_reg1,
-                                              const int count, const bool pairs, const float* __restrict__ coef,
-                                              float* scratch, uint32_t gbase, uint32_t tid, uint32_t nthr) {
+__device__ __forceinline__ void store_marginals(const float2 (&a)[1 << K], const float2 (&b)[1 << K],
+                                                const uint32_t vmask, const int unit0, float* scratch,
+                                                const uint32_t tid, const uint32_t nthr) {
   Marginals<K> mg;
-  compute_marginals<K>(a, b, mg, pairs);
-  const float2 T = mg.T;
-  int i = 0;
-  // gates whose qubits are all thread-constant: one selected entry times the thread totals
-  for (; i < n_const; ++i) {
-    const OpRec op = load_op(ops + i);  // shared memory: no prefetch needed
-    int sel = (gbase >> op.aux0) & 1;
-    if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1);
-    const float2 m = ldg2(coef + op.coef + 2 * sel);
-    scratch[op.gslot() * nthr + tid] = 2.f * hsum(mul2(m, T));
+  compute_marginals<K>(a, b, mg, (vmask >> (1 + K)) != 0u);
+  float2* v = reinterpret_cast<float2*>(scratch + (size_t)unit0 * nthr) + tid;
+  *v = mg.T;
+  v += nthr;
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    if ((vmask >> (1 + p)) & 1u) {
+      *v = mg.S[p];
+      v += nthr;
+    }
   }
-  // one register bit (plus, for OP_GD_MIX, one thread-constant bit)
-  for (; i < n_const + n_reg1; ++i) {
-    const OpRec op = load_op(ops + i);  // shared memory: no prefetch needed
-    const int cb = op.type() == OP_GD_MIX ? ((gbase >> op.aux0) & 1) : 0;
-    const float2 S1 = pick2<K>(mg.S, op.p0());
-    const float4 m = ldg4(coef + op.coef + 4 * cb);
-    const float2 D = add2(T, make_float2(-S1.x, -S1.y));
-    const float2 v = fma2(make_float2(m.z, m.w), S1, mul2(make_float2(m.x, m.y), D));
-    scratch[op.gslot() * nthr + tid] = 2.f * hsum(v);
-  }
-  // two register bits, p0 > p1
-  for (; i < count; ++i) {
-    const OpRec op = load_op(ops + i);  // shared memory: no prefetch needed
-    const float* e = coef + op.coef;
-    const float2 Sh = pick2<K>(mg.S, op.p0()), Sl = pick2<K>(mg.S, op.p1());
-    const float2 S11 = pick2<Marginals<K>::NP>(mg.SS, op.p0() * (op.p0() - 1) / 2 + op.p1());
-    const float4 m01 = ldg4(e), m23 = ldg4(e + 4);
-    const float2 n11 = make_float2(-S11.x, -S11.y);
-    const float2 Slo = add2(Sl, n11), Shi = add2(Sh, n11);                 // lo bit only / hi bit only
-    const float2 S00 = add2(add2(T, make_float2(-Sh.x, -Sh.y)), make_float2(-Slo.x, -Slo.y));
-    float2 v = mul2(make_float2(m01.x, m01.y), S00);
-    v = fma2(make_float2(m01.z, m01.w), Slo, v);
-    v = fma2(make_float2(m23.x, m23.y), Shi, v);
-    v = fma2(make_float2(m23.z, m23.w), S11, v);
-    scratch[op.gslot() * nthr + tid] = 2.f * hsum(v);
+#pragma unroll
+  for (int pi = 0; pi < Marginals<K>::NP; ++pi) {
+    if ((vmask >> (1 + K + pi)) & 1u) {
+      *v = mg.SS[pi];
+      v += nthr;
+    }
   }
 }
 
@@ -429,22 +412,24 @@ struct PassCtx {
   float4* stage;
   float* gacc;
   int buf;
-  bool dbuf;  // two program buffers (adjoint kernel); the forward-only kernel keeps one, to fit three CTAs per SM
+  bool dbuf;    // two program buffers (adjoint kernel); the forward-only kernel keeps one, to fit three CTAs per SM
+  int ops_cap;  // op descriptors per buffer: kStageOpsAdj in the adjoint kernel (ops + reduction tasks), else kStageOps
+  __device__ __forceinline__ int stride() const { return stage_f4(ops_cap); }
+  __host__ __device__ static constexpr int stage_f4(int cap) { return (int)(sizeof(DevPass) / 16) + cap + kStageCoef / 4; }
 };
 constexpr int kPassF4 = (int)(sizeof(DevPass) / 16);
-constexpr int kStageF4 = kPassF4 + kStageOps + kStageCoef / 4;  // float4 per program buffer
 static_assert(sizeof(DevPass) % 16 == 0, "DevPass is copied in 16-byte pieces");
 
 // Copies pass p's program into stage buffer `buf`.  ASYNC: cp.async, completed by stage_wait().
 template <bool ASYNC>
-__device__ __forceinline__ void stage_program(const KernelArgs& ka, float4* buf, const int p, const int op_begin,
-                                              const int op_end, const int cb, const int ce) {
+__device__ __forceinline__ void stage_program(const KernelArgs& ka, float4* buf, const int ops_cap, const int p,
+                                              const int op_begin, const int op_end, const int cb, const int ce) {
   const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
   const float4* g_ps = reinterpret_cast<const float4*>(ka.passes + p);
   const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
   const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);  // coefficient slots are 16-byte aligned
   float4* s_ops = buf + kPassF4;
-  float4* s_cf = buf + kPassF4 + kStageOps;
+  float4* s_cf = buf + kPassF4 + ops_cap;
   const int n_ops = op_end - op_begin, n_cf = (ce - cb + 3) / 4;
   if constexpr (ASYNC) {
     if (tid < kPassF4) __pipeline_memcpy_async(buf + tid, g_ps + tid, 16);
@@ -464,32 +449,34 @@ struct PassView {
   const DevPass* ps;      // in shared memory
   const PackedOp* ops;    // indexed by absolute op number
   const float* coef;      // indexed by absolute float offset
-  int op_begin, op_end;
+  int op_begin, op_end;   // op_end = end of the per-thread ops (DevPass::exec_end); tasks follow up to task_end
+  int task_end;
 };
 __device__ __forceinline__ PassView begin_pass(const KernelArgs& ka, PassCtx& cx, const int p, const bool first,
                                                const bool last) {
   if (first || !cx.dbuf) {
     __syncthreads();  // the previous phase is done with the tiles and the stage buffers
     const DevPass* gp = ka.passes + p;
-    stage_program<false>(ka, cx.stage + cx.buf * kStageF4, p, __ldg(&gp->op_begin), __ldg(&gp->op_end),
+    stage_program<false>(ka, cx.stage + cx.buf * cx.stride(), cx.ops_cap, p, __ldg(&gp->op_begin), __ldg(&gp->op_end),
                          __ldg(&gp->coef_begin), __ldg(&gp->coef_end));
     if (ka.async_tile) __pipeline_wait_prior(0);  // cp.async tile loads of this thread (experiment switch)
   } else {
     __pipeline_wait_prior(0);
   }
   __syncthreads();  // program visible; the previous pass's tile stores and gradient reduction are complete
-  float4* buf = cx.stage + cx.buf * kStageF4;
+  float4* buf = cx.stage + cx.buf * cx.stride();
   PassView v;
   v.ps = reinterpret_cast<const DevPass*>(buf);
   v.op_begin = v.ps->op_begin;
-  v.op_end = v.ps->op_end;
+  v.op_end = v.ps->exec_end;
+  v.task_end = v.ps->op_end;
   const int cb = v.ps->coef_begin;
   v.ops = reinterpret_cast<const PackedOp*>(buf + kPassF4) - v.op_begin;
-  v.coef = reinterpret_cast<const float*>(buf + kPassF4 + kStageOps) - cb;
+  v.coef = reinterpret_cast<const float*>(buf + kPassF4 + cx.ops_cap) - cb;
   if (cx.dbuf) {
     if (!last)  // passes of a range are consecutive: the next program starts where this one ends
-      stage_program<true>(ka, cx.stage + (cx.buf ^ 1) * kStageF4, p + 1, v.op_end, v.ps->next_op_end, v.ps->coef_end,
-                          v.ps->next_coef_end);
+      stage_program<true>(ka, cx.stage + (cx.buf ^ 1) * cx.stride(), cx.ops_cap, p + 1, v.task_end, v.ps->next_op_end,
+                          v.ps->coef_end, v.ps->next_coef_end);
     cx.buf ^= 1;
   }
   return v;
@@ -674,7 +661,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
             const float g = op.p0() == 0 ? mat2<K, 0, true>(a, b, cf) : mat2<K, 2, true>(a, b, cf);
             scratch[op.gslot() * nthr + tid] = g;
           } else if (op.type() == OP_GD_BEGIN) {
-            grad_diag_run<K>(a, b, ops_base + oi + 1, op.p0(), op.p1(), op.aux0, op.aux1 != 0, coef_base, scratch, gbase, tid, nthr);
+            store_marginals<K>(a, b, (uint32_t)op.coef, op.gslot(), scratch, tid, nthr);
           }
         }
         break;
@@ -682,44 +669,97 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
     oi += step;
   }
 
+  bool flush = false;
+  if constexpr (BOTH) flush = ps->gd_flush_end > ps->gd_flush_begin;
   if (ngrad > 0) {
     __syncthreads();  // every thread's gradient values of this pass are in the scratch
+    // Reduction tasks, two per warp at a time (independent load/add chains and interleaved shuffle trees).
     const uint32_t w = tid >> 5, lane = tid & 31, nw = nthr >> 5;
-    const int gs0 = ps->gsym_off;
-    const bool in_smem = ka.L.gslot_count <= kGaccSlots;
-    double* grow = ka.gacc + (size_t)(ka.per_state ? (ka.grow0 + (int)u) : 0) * ka.P;
-    // two slots per warp at a time, two partial sums each: 4 independent load/add chains and two
-    // interleaved shuffle trees instead of one latency-bound chain per slot
-    for (int g0 = (int)w; g0 < ngrad; g0 += 2 * (int)nw) {
-      const int g1 = g0 + (int)nw;
-      const bool two = g1 < ngrad;
-      const float* r0 = scratch + (size_t)g0 * nthr;
-      const float* r1 = scratch + (size_t)(two ? g1 : g0) * nthr;
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    auto partial = [&](const OpRec& t) -> float2 {  // this lane's share of task t
+      const float* src = scratch + (size_t)t.p0() * nthr;
+      if (t.type() == OP_TASK_F) {
+        float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 4
-      for (uint32_t i = lane; i < nthr; i += 64) {
-        const bool hi = i + 32 < nthr;
-        acc0 += r0[i];
-        acc2 += r1[i];
-        if (hi) { acc1 += r0[i + 32]; acc3 += r1[i + 32]; }
+        for (uint32_t i = lane; i < nthr; i += 64) {
+          acc0 += src[i];
+          if (i + 32 < nthr) acc1 += src[i + 32];
+        }
+        return make_float2(acc0 + acc1, 0.f);
       }
-      float sum0 = acc0 + acc1, sum1 = acc2 + acc3;
+      // complex vector, restricted to the threads whose index has every bit of the mask set: blocks of
+      // 32 threads are skipped as a whole, the lane bits of the mask zero this lane's share at the end
+      const float2* v = reinterpret_cast<const float2*>(src) + lane;
+      const uint32_t m = (uint32_t)t.aux0, mh = m & ~31u;
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll 4
+      for (uint32_t i0 = 0; i0 < nthr; i0 += 64) {
+        if ((i0 & mh) == mh) acc0 = add2(acc0, v[i0]);
+        if (i0 + 32 < nthr && ((i0 + 32) & mh) == mh) acc1 = add2(acc1, v[i0 + 32]);
+      }
+      const float2 acc = add2(acc0, acc1);
+      return ((lane & m) == (m & 31u)) ? acc : make_float2(0.f, 0.f);
+    };
+    for (int t0 = op_end + (int)w; t0 < pv.task_end; t0 += 2 * (int)nw) {
+      const int t1 = t0 + (int)nw;
+      const bool two = t1 < pv.task_end;
+      const OpRec ta = load_op(ops_base + t0);
+      const OpRec tb = load_op(ops_base + (two ? t1 : t0));
+      float2 sa = partial(ta), sb = partial(tb);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, o);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, o);
+        sa.x += __shfl_xor_sync(0xffffffffu, sa.x, o);
+        sb.x += __shfl_xor_sync(0xffffffffu, sb.x, o);
+        sa.y += __shfl_xor_sync(0xffffffffu, sa.y, o);
+        sb.y += __shfl_xor_sync(0xffffffffu, sb.y, o);
       }
-      if (lane == 0) {
-        if (in_smem) {  // each slot belongs to exactly one pass
-          cx.gacc[gs0 + g0 - ka.L.gslot_begin] = sum0;
-          if (two) cx.gacc[gs0 + g1 - ka.L.gslot_begin] = sum1;
-        } else {
-          atomicAdd(grow + __ldg(&ka.gsym[gs0 + g0]), (double)sum0);
-          if (two) atomicAdd(grow + __ldg(&ka.gsym[gs0 + g1]), (double)sum1);
+      if (lane == 0) {  // every task owns its slot(s) of the flush window
+        cx.gacc[ta.coef] = sa.x;
+        if (ta.type() == OP_TASK_C) cx.gacc[ta.coef + 1] = sa.y;
+        if (two) {
+          cx.gacc[tb.coef] = sb.x;
+          if (tb.type() == OP_TASK_C) cx.gacc[tb.coef + 1] = sb.y;
         }
       }
     }
-    __syncthreads();  // the scratch is the tile: reductions must finish before amplitudes are stored back
+  }
+  if (ngrad > 0 || flush) __syncthreads();  // the scratch is the tile: reductions finish before amplitudes are stored
+  if constexpr (BOTH) {
+    if (flush) {
+      // End of a flush window: one thread per gradient slot combines the reduced sums (DevGradDesc) and
+      // adds the CTA's share to the float64 accumulators.
+      double* grow = ka.gacc + (size_t)(ka.per_state ? (ka.grow0 + (int)u) : 0) * ka.P;
+      const float* G = cx.gacc;
+      for (int g = ps->gd_flush_begin + (int)tid; g < ps->gd_flush_end; g += (int)nthr) {
+        const int4 d0 = __ldg(reinterpret_cast<const int4*>(ka.gdescs + g));
+        const int4 d1 = __ldg(reinterpret_cast<const int4*>(ka.gdescs + g) + 1);
+        const int kind = d0.x, i_tot = d0.w & 0xffff, i_a = (int)((uint32_t)d0.w >> 16);
+        float val;
+        if (kind == 0) {
+          val = G[i_tot];
+        } else {
+          const int ca = (int)(int8_t)(d1.y & 0xff), cb = (int)(int8_t)((d1.y >> 8) & 0xff);
+          const bool ok_a = ca < 0 || ((goff >> ca) & 1u), ok_b = cb < 0 || ((goff >> cb) & 1u);
+          const float2 tot = make_float2(G[i_tot], G[i_tot + 1]);
+          const float2 A = ok_a ? make_float2(G[i_a], G[i_a + 1]) : make_float2(0.f, 0.f);
+          const float* m = ka.coef + d0.z;
+          const float4 m01 = __ldg(reinterpret_cast<const float4*>(m));
+          if (kind == 1) {
+            const float2 U0 = make_float2(tot.x - A.x, tot.y - A.y);
+            val = 2.f * (m01.x * U0.x + m01.y * U0.y + m01.z * A.x + m01.w * A.y);
+          } else {
+            const int i_b = d1.x & 0xffff, i_ab = (int)((uint32_t)d1.x >> 16);
+            const float4 m23 = __ldg(reinterpret_cast<const float4*>(m) + 1);
+            const float2 B = ok_b ? make_float2(G[i_b], G[i_b + 1]) : make_float2(0.f, 0.f);
+            const float2 AB = (ok_a && ok_b) ? make_float2(G[i_ab], G[i_ab + 1]) : make_float2(0.f, 0.f);
+            const float2 U10 = make_float2(A.x - AB.x, A.y - AB.y), U01 = make_float2(B.x - AB.x, B.y - AB.y);
+            const float2 U00 = make_float2(tot.x - A.x - U01.x, tot.y - A.y - U01.y);
+            val = 2.f * (m01.x * U00.x + m01.y * U00.y + m01.z * U01.x + m01.w * U01.y +
+                         m23.x * U10.x + m23.y * U10.y + m23.z * AB.x + m23.w * AB.y);
+          }
+        }
+        if (val != 0.f) atomicAdd(grow + d0.y, (double)val);
+      }
+    }
   }
   {
     const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
@@ -1219,8 +1259,9 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
     sweep_kernel(const __grid_constant__ KernelArgs ka) {
   static_assert(!(DENSE && ADJ), "the dense variant is forward-only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float4 s_stage[((ADJ || DENSE) ? 2 : 1) * kStageF4];
-  __shared__ float s_gacc[ADJ ? kGaccSlots : 1];
+  constexpr int kOpsCap = ADJ ? kStageOpsAdj : kStageOps;
+  __shared__ float4 s_stage[((ADJ || DENSE) ? 2 : 1) * PassCtx::stage_f4(kOpsCap)];
+  __shared__ float s_gacc[ADJ ? kGaccFloats : 1];
   float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float2* s_lam = s_psi + (ADJ ? (1u << ka.T) : 0u);
   constexpr int R = 1 << K;
@@ -1238,11 +1279,7 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   cx.gacc = s_gacc;
   cx.buf = 0;
   cx.dbuf = ADJ || DENSE;
-  const bool flush_gacc = ADJ && ka.L.gslot_count > 0 && ka.L.gslot_count <= kGaccSlots;
-  if constexpr (ADJ) {
-    if (flush_gacc)
-      for (int g = (int)tid; g < ka.L.gslot_count; g += (int)nthr) s_gacc[g] = 0.f;
-  }
+  cx.ops_cap = kOpsCap;
 
   bool active = true;
   if (flags & LF_INIT_BASIS) {
@@ -1296,16 +1333,6 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
     if (flags & LF_STORE_PSI) store_tile<K>(s_psi, ka.psi_out + ((size_t)u << ka.n), goff, ka, one);
     if constexpr (ADJ) {
       if (flags & LF_STORE_LAM) store_tile<K>(s_lam, lam_u, goff, ka, one);
-    }
-  }
-  if constexpr (ADJ) {
-    if (flush_gacc) {
-      __syncthreads();  // the last pass's sums are in s_gacc
-      double* grow = ka.gacc + (size_t)(ka.per_state ? (ka.grow0 + (int)u) : 0) * ka.P;
-      for (int g = (int)tid; g < ka.L.gslot_count; g += (int)nthr) {
-        const float v = s_gacc[g];
-        if (v != 0.f) atomicAdd(grow + __ldg(&ka.gsym[ka.L.gslot_begin + g]), (double)v);
-      }
     }
   }
 }

@@ -146,16 +146,37 @@ struct Ctx {
   std::vector<float> coef;
   std::vector<cplx> psi, lam;  // global state
   std::vector<double> eacc, gacc;
+  std::vector<double> gwin = std::vector<double>(kGaccFloats, 0.0);  // reduced sums of the current flush window
   const float* dgrad;
 };
 
 static cplx cf(const Ctx& c, int off, int i) { return cplx(c.coef[off + 2 * i], c.coef[off + 2 * i + 1]); }
 
-static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector<cplx>& tp, std::vector<cplx>& tl,
+// Unpacks a device op (PackedOp) back into the DevOp fields the interpreter reads.
+static DevOp unpack_op(const PackedOp& q) {
+  DevOp o;
+  std::memset(&o, 0, sizeof(o));
+  o.type = (int32_t)(q.w0 & 0xffu);
+  o.p0 = (int32_t)((q.w0 >> 8) & 0xffu);
+  o.p1 = (int32_t)((q.w0 >> 16) & 0xffu);
+  o.gslot = (int32_t)(q.w0 >> 24);
+  if (o.p0 == 255) o.p0 = -1;
+  if (o.p1 == 255) o.p1 = -1;
+  o.coef = q.coef;
+  o.aux0 = q.aux0;
+  o.aux1 = q.aux1;
+  return o;
+}
+
+// Runs DEVICE pass `pi` (HostPlan::dev_passes / dev_ops) the way the kernel does, including the gradient
+// machinery: per-thread scratch units, the reduction tasks behind the pass's ops, and the descriptors
+// of a flush window.
+static void run_pass(Ctx& c, const LaunchDesc& L, int pi, std::vector<cplx>& tp, std::vector<cplx>& tl,
                      uint32_t goff, bool both) {
   const HostPlan& hp = *c.hp;
+  const DevPass& ps = hp.dev_passes[pi];
   const int K = hp.K, R = 1 << K, nthr = 1 << (hp.T - K);
-  std::vector<double> gsum(ps.ngrad, 0.0);
+  std::vector<double> scratch((size_t)4 * R * nthr, 0.0);  // 4 * 2^K units of one float per thread
   for (int tid = 0; tid < nthr; ++tid) {
     uint32_t base = tid;
     for (int j = 0; j < K; ++j) { int sp = ps.sorted[j]; base = ((base >> sp) << (sp + 1)) | (base & ((1u << sp) - 1u)); }
@@ -183,8 +204,8 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
       }
       if (gout) *gout = 2 * s;
     };
-    for (int oi = ps.op_begin; oi < ps.op_end; ++oi) {
-      const DevOp& op = hp.ops[oi];
+    for (int oi = ps.op_begin; oi < ps.exec_end; ++oi) {
+      const DevOp op = unpack_op(hp.dev_ops[oi]);
       switch (op.type) {
         case OP_MAT1: mat1(a, op.p0, op.coef); if (both) mat1(b, op.p0, op.coef); break;
         case OP_XROT: case OP_YROT: {
@@ -200,7 +221,7 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
               else { y0 = cplx(0, -1) * a[q]; y1 = cplx(0, 1) * a[r]; }
               sacc += (std::conj(b[r]) * y0 + std::conj(b[q]) * y1).imag();
             }
-            gsum[op.gslot] += c.coef[op.coef + 2] * sacc;
+            scratch[(size_t)op.gslot * nthr + tid] = c.coef[op.coef + 2] * sacc;
           }
           for (int which = 0; which < (both ? 2 : 1); ++which) {
             std::vector<cplx>& v = which ? b : a;
@@ -227,7 +248,7 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
                 if (isx) { y0 = a[q]; y1 = a[r]; } else { y0 = cplx(0, -1) * a[q]; y1 = cplx(0, 1) * a[r]; }
                 sacc += (std::conj(b[r]) * y0 + std::conj(b[q]) * y1).imag();
               }
-              gsum[P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1] += kap * sacc;
+              scratch[(size_t)(P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1) * nthr + tid] = kap * sacc;
             }
             for (int which = 0; which < (both ? 2 : 1); ++which) {
               std::vector<cplx>& v = which ? b : a;
@@ -248,7 +269,7 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
             else { y0 = cplx(0, -1) * a[q]; y1 = cplx(0, 1) * a[r]; }
             sacc += (std::conj(b[r]) * y0 + std::conj(b[q]) * y1).imag();
           }
-          gsum[op.gslot] += c.coef[op.coef] * sacc;
+          scratch[(size_t)op.gslot * nthr + tid] = c.coef[op.coef] * sacc;
         } break;
         case OP_MAT2: mat2(a, op.p0 ? 2 : 0, op.coef, nullptr, nullptr); if (both) mat2(b, op.p0 ? 2 : 0, op.coef, nullptr, nullptr); break;
         case OP_DCONST_TAB: F *= cf(c, op.coef, (gbase >> op.aux0) & op.aux1); break;
@@ -263,28 +284,86 @@ static void run_pass(Ctx& c, const LaunchDesc& L, const DevPass& ps, std::vector
             s += (std::conj(b[r]) * (cf(c, op.coef, 0) * x0 + cf(c, op.coef, 1) * x1)).real();
             s += (std::conj(b[r | (1 << op.p0)]) * (cf(c, op.coef, 2) * x0 + cf(c, op.coef, 3) * x1)).real();
           }
-          gsum[op.gslot] += 2 * s;
+          scratch[(size_t)op.gslot * nthr + tid] = 2 * s;
         } break;
-        case OP_GRAD_MAT2: { double g = 0; mat2(a, op.p0 ? 2 : 0, op.coef, &b, &g); gsum[op.gslot] += g; } break;
-        case OP_GD_BEGIN: break;
-        case OP_GD_CONST: case OP_GD_REG1: case OP_GD_REG2: case OP_GD_MIX: {
-          double s = 0;
-          for (int r = 0; r < R; ++r) {
-            int sel;
-            if (op.type == OP_GD_CONST) { sel = (gbase >> op.aux0) & 1; if (op.aux1 >= 0) sel = 2 * sel + ((gbase >> op.aux1) & 1); }
-            else if (op.type == OP_GD_REG1) sel = (r >> op.p0) & 1;
-            else if (op.type == OP_GD_REG2) sel = 2 * ((r >> op.p0) & 1) + ((r >> op.p1) & 1);
-            else sel = 2 * ((gbase >> op.aux0) & 1) + ((r >> op.p0) & 1);
-            s += (cf(c, op.coef, sel) * std::conj(b[r]) * a[r]).real();
+        case OP_GRAD_MAT2: { double g = 0; mat2(a, op.p0 ? 2 : 0, op.coef, &b, &g); scratch[(size_t)op.gslot * nthr + tid] = g; } break;
+        case OP_GD_BEGIN: {
+          // marginal vectors of w = conj(b) a = u + i v, stored as (u, -v): T, S[p], SS[pi] in mask order
+          const uint32_t vmask = (uint32_t)op.coef;
+          int vec = 0;
+          auto store = [&](cplx w) {
+            const size_t at = (size_t)(op.gslot + 2 * vec) * nthr + 2 * (size_t)tid;
+            scratch[at] = w.real();
+            scratch[at + 1] = -w.imag();
+            ++vec;
+          };
+          cplx T = 0;
+          for (int r = 0; r < R; ++r) T += std::conj(b[r]) * a[r];
+          store(T);
+          for (int p = 0; p < K; ++p) {
+            if (!((vmask >> (1 + p)) & 1)) continue;
+            cplx S = 0;
+            for (int r = 0; r < R; ++r) if ((r >> p) & 1) S += std::conj(b[r]) * a[r];
+            store(S);
           }
-          gsum[op.gslot] += 2 * s;
+          for (int ph = 1; ph < K; ++ph) for (int pl = 0; pl < ph; ++pl) {
+            if (!((vmask >> (1 + K + ph * (ph - 1) / 2 + pl)) & 1)) continue;
+            cplx S = 0;
+            for (int r = 0; r < R; ++r) if (((r >> ph) & 1) && ((r >> pl) & 1)) S += std::conj(b[r]) * a[r];
+            store(S);
+          }
+          oi += op.aux0;  // the run's descriptors are host-side information only
         } break;
         default: throw std::runtime_error("verify: unknown op");
       }
     }
     for (int r = 0; r < R; ++r) { tp[idx[r]] = a[r]; if (both) tl[idx[r]] = b[r]; }
   }
-  for (int g = 0; g < ps.ngrad; ++g) c.gacc[hp.gsym[ps.gsym_off + g]] += gsum[g];
+  if (!both) return;
+  for (int t = ps.exec_end; t < ps.op_end; ++t) {  // reduction tasks
+    const DevOp op = unpack_op(hp.dev_ops[t]);
+    if (op.type == OP_TASK_F) {
+      double sum = 0;
+      for (int i = 0; i < nthr; ++i) sum += scratch[(size_t)op.p0 * nthr + i];
+      c.gwin.at(op.coef) = sum;
+    } else if (op.type == OP_TASK_C) {
+      double sx = 0, sy = 0;
+      for (int i = 0; i < nthr; ++i) {
+        if (((uint32_t)i & (uint32_t)op.aux0) != (uint32_t)op.aux0) continue;
+        sx += scratch[(size_t)op.p0 * nthr + 2 * (size_t)i];
+        sy += scratch[(size_t)op.p0 * nthr + 2 * (size_t)i + 1];
+      }
+      c.gwin.at(op.coef) = sx;
+      c.gwin.at(op.coef + 1) = sy;
+    } else {
+      throw std::runtime_error("verify: unexpected op among the reduction tasks");
+    }
+  }
+  for (int g = ps.gd_flush_begin; g < ps.gd_flush_end; ++g) {  // end of a flush window
+    const DevGradDesc& d = hp.gdescs.at(g);
+    double val;
+    if (d.kind == 0) {
+      val = c.gwin.at(d.i_tot);
+    } else {
+      const bool ok_a = d.cond_a < 0 || ((goff >> d.cond_a) & 1u), ok_b = d.cond_b < 0 || ((goff >> d.cond_b) & 1u);
+      auto G2 = [&](int i) { return std::pair<double, double>(c.gwin.at(i), c.gwin.at(i + 1)); };
+      const auto tot = G2(d.i_tot);
+      const auto A = ok_a ? G2(d.i_a) : std::pair<double, double>(0, 0);
+      const float* m = &c.coef[d.coef];
+      if (d.kind == 1) {
+        val = 2 * (m[0] * (tot.first - A.first) + m[1] * (tot.second - A.second) + m[2] * A.first + m[3] * A.second);
+      } else {
+        const auto B = ok_b ? G2(d.i_b) : std::pair<double, double>(0, 0);
+        const auto AB = (ok_a && ok_b) ? G2(d.i_ab) : std::pair<double, double>(0, 0);
+        const double u10x = A.first - AB.first, u10y = A.second - AB.second;
+        const double u01x = B.first - AB.first, u01y = B.second - AB.second;
+        const double u00x = tot.first - A.first - u01x, u00y = tot.second - A.second - u01y;
+        val = 2 * (m[0] * u00x + m[1] * u00y + m[2] * u01x + m[3] * u01y + m[4] * u10x + m[5] * u10y +
+                   m[6] * AB.first + m[7] * AB.second);
+      }
+    }
+    c.gacc[d.sym] += val;
+  }
 }
 
 // Observable pass (OP_HX / OP_HD): th += H_part tp for the strings this pass owns.
@@ -299,7 +378,7 @@ static void run_hpass(Ctx& c, const LaunchDesc& L, const DevPass& ps, const std:
     std::vector<uint32_t> idx(R);
     for (int r = 0; r < R; ++r) { uint32_t dep = 0; for (int j = 0; j < K; ++j) if ((r >> j) & 1) dep |= 1u << ps.regbit[j]; idx[r] = base | dep; }
     for (int oi = ps.op_begin; oi < ps.op_end; ++oi) {
-      const DevOp& op = hp.ops[oi];
+      const DevOp op = unpack_op(hp.dev_ops[oi]);
       if (op.type != OP_HX && op.type != OP_HD) throw std::runtime_error("unexpected op in an observable pass");
       const double sg = (__builtin_popcount(gbase & (uint32_t)op.aux0) & 1) ? -1.0 : 1.0;
       const int xr = op.type == OP_HD ? 0 : op.p0;
@@ -325,7 +404,7 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
       for (int l = 0; l < tsz; ++l) tp[l] = c.psi[goff | scatter(l, L.runs, L.n_runs)];
     }
     if (L.flags & LF_LOAD_LAM) for (int l = 0; l < tsz; ++l) tl[l] = c.lam[goff | scatter(l, L.runs, L.n_runs)];
-    if (active) for (int p = L.pass_a_begin; p < L.pass_a_end; ++p) run_pass(c, L, hp.passes[p], tp, tl, goff, false);
+    if (active) for (int p = L.pass_a_begin; p < L.pass_a_end; ++p) run_pass(c, L, p, tp, tl, goff, false);
     if (L.flags & LF_EXPECT) {
       for (const DevDiagTerm& d : hp.dterms) {  // WHT-path terms: same mathematics, evaluated directly here
         if (L.expect_stage != 0) break;
@@ -339,7 +418,7 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
       }
       if (L.pass_h_end > L.pass_h_begin) {  // single observable: its in-register strings
         std::vector<cplx> th(tsz, 0);
-        for (int p = L.pass_h_begin; p < L.pass_h_end; ++p) run_hpass(c, L, hp.passes[p], tp, th, goff);
+        for (int p = L.pass_h_begin; p < L.pass_h_end; ++p) run_hpass(c, L, hp.dev_passes[p], tp, th, goff);
         const double g0 = (adjoint && c.dgrad) ? c.dgrad[0] : 0.0;
         for (int l = 0; l < tsz; ++l) {
           c.eacc[0] += (std::conj(tp[l]) * th[l]).real();
@@ -371,7 +450,7 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
         c.eacc[j] += ej;
       }
     }
-    for (int p = L.pass_b_begin; p < L.pass_b_end; ++p) run_pass(c, L, hp.passes[p], tp, tl, goff, true);
+    for (int p = L.pass_b_begin; p < L.pass_b_end; ++p) run_pass(c, L, p, tp, tl, goff, true);
     for (int l = 0; l < tsz; ++l) {
       const uint32_t gi = goff | scatter(l, L.runs, L.n_runs);
       if ((L.flags & LF_STORE_PSI) || tiles == 1) psi_next[gi] = tp[l];

@@ -128,3 +128,12 @@ def test_forward_only_plans_with_expectation_stages(n, T, K, kind, monkeypatch):
   np.testing.assert_allclose(e, e_ref, atol=2e-4)
   if n > max(T, K + 5) and kind != "random":
     assert info[6] > info[0] + 1  # launches > forward sweeps + one expectation launch
+
+
+def test_deep_circuit_several_flush_windows():
+  """A single-tile plan with 18 gradient passes in one launch: the reduced sums of all its passes exceed one
+  flush window (kGaccFloats), so the device program must flush mid-launch and rebase later passes."""
+  rng = np.random.default_rng(5)
+  n, layers = 10, 14
+  gates, names = orc.hea_circuit(n, layers)
+  _check(gates, n, len(names), [orc.xxz_ring(n)], rng, 10, 4)

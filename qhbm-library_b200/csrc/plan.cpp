@@ -316,7 +316,7 @@ class Compiler {
           uint32_t dep = 0;
           for (int j = 0; j < K; ++j) if ((r >> j) & 1) dep |= 1u << ps.regbit[j];
           const uint32_t sw = (dep & ~15u) | ((dep ^ (dep >> 4) ^ (dep >> 8) ^ (dep >> 12)) & 15u);
-          ps.eoff[r] = r < (1 << K) ? (uint16_t)sw : 0;
+          ps.eoff8[r] = r < (1 << K) ? 8u * sw : 0u;
         }
         ps.op_begin = (int)hp_.ops.size();
         ps.gsym_off = (int)hp_.gsym.size();
@@ -1023,7 +1023,7 @@ class Compiler {
         for (int j = 0; j < K; ++j) if ((r >> j) & 1) { dep |= 1u << ps.regbit[j]; sdep |= 1u << p.regs[j]; }
         if (r < R) rbits[r] = sdep;
         const uint32_t sw = (dep & ~15u) | ((dep ^ (dep >> 4) ^ (dep >> 8) ^ (dep >> 12)) & 15u);
-        ps.eoff[r] = r < R ? (uint16_t)sw : 0;
+        ps.eoff8[r] = r < R ? 8u * sw : 0u;
       }
       ps.op_begin = (int)hp_.ops.size();
       ps.gsym_off = 0;

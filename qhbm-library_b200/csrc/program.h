@@ -118,14 +118,14 @@ struct DevGradDesc {  // 32 bytes
   int32_t pad1[2];
 };
 
-struct DevPass {  // 160 bytes
+struct DevPass {  // 224 bytes
   int32_t regbit[kMaxRegQubits];     // tile-local bit of register position j
   int32_t sorted[kMaxRegQubits];     // the same bits in ascending order
   int32_t op_begin, op_end;
   int32_t ngrad, gsym_off;           // gradient slots of this pass -> symbols gsym[gsym_off..];
                                      // ngrad == -1 marks an observable pass (OP_HX / OP_HD only)
   int32_t coef_begin, coef_end;      // float range of the coefficient buffer this pass reads
-  uint16_t eoff[1 << kMaxRegQubits]; // swizzled smem offset of register amplitude r (XOR with the thread base)
+  uint32_t eoff8[1 << kMaxRegQubits]; // swizzled smem BYTE offset of register amplitude r (XOR with the thread base)
   int32_t next_op_end, next_coef_end;  // ends of the NEXT pass's ranges (they start where this pass's end):
                                        // what the kernel needs to prefetch that program while this pass runs
   // device program only (HostPlan::dev_passes):

@@ -192,6 +192,9 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
   // (profiles/r2_tile_copy_experiment.md); QHBM_SYNC_TILE=1 restores the register-staged copy
   static const bool sync_tile = std::getenv("QHBM_SYNC_TILE") != nullptr;
   ka.async_tile = sync_tile ? 0 : 1;
+  // pass programs through the bulk-copy engine (profiles/r2_bulk_stage_experiment.md)
+  static const bool no_bulk = std::getenv("QHBM_NO_BULK_STAGE") != nullptr;
+  ka.bulk_stage = no_bulk ? 0 : 1;
 }
 
 // Coefficient jobs + clearing of the call's float64 accumulators in one launch.

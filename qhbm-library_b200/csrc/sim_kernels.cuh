@@ -45,7 +45,36 @@ struct KernelArgs {
   int32_t per_state;
   int32_t phase_coef;     // coef offset of the dropped global phase (debug state output), or -1
   int32_t async_tile;     // tiles are loaded with cp.async (default; QHBM_SYNC_TILE=1 turns it off)
+  int32_t bulk_stage;     // pass programs are staged by the bulk-copy engine (cp.async.bulk + mbarrier; default;
+                          // QHBM_NO_BULK_STAGE=1 restores the per-thread 16-byte copies)
 };
+
+// ---- bulk asynchronous copies (TMA engine, 1-D) completed through an mbarrier ----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
 
 __device__ __forceinline__ uint32_t swz(uint32_t x) {
   return (x & ~15u) | ((x ^ (x >> 4) ^ (x >> 8) ^ (x >> 12)) & 15u);
@@ -414,6 +443,8 @@ struct PassCtx {
   int buf;
   bool dbuf;    // two program buffers (adjoint kernel); the forward-only kernel keeps one, to fit three CTAs per SM
   int ops_cap;  // op descriptors per buffer: kStageOpsAdj in the adjoint kernel (ops + reduction tasks), else kStageOps
+  uint64_t* bars;  // one mbarrier per program buffer (bulk staging)
+  uint32_t phase;  // bit b: parity of the next completion of buffer b's mbarrier
   __device__ __forceinline__ int stride() const { return stage_f4(ops_cap); }
   __host__ __device__ static constexpr int stage_f4(int cap) { return (int)(sizeof(DevPass) / 16) + cap + kStageCoef / 4; }
 };
@@ -443,6 +474,18 @@ __device__ __forceinline__ void stage_program(const KernelArgs& ka, float4* buf,
   }
 }
 
+// The same copy issued by ONE thread to the bulk-copy engine: three cp.async.bulk (descriptor, ops,
+// coefficients) that complete on the buffer's mbarrier.  Sizes are multiples of 16 bytes by construction.
+__device__ __forceinline__ void stage_program_bulk(const KernelArgs& ka, float4* buf, uint64_t* bar, const int ops_cap,
+                                                   const int p, const int op_begin, const int op_end, const int cb,
+                                                   const int ce) {
+  const uint32_t n_ops = (uint32_t)(op_end - op_begin), n_cf = (uint32_t)((ce - cb + 3) / 4);
+  mbar_expect_tx(bar, (uint32_t)sizeof(DevPass) + 16u * (n_ops + n_cf));
+  bulk_g2s(buf, ka.passes + p, (uint32_t)sizeof(DevPass), bar);
+  if (n_ops) bulk_g2s(buf + kPassF4, ka.ops + op_begin, 16u * n_ops, bar);
+  if (n_cf) bulk_g2s(buf + kPassF4 + ops_cap, ka.coef + cb, 16u * n_cf, bar);
+}
+
 // Start of a pass: makes pass p's program current (staging it now if it is the first of its range, else
 // waiting for the prefetch), starts the prefetch of pass p + 1, and returns the views into the buffer.
 struct PassView {
@@ -454,14 +497,25 @@ struct PassView {
 };
 __device__ __forceinline__ PassView begin_pass(const KernelArgs& ka, PassCtx& cx, const int p, const bool first,
                                                const bool last) {
+  const bool bulk = ka.bulk_stage != 0;
   if (first || !cx.dbuf) {
     __syncthreads();  // the previous phase is done with the tiles and the stage buffers
     const DevPass* gp = ka.passes + p;
-    stage_program<false>(ka, cx.stage + cx.buf * cx.stride(), cx.ops_cap, p, __ldg(&gp->op_begin), __ldg(&gp->op_end),
-                         __ldg(&gp->coef_begin), __ldg(&gp->coef_end));
+    if (bulk) {
+      if (threadIdx.x == 0)
+        stage_program_bulk(ka, cx.stage + cx.buf * cx.stride(), cx.bars + cx.buf, cx.ops_cap, p, __ldg(&gp->op_begin),
+                           __ldg(&gp->op_end), __ldg(&gp->coef_begin), __ldg(&gp->coef_end));
+    } else {
+      stage_program<false>(ka, cx.stage + cx.buf * cx.stride(), cx.ops_cap, p, __ldg(&gp->op_begin), __ldg(&gp->op_end),
+                           __ldg(&gp->coef_begin), __ldg(&gp->coef_end));
+    }
     if (ka.async_tile) __pipeline_wait_prior(0);  // cp.async tile loads of this thread (experiment switch)
-  } else {
+  } else if (!bulk) {
     __pipeline_wait_prior(0);
+  }
+  if (bulk) {  // every thread observes the completion: the engine's writes are visible to it afterwards
+    mbar_wait(cx.bars + cx.buf, (cx.phase >> cx.buf) & 1u);
+    cx.phase ^= 1u << cx.buf;
   }
   __syncthreads();  // program visible; the previous pass's tile stores and gradient reduction are complete
   float4* buf = cx.stage + cx.buf * cx.stride();
@@ -474,9 +528,16 @@ __device__ __forceinline__ PassView begin_pass(const KernelArgs& ka, PassCtx& cx
   v.ops = reinterpret_cast<const PackedOp*>(buf + kPassF4) - v.op_begin;
   v.coef = reinterpret_cast<const float*>(buf + kPassF4 + cx.ops_cap) - cb;
   if (cx.dbuf) {
-    if (!last)  // passes of a range are consecutive: the next program starts where this one ends
-      stage_program<true>(ka, cx.stage + (cx.buf ^ 1) * cx.stride(), cx.ops_cap, p + 1, v.task_end, v.ps->next_op_end,
-                          v.ps->coef_end, v.ps->next_coef_end);
+    if (!last) {  // passes of a range are consecutive: the next program starts where this one ends
+      if (bulk) {
+        if (threadIdx.x == 0)
+          stage_program_bulk(ka, cx.stage + (cx.buf ^ 1) * cx.stride(), cx.bars + (cx.buf ^ 1), cx.ops_cap, p + 1,
+                             v.task_end, v.ps->next_op_end, v.ps->coef_end, v.ps->next_coef_end);
+      } else {
+        stage_program<true>(ka, cx.stage + (cx.buf ^ 1) * cx.stride(), cx.ops_cap, p + 1, v.task_end, v.ps->next_op_end,
+                            v.ps->coef_end, v.ps->next_coef_end);
+      }
+    }
     cx.buf ^= 1;
   }
   return v;
@@ -502,17 +563,20 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
   const uint32_t gbase = goff | scatter_bits(base, ka.L.runs, ka.L.n_runs);
   float2 a[R];
   float2 b[BOTH ? R : 1];
+  // Byte addressing: amplitude r sits at tile + (8 B ^ eoff8[r]) -- one LOP3 per access, the tile base folds
+  // into the LDS / STS address operand.
+  const uint32_t B8 = 8u * B;
   {
-    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
+    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff8);
 #pragma unroll
-    for (int i = 0; i < R / 8; ++i) {
+    for (int i = 0; i < R / 4; ++i) {
       const uint4 w = ep[i];
-      const uint32_t eo[8] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16,
-                              w.z & 0xffffu, w.z >> 16, w.w & 0xffffu, w.w >> 16};
+      const uint32_t eo[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        a[8 * i + r] = s_psi[B ^ eo[r]];
-        if constexpr (BOTH) b[8 * i + r] = s_lam[B ^ eo[r]];
+      for (int r = 0; r < 4; ++r) {
+        a[4 * i + r] = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(s_psi) + (B8 ^ eo[r]));
+        if constexpr (BOTH)
+          b[4 * i + r] = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(s_lam) + (B8 ^ eo[r]));
       }
     }
   }
@@ -762,16 +826,15 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
     }
   }
   {
-    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff);
+    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff8);
 #pragma unroll
-    for (int i = 0; i < R / 8; ++i) {
+    for (int i = 0; i < R / 4; ++i) {
       const uint4 w = ep[i];
-      const uint32_t eo[8] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16,
-                              w.z & 0xffffu, w.z >> 16, w.w & 0xffffu, w.w >> 16};
+      const uint32_t eo[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        s_psi[B ^ eo[r]] = a[8 * i + r];
-        if constexpr (BOTH) s_lam[B ^ eo[r]] = b[8 * i + r];
+      for (int r = 0; r < 4; ++r) {
+        *reinterpret_cast<float2*>(reinterpret_cast<char*>(s_psi) + (B8 ^ eo[r])) = a[4 * i + r];
+        if constexpr (BOTH) *reinterpret_cast<float2*>(reinterpret_cast<char*>(s_lam) + (B8 ^ eo[r])) = b[4 * i + r];
       }
     }
   }
@@ -847,30 +910,35 @@ __device__ __forceinline__ void run_hpass(const KernelArgs& ka, PassCtx& cx, con
   float e = 0.f;
 #pragma unroll 1
   for (int half = 0; half < R / 16; ++half) {
-    uint32_t eo[16];
-    {
-      const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff) + 2 * half;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint4 w = ep[i];
-        eo[8 * i + 0] = w.x & 0xffffu; eo[8 * i + 1] = w.x >> 16;
-        eo[8 * i + 2] = w.y & 0xffffu; eo[8 * i + 3] = w.y >> 16;
-        eo[8 * i + 4] = w.z & 0xffffu; eo[8 * i + 5] = w.z >> 16;
-        eo[8 * i + 6] = w.w & 0xffffu; eo[8 * i + 7] = w.w >> 16;
-      }
-    }
+    const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff8) + 4 * half;
+    const uint32_t B8 = 8u * B;
     float2 a[16];
     float2 b[BOTH ? 16 : 1];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      a[r] = s_psi[B ^ eo[r]];
-      if constexpr (BOTH) b[r] = s_lam[B ^ eo[r]];
+    for (int i = 0; i < 4; ++i) {
+      const uint4 w = ep[i];
+      const uint32_t eo[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        a[4 * i + r] = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(s_psi) + (B8 ^ eo[r]));
+        if constexpr (BOTH)
+          b[4 * i + r] = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(s_lam) + (B8 ^ eo[r]));
+      }
     }
+    float dsum = 0.f;
+    bool any_dsum = false;  // uniform
     for (int oi = op_begin; oi < op_end; ++oi) {
       const OpRec op = load_op(ops_base + oi);
       const float* cf = coef_base + op.coef + 16 * half;
       const float sgn = (__popc(gbase & (uint32_t)op.aux0) & 1) ? -1.f : 1.f;
       const int mode = op.aux1;
+      if (op.type() == OP_HD && mode == 1) {
+        // a Z string that misses the register qubits: one scalar per thread; all of them are applied
+        // together after the loop (one multiply-add per amplitude for the whole set)
+        dsum = fmaf(sgn, cf[0], dsum);
+        any_dsum = true;
+        continue;
+      }
       auto apply = [&](auto xc) {
         constexpr int XR = decltype(xc)::value;
         if (mode == 1) hx_apply<XR, BOTH, 1>(a, b, cf, sgn, e);
@@ -893,9 +961,26 @@ __device__ __forceinline__ void run_hpass(const KernelArgs& ka, PassCtx& cx, con
         default: break;
       }
     }
+    if (any_dsum) {
+      if constexpr (BOTH) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) b[r] = fma2(bc(dsum), a[r], b[r]);
+      } else {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc = fma2(a[r], a[r], acc);
+        e = fmaf(dsum, hsum(acc), e);
+      }
+    }
     if constexpr (BOTH) {
 #pragma unroll
-      for (int r = 0; r < 16; ++r) s_lam[B ^ eo[r]] = b[r];
+      for (int i = 0; i < 4; ++i) {
+        const uint4 w = ep[i];  // re-read: 16 offsets must not stay live across the op loop
+        const uint32_t eo[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          *reinterpret_cast<float2*>(reinterpret_cast<char*>(s_lam) + (B8 ^ eo[r])) = b[4 * i + r];
+      }
     }
   }
   if constexpr (!BOTH) {
@@ -1037,6 +1122,15 @@ __device__ __forceinline__ bool uniform_coefficient(const DevTerm* terms, const 
   return true;
 }
 
+// Scalar-coefficient fast path of an x-group (no term distinguishes the thread's amplitudes): also in the
+// adjoint kernel since the groups that reach it are the out-of-tile ones, where a zero scalar skips the
+// cross-tile reads (measured 15.01 -> 14.89 ms per 4096 bitstrings on config 3, gpurun_out/s6).
+#ifndef QHBM_ADJ_SCALAR
+#define QHBM_ADJ_SCALAR 1
+#endif
+template <bool ADJ>
+constexpr bool kScalarGroups = !ADJ || QHBM_ADJ_SCALAR;
+
 template <int MC, bool CPLX, bool GLOBAL, bool SCALAR>
 __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const DevTerm* terms, const float2* s_psi,
                                               const float2* __restrict__ psi_u, float2 (&h)[MC],
@@ -1047,6 +1141,7 @@ __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const DevTer
   if constexpr (SCALAR) {  // forward-only kernel: in the adjoint kernel the extra code costs more than it saves
     float c0r = k0r, c0i = k0i;
     if (uniform_coefficient<MC, CPLX>(terms, gi_tid, m0, t0, t1, c0r, c0i)) {
+      if (c0r == 0.f && (!CPLX || c0i == 0.f)) return;  // e.g. XX + YY on an aligned pair: nothing to add
 #pragma unroll
       for (int m = 0; m < MC; ++m) {
         float2 p;
@@ -1182,11 +1277,11 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
           for (int m = 0; m < MC; ++m) h[m] = make_float2(0.f, 0.f);
         }
         if (ck.z == 0) {
-          if (xl >= 0) group_offdiag<MC, false, false, !ADJ>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
-          else group_offdiag<MC, false, true, !ADJ>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          if (xl >= 0) group_offdiag<MC, false, false, kScalarGroups<ADJ>>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          else group_offdiag<MC, false, true, kScalarGroups<ADJ>>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
         } else {
-          if (xl >= 0) group_offdiag<MC, true, false, !ADJ>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
-          else group_offdiag<MC, true, true, !ADJ>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          if (xl >= 0) group_offdiag<MC, true, false, kScalarGroups<ADJ>>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
+          else group_offdiag<MC, true, true, kScalarGroups<ADJ>>(ka, terms, s_psi, psi_u, h, gi_tid, ph_tid, nthr, m0, x, xl, ch.z, ch.w, k0r, k0i);
         }
       }
       if (offdiag) {
@@ -1280,6 +1375,14 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   cx.buf = 0;
   cx.dbuf = ADJ || DENSE;
   cx.ops_cap = kOpsCap;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  cx.bars = s_bar;
+  cx.phase = 0u;
+  if (ka.bulk_stage && tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();  // (the first begin_pass starts with a barrier before any copy is issued)
+  }
 
   bool active = true;
   if (flags & LF_INIT_BASIS) {

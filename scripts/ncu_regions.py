@@ -66,7 +66,7 @@ src_cache = {}
 
 def src(f, ln):
   if f not in src_cache:
-    p = os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", f)
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "qhbm-library_b200", "csrc", f)
     src_cache[f] = open(p).read().splitlines() if os.path.exists(p) else []
   L = src_cache[f]
   return L[ln - 1].strip()[:90] if 0 < ln <= len(L) else ""

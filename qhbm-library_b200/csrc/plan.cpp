@@ -1406,6 +1406,11 @@ void lower_device_program(HostPlan& hp) {
     const bool has_next = p + 1 < npass;
     hp.dev_passes[p].next_op_end = has_next ? hp.dev_passes[p + 1].op_end : hp.dev_passes[p].op_end;
   }
+  hp.lean = true;
+  for (const PackedOp& q : hp.dev_ops) {
+    const int t = (int)(q.w0 & 0xffu);
+    if (t == OP_MAT1 || t == OP_MAT2 || t == OP_GRAD_MAT1 || t == OP_GRAD_MAT2 || t == OP_YROTM) hp.lean = false;
+  }
   // Flush windows: consecutive gradient passes of a launch share the shared-memory sums until they would
   // overflow; the last pass of a window evaluates the window's descriptors.
   for (const LaunchDesc& L : hp.launches) {

@@ -55,6 +55,7 @@ struct HostPlan {
   std::vector<DevPass> dev_passes;
   std::vector<PackedOp> dev_ops;
   std::vector<DevGradDesc> gdescs;
+  bool lean = false;  // no general-matrix op anywhere: the kernels' GEN = false instantiations run it
 
   int tiles() const { return 1 << (n_eff - T); }
 };

@@ -10,7 +10,7 @@
 
 #include "common.h"
 #include "plan.h"
-#include "sim_kernels.cuh"
+#include "sim_launch.h"
 
 namespace qhbm {
 
@@ -78,6 +78,14 @@ struct qhbm_plan {
   ~qhbm_plan() { if (done) cudaEventDestroy(done); }
 };
 
+namespace qhbm {
+void launch_sweep_gen(int K, bool adj, bool dense, const KernelArgs& ka, unsigned grid, int threads, size_t smem,
+                      cudaStream_t s) {
+  launch_sweep_impl<true>(K, adj, dense, ka, grid, threads, smem, s);
+}
+void allow_large_smem_gen() { QHBM_CUDA(allow_large_smem_impl<true>()); }
+}  // namespace qhbm
+
 namespace {
 // Holds the plan's host lock and orders this call's device work after the previous call's.
 struct PlanUse {
@@ -98,54 +106,33 @@ struct PlanUse {
 
 namespace {
 
-template <int K, bool ADJ>
-void launch_sweep(const KernelArgs& ka, int n_states, int tiles, int threads, size_t smem, cudaStream_t s) {
-  sweep_kernel<K, ADJ><<<(unsigned)(n_states * tiles), threads, smem, s>>>(ka);
-  QHBM_CUDA(cudaGetLastError());
-}
-
 // Opt in to large dynamic shared memory once per plan creation (the attribute is per device and
 // function and sticky; launches then only pass the size they need).
 void allow_large_smem() {
-  int dev = 0, optin = 0;
-  QHBM_CUDA(cudaGetDevice(&dev));
-  QHBM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  auto allow = [&](const void* fn) {
-    cudaFuncAttributes attr;
-    QHBM_CUDA(cudaFuncGetAttributes(&attr, fn));
-    QHBM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)attr.sharedSizeBytes));
-  };
-  allow(reinterpret_cast<const void*>(sweep_kernel<4, true>));
-  allow(reinterpret_cast<const void*>(sweep_kernel<4, false>));
-  allow(reinterpret_cast<const void*>(sweep_kernel<5, true>));
-  allow(reinterpret_cast<const void*>(sweep_kernel<5, false>));
-  allow(reinterpret_cast<const void*>(sweep_kernel<4, false, true>));
+  allow_large_smem_gen();
+  allow_large_smem_lean();
 }
 
 void launch_any(const qhbm_plan* p, bool adj, const KernelArgs& ka, int n_states, cudaStream_t s) {
   const HostPlan& hp = p->hp;
   const int threads = 1 << (hp.T - hp.K);
+  static const bool no_lean = std::getenv("QHBM_NO_LEAN") != nullptr;
+  const auto launch = (hp.lean && !no_lean) ? launch_sweep_lean : launch_sweep_gen;
+  const unsigned grid = (unsigned)(n_states * hp.tiles());
   // forward sweeps of an adjoint plan (psi only, no expectation phase, no backward passes) run on the dense
   // forward kernel: one tile of shared memory and ~80 registers instead of two tiles and 128
   const bool psi_only = !(ka.L.flags & (LF_EXPECT | LF_LOAD_LAM | LF_STORE_LAM | LF_WRITE_STATE)) &&
                         ka.L.pass_b_end == ka.L.pass_b_begin;
   static const bool no_dense = std::getenv("QHBM_NO_DENSE_FWD") != nullptr;
   if (adj && psi_only && hp.K == 4 && threads <= 256 && hp.tiles() > 1 && !no_dense) {
-    const size_t smem1 = (size_t)8u * (1u << hp.T);
-    sweep_kernel<4, false, true><<<(unsigned)(n_states * hp.tiles()), threads, smem1, s>>>(ka);
+    launch(4, false, true, ka, grid, threads, (size_t)8u * (1u << hp.T), s);
     QHBM_CUDA(cudaGetLastError());
     return;
   }
   // psi tile (+ lambda tile for the adjoint kernel; forward-only WHT needs a float scratch tile)
   const size_t smem = (size_t)(adj ? 2 : 1) * 8u * (1u << hp.T) + ((!adj && !hp.dterms.empty()) ? 4u * (1u << hp.T) : 0u);
-  const int tiles = hp.tiles();
-  if (hp.K == 4) {
-    if (adj) launch_sweep<4, true>(ka, n_states, tiles, threads, smem, s);
-    else launch_sweep<4, false>(ka, n_states, tiles, threads, smem, s);
-  } else {
-    if (adj) launch_sweep<5, true>(ka, n_states, tiles, threads, smem, s);
-    else launch_sweep<5, false>(ka, n_states, tiles, threads, smem, s);
-  }
+  launch(hp.K, adj, false, ka, grid, threads, smem, s);
+  QHBM_CUDA(cudaGetLastError());
 }
 
 int default_chunk(const qhbm_plan* p) {

@@ -108,7 +108,7 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 // Sign pair in the constant bank.  A pair such as (-y, y) built with register moves is re-materialised by
 // ptxas at every use (one MOV per packed instruction, measured); as the product bc(y) * kNP it is ONE
 // FMUL2 whose result is an ordinary register pair.
-__constant__ float2 kNP = {-1.f, 1.f};
+static __constant__ float2 kNP = {-1.f, 1.f};  // (static: the header is compiled into two units)
 __device__ __forceinline__ float2 np_pair(float y) { return mul2(bc(y), kNP); }  // (-y, y)
 // A complex constant c prepared for packed use: re = c.x and q = (-c.y, c.y).
 struct CK {
@@ -543,7 +543,11 @@ __device__ __forceinline__ PassView begin_pass(const KernelArgs& ka, PassCtx& cx
   return v;
 }
 
-template <int K, bool BOTH>
+// GEN = false compiles the general-matrix ops out (OP_MAT1 / OP_MAT2 / OP_GRAD_MAT* / OP_YROTM): their 4x4
+// blocks set the register allocation of the whole interpreter loop (120 bytes of spills per thread in the
+// adjoint kernel, 16 without them), so plans that never use them -- X-power / diagonal-gate circuits such
+// as the hardware-efficient ansatz -- run on the lean instantiation (HostPlan::lean).
+template <int K, bool BOTH, bool GEN>
 __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, const int p, const bool first,
                                          const bool last, float2* s_psi, float2* s_lam, uint32_t goff, uint32_t u) {
   constexpr int R = 1 << K;
@@ -631,7 +635,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
           }
         });
       } break;
-      case OP_YROTM: {
+      case OP_YROTM: if constexpr (GEN) {
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
           if (op.p0() & (1 << P)) {
@@ -647,7 +651,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
           }
         });
       } break;
-      case OP_MAT1: {
+      case OP_MAT1: if constexpr (GEN) {
         const float4 m0 = ldg4(cf), m1 = ldg4(cf + 4);
         dispatch_pos<K>(op.p0(), [&](auto pc) {
           constexpr int P = decltype(pc)::value;
@@ -655,7 +659,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
           if constexpr (BOTH) mat1<K, P>(b, m0, m1);
         });
       } break;
-      case OP_MAT2: {
+      case OP_MAT2: if constexpr (GEN) {
         if (op.p0() == 0) {
           mat2<K, 0, false>(a, a, cf);
           if constexpr (BOTH) mat2<K, 0, false>(b, b, cf);
@@ -716,12 +720,12 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
       } break;
       default:
         if constexpr (BOTH) {
-          if (op.type() == OP_GRAD_MAT1) {
+          if (GEN && op.type() == OP_GRAD_MAT1) {
             const float4 m0 = ldg4(cf), m1 = ldg4(cf + 4);
             float v = 0.f;
             dispatch_pos<K>(op.p0(), [&](auto pc) { v = grad_mat1<K, decltype(pc)::value>(a, b, m0, m1); });
             scratch[op.gslot() * nthr + tid] = v;
-          } else if (op.type() == OP_GRAD_MAT2) {
+          } else if (GEN && op.type() == OP_GRAD_MAT2) {
             const float g = op.p0() == 0 ? mat2<K, 0, true>(a, b, cf) : mat2<K, 2, true>(a, b, cf);
             scratch[op.gslot() * nthr + tid] = g;
           } else if (op.type() == OP_GD_BEGIN) {
@@ -1349,7 +1353,7 @@ constexpr int sweep_max_threads() { return ADJ ? (1 << (13 - K)) : 512; }
 // DENSE (forward kernel, K = 4, <= 256 threads): compiled for three resident CTAs per SM with two program
 // buffers; it runs the forward sweeps of ADJOINT plans, which hold one 32 KiB psi tile each and would
 // otherwise occupy the SM with the two-CTA, 128-register adjoint kernel.
-template <int K, bool ADJ, bool DENSE = false>
+template <int K, bool ADJ, bool DENSE = false, bool GEN = true>
 __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DENSE ? 3 : 1)
     sweep_kernel(const __grid_constant__ KernelArgs ka) {
   static_assert(!(DENSE && ADJ), "the dense variant is forward-only");
@@ -1404,7 +1408,7 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
 
   if (active) {
     for (int p = ka.L.pass_a_begin; p < ka.L.pass_a_end; ++p)
-      run_pass<K, false>(ka, cx, p, p == ka.L.pass_a_begin, p + 1 == ka.L.pass_a_end, s_psi, s_lam, goff, u);
+      run_pass<K, false, GEN>(ka, cx, p, p == ka.L.pass_a_begin, p + 1 == ka.L.pass_a_end, s_psi, s_lam, goff, u);
   }
   if (ka.async_tile) __pipeline_wait_prior(0);  // (experiment switch) tile copies that no pass has waited for
   if constexpr (!DENSE) {  // (the dense forward variant only ever runs plain forward sweeps)
@@ -1429,7 +1433,7 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   }
   if constexpr (ADJ) {
     for (int p = ka.L.pass_b_begin; p < ka.L.pass_b_end; ++p)
-      run_pass<K, true>(ka, cx, p, p == ka.L.pass_b_begin, p + 1 == ka.L.pass_b_end, s_psi, s_lam, goff, u);
+      run_pass<K, true, GEN>(ka, cx, p, p == ka.L.pass_b_begin, p + 1 == ka.L.pass_b_end, s_psi, s_lam, goff, u);
   }
   if (flags & (LF_STORE_PSI | LF_STORE_LAM)) {
     __syncthreads();
@@ -1440,6 +1444,7 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   }
 }
 
+#ifndef QHBM_SWEEP_KERNELS_ONLY  // (sim_lean.cu only instantiates the sweep kernels)
 // ---------------------------------------------------------------------------------
 // Coefficient preparation: symbols -> gate matrices, gradient matrices, phase tables.
 // One CTA per job; float64 math, float32 results.
@@ -1643,5 +1648,6 @@ __global__ void finalize_kernel(const double* __restrict__ src_a, float* __restr
   if (i < n_a) dst_a[i] = (float)src_a[i];
   else if (i < n_a + n_b) dst_b[i - n_a] = (float)src_b[i - n_a];
 }
+#endif  // QHBM_SWEEP_KERNELS_ONLY
 
 }  // namespace qhbm

@@ -11,8 +11,9 @@ for f in ebm measure; do
   if [ ! -f $OBJ/$f.o ] || [ $C/$f.cu -nt $OBJ/$f.o ]; then nvcc $FLAGS -c $C/$f.cu -o $OBJ/$f.o & fi
 done
 nvcc $FLAGS -c $C/plan.cpp -o $OBJ/plan_$$.o &
+nvcc $FLAGS "$@" -c $C/sim_lean.cu -o $OBJ/sim_lean_$$.o &
 nvcc $FLAGS "$@" -c $C/sim.cu -o $OBJ/sim_$$.o
 wait
-nvcc -shared -o $OUT $OBJ/sim_$$.o $OBJ/plan_$$.o $OBJ/ebm.o $OBJ/measure.o
-rm -f $OBJ/sim_$$.o $OBJ/plan_$$.o
+nvcc -shared -o $OUT $OBJ/sim_$$.o $OBJ/sim_lean_$$.o $OBJ/plan_$$.o $OBJ/ebm.o $OBJ/measure.o
+rm -f $OBJ/sim_$$.o $OBJ/sim_lean_$$.o $OBJ/plan_$$.o
 echo built $OUT

@@ -171,6 +171,8 @@ def kernel_source_sha():
   h = hashlib.sha256()
   csrc = os.path.join(ROOT, "qhbm-library_b200", "csrc")
   for f in sorted(os.listdir(csrc)):
+    if not os.path.isfile(os.path.join(csrc, f)) or f.startswith("."):
+      continue
     with open(os.path.join(csrc, f), "rb") as fh:
       h.update(fh.read())
   return h.hexdigest()[:16]

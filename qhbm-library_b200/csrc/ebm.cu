@@ -1076,7 +1076,11 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
     int blocks = (int)std::min<uint64_t>((rows + kEnergyThreads - 1) / kEnergyThreads, 148 * 8);
     blocks = std::max(blocks, 1);
     void* partial = sweep_scratch(s);  // per-CTA partial statistics
-    if (e->kind == QHBM_ENERGY_MLP && e->n_layers >= 2 && rows >= 4096) {
+    // The kernel is chosen from the PROBLEM size (2^n_bits rows), never from this call's row count: a
+    // rank that sweeps one shard of the range must produce bit-identical logits to a single sweep of the
+    // whole range, or the sharded sampler would not reproduce the single-GPU draw.
+    const bool big = e->n_bits >= 12 && rows >= 1;
+    if (e->kind == QHBM_ENERGY_MLP && e->n_layers >= 2 && big) {
       // register-tiled dense-stack kernel: weights + one [64][128] activation buffer in shared memory
       const size_t msmem = ((mlp_sweep_weight_floats(*e) * sizeof(float) + 15) & ~(size_t)15) +
                            sizeof(float) * kMaxWidth * kMlpRows;
@@ -1084,7 +1088,7 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
       const uint64_t ntiles = (hi - 1) / kMlpRows - lo / kMlpRows + 1;
       blocks = (int)std::min<uint64_t>(ntiles, 148 * 3);
       ebm_mlp_sweep_kernel<<<blocks, kMlpThreads, msmem, s>>>(ea, lo, hi, d_logits, (Stat*)partial);
-    } else if (e->kind != QHBM_ENERGY_MLP && rows >= 4096 && (size_t)e->n_terms * 12 <= 200 * 1024) {
+    } else if (e->kind != QHBM_ENERGY_MLP && big && (size_t)e->n_terms * 12 <= 200 * 1024) {
       // Walsh-Hadamard tiles of 256 rows: theta, masks and the bucket order in shared memory
       const size_t psmem = (size_t)std::max(e->n_terms, 1) * 12;
       QHBM_CUDA(cudaFuncSetAttribute(ebm_parity_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));

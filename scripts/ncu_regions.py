@@ -21,8 +21,9 @@ rep, k, so, kern = sys.argv[1:5]
 depth = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.startswith("sim.") and f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+dis = ""
+for cubin in sorted(f for f in os.listdir(tmp) if f.startswith("sim") and f.endswith(".cubin")):
+  dis += subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 
 chains = {}   # offset -> tuple of (file, line) outermost first
 opc = {}

@@ -177,7 +177,7 @@ def test_two_gpu_vqt_and_qmhl_equal_single_gpu(tmp_path):
   for key in single:
     np.testing.assert_array_equal(r0[key], r1[key])              # all ranks agree exactly
   # the sharded analytic sampler reproduces the single-GPU draw (same seed, any number of ranks)
-  assert int((r0["samples"] != single["samples"]).sum()) <= 2
+  np.testing.assert_array_equal(r0["samples"], single["samples"])  # (shards sweep bit-identical logits)
   np.testing.assert_allclose(r0["entropy"], single["entropy"], rtol=1e-6)
   for key in ("vqt_loss", "qmhl_loss"):
     np.testing.assert_allclose(r0[key], single[key], rtol=2e-6, atol=2e-6)

@@ -256,3 +256,36 @@ def test_deep_circuits_split_passes_to_fit_the_staging_buffers(n, layers, T, K):
   np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=1e-5, atol=1e-6 * scale.max())
   floor = 1e-6 * (np.abs(dg) * scale[None, :]).sum(1)[:, None] * math.sqrt(layers)
   assert (np.abs(g.cpu().numpy() - g_ref) <= 1e-5 * np.abs(g_ref) + floor).all()
+
+
+# ------------------------------------------------------------------ shards sweep bit-identical logits
+@pytest.mark.parametrize("kind", ["kobe", "mlp"])
+def test_shard_sweeps_reproduce_the_full_sweep_bit_for_bit(kind):
+  """A rank that sweeps a shard of the 2^n rows must produce the logits a single sweep of the whole range
+  produces, bit for bit (the kernel is chosen from the problem size, not from the shard's row count):
+  only then does the rank-sharded sampler draw exactly the single-GPU samples.  Covers aligned 8-way
+  shards and an unaligned split, and the merged (m, s, t) statistics."""
+  from qhbmlib import distributed as qd
+  from qhbmlib.inference import ebm
+  n = 12
+  if kind == "kobe":
+    energy = models.KOBE(list(range(n)), 2, energy_utils.RandomNormal(0.0, 0.3, 21))
+  else:
+    torch.manual_seed(3)
+    energy = models.BitstringEnergy(list(range(n)), [FloatLinear(n, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32),
+                                                     torch.nn.Tanh(), torch.nn.Linear(32, 1), utils.Squeeze(-1)])
+  inf = inference.AnalyticEnergyInference(energy, 10, initial_seed=[1, 2])
+  with torch.no_grad():
+    log_z = float(inf.log_partition())
+  desc = ebm.energy_descriptor(inf.energy)
+  assert desc is not None
+  full, stats = desc.sweep(0, 1 << n, device=DEV)
+  assert torch.equal(full, inf._logits)
+  for bounds in ([i << 9 for i in range(9)], [0, 100, 1357, 1358, 2048, 4000, 4096]):
+    triples = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+      part, st = desc.sweep(lo, hi, device=DEV)
+      assert torch.equal(part, full[lo:hi]), (kind, lo, hi)
+      triples.append(st.cpu().tolist())
+    m, s, _ = qd.merge_log_stats(triples)
+    np.testing.assert_allclose(m + math.log(s), log_z, rtol=1e-6)

@@ -53,6 +53,7 @@ void validate_ops(const OpsIR& o) {
 namespace {
 
 struct Atom {
+  bool tail = false;  // backward order: no later atom touches its qubits, so un-applying it serves nothing
   bool diag = false;
   int nq = 1;
   int bit[2] = {-1, -1};
@@ -149,6 +150,16 @@ class Compiler {
       if (a.nq == 2) a.bit[1] = bit_of(g.q1);
       a.gates.push_back(gi);
       atoms.push_back(a);
+    }
+    // The first gates of the circuit come last here.  Nothing is un-applied after them on their qubits and
+    // every later gradient inner product <lam| dG |psi> sits on other qubits, which they commute with:
+    // only their own gradient is needed, never the un-application (a third of a rotation's arithmetic).
+    std::vector<char> seen(hp_.n_eff, 0);
+    for (size_t ai = atoms.size(); ai-- > 0;) {
+      Atom& a = atoms[ai];
+      a.tail = true;
+      for (int i = 0; i < a.nq; ++i) a.tail = a.tail && !seen[a.bit[i]];
+      for (int i = 0; i < a.nq; ++i) seen[a.bit[i]] = 1;
     }
     return atoms;
   }
@@ -466,8 +477,12 @@ class Compiler {
       const DevOp& o = hp_.ops[i];
       if (o.type != OP_XROT && o.type != OP_YROT) { out.push_back(o); ++i; continue; }
       size_t j = i;
-      int mask = 0;
-      while (j < end && hp_.ops[j].type == o.type && !(mask & (1 << hp_.ops[j].p0))) { mask |= 1 << hp_.ops[j].p0; ++j; }
+      int mask = 0, used = 0;  // positions that are rotated / positions taken by this op (rotated or gradient-only)
+      while (j < end && hp_.ops[j].type == o.type && !(used & (1 << hp_.ops[j].p0))) {
+        used |= 1 << hp_.ops[j].p0;
+        if (hp_.ops[j].aux0 != 1) mask |= 1 << hp_.ops[j].p0;
+        ++j;
+      }
       DevOp m = make_op(o.type == OP_XROT ? OP_XROTM : OP_YROTM);
       m.p0 = mask;
       m.aux0 = 0;
@@ -487,7 +502,7 @@ class Compiler {
           else m.p1 = r.gslot;
         }
       }
-      if (m.type == OP_XROTM && __builtin_popcount(mask) >= K - 1) {
+      if (m.type == OP_XROTM && mask == used && __builtin_popcount(mask) >= K - 1) {
         // one job computes all K rotations of the op together (it needs the product of the cosines)
         m.type = OP_XROTF;
         std::vector<int32_t> per_pos(K, -1);
@@ -518,8 +533,11 @@ class Compiler {
       const int gi = a.gates[0];
       const qhbm_gate_t& g = hp_.gates[gi];
       const bool is_y = g.type == QHBM_GATE_YPOW;
+      const bool grad_only = backward && a.tail && std::getenv("QHBM_NO_TAIL_SKIP") == nullptr;
+      if (grad_only && g.sym[0] < 0) return;  // nothing depends on this un-rotation
       DevOp o = make_op(is_y ? OP_YROT : OP_XROT);
       o.p0 = p;
+      o.aux0 = grad_only ? 1 : 0;  // 1: gradient inner product only (merge_rotations keeps it out of the rotation mask)
       o.coef = alloc_coef(4);  // (c, s, kappa, -)
       add_job(PJ_ROT, o.coef, backward ? 1 : 0, 0, 0, 0, {gi});
       if (backward) {

@@ -599,10 +599,10 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
     int step = 1;
     if (op.type() == OP_GD_BEGIN) step += op.aux0;
     switch (op.type()) {
-      case OP_XROTM: {
-        for_each_pos<K>([&](auto pc) {
+      case OP_XROTM: {  // p0: positions that are rotated; aux0: positions with a gradient (a superset for the
+        for_each_pos<K>([&](auto pc) {  // circuit's first gates, whose un-rotation nothing needs)
           constexpr int P = decltype(pc)::value;
-          if (op.p0() & (1 << P)) {
+          if ((op.p0() | (BOTH ? op.aux0 : 0)) & (1 << P)) {
             const float4 cs = ldg4(cf + 4 * P);  // (c, s, kappa, -)
             if constexpr (BOTH) {
               if (op.aux0 & (1 << P)) {
@@ -610,8 +610,10 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
                 scratch[slot * nthr + tid] = cs.z * im_bxa<K, P>(a, b);
               }
             }
-            xrot<K, P>(a, cs.x, cs.y);
-            if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
+            if (op.p0() & (1 << P)) {
+              xrot<K, P>(a, cs.x, cs.y);
+              if constexpr (BOTH) xrot<K, P>(b, cs.x, cs.y);
+            }
           }
         });
       } break;
@@ -638,7 +640,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
       case OP_YROTM: if constexpr (GEN) {
         for_each_pos<K>([&](auto pc) {
           constexpr int P = decltype(pc)::value;
-          if (op.p0() & (1 << P)) {
+          if ((op.p0() | (BOTH ? op.aux0 : 0)) & (1 << P)) {
             const float4 cs = ldg4(cf + 4 * P);
             if constexpr (BOTH) {
               if (op.aux0 & (1 << P)) {
@@ -646,8 +648,10 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
                 scratch[slot * nthr + tid] = cs.z * im_bya<K, P>(a, b);
               }
             }
-            yrot<K, P>(a, cs.x, cs.y);
-            if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
+            if (op.p0() & (1 << P)) {
+              yrot<K, P>(a, cs.x, cs.y);
+              if constexpr (BOTH) yrot<K, P>(b, cs.x, cs.y);
+            }
           }
         });
       } break;

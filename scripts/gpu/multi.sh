@@ -1,6 +1,6 @@
 #!/bin/bash
-# Multi-GPU session: usage multi.sh <N> <tag>.  Runs the N-rank NCCL tests (N >= 2) and the strong-scaling
-# bench lines of configs 3, 4 and 5 at every power of two up to N.
+# Multi-GPU session: usage multi.sh <N> <tag> [list of rank counts, default "1 2 4 8"].  Runs the 2-rank NCCL
+# tests (N >= 2) and the strong-scaling bench lines of configs 3, 4 and 5 at the listed rank counts <= N.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 N=$1; O=gpurun_out/${2:-multi$N}; mkdir -p $O
 nvidia-smi -L > $O/env.txt; nproc >> $O/env.txt
@@ -9,8 +9,8 @@ if [ "$N" -ge 2 ]; then
   tail -15 $O/pytest_gpu_multi.log
 fi
 P=29500
-for G in 1 2 4 8; do
-  [ "$G" -gt "$N" ] && break
+for G in ${3:-1 2 4 8}; do
+  [ "$G" -gt "$N" ] && continue
   for C in c3 c4 c5; do
     P=$((P+1))
     if [ "$G" -eq 1 ]; then
@@ -20,7 +20,7 @@ for G in 1 2 4 8; do
         bench.py --config $C --gpus $G --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_${C}_n$G.json 2> $O/bench_${C}_n$G.err
     fi
     echo "$C n=$G rc=$?" >> $O/env.txt
-    grep -h "NCCL INFO.*\(NVLS\|nranks\|Connected all\)" $O/bench_${C}_n$G.err 2>/dev/null | head -4 > $O/nccl_${C}_n$G.txt
+    grep -h "NCCL INFO" $O/bench_${C}_n$G.json 2>/dev/null | grep -i "nvls\|nranks" | head -6 > $O/nccl_${C}_n$G.txt
   done
 done
 for f in $O/bench_*.json; do echo "== $f"; python - "$f" <<'PY'

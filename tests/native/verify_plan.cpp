@@ -233,7 +233,8 @@ static void run_pass(Ctx& c, const LaunchDesc& L, int pi, std::vector<cplx>& tp,
           }
         } break;
         case OP_XROTM: case OP_YROTM: case OP_XROTF: {
-          for (int P = 0; P < K; ++P) if ((op.p0 & (1 << P)) || op.type == OP_XROTF) {
+          for (int P = 0; P < K; ++P) if (((op.p0 | (both ? op.aux0 : 0)) & (1 << P)) || op.type == OP_XROTF) {
+            const bool rotate = (op.p0 & (1 << P)) || op.type == OP_XROTF;  // else: gradient only
             double cc = c.coef[op.coef + 4 * P], ss = c.coef[op.coef + 4 * P + 1];
             const double kap = c.coef[op.coef + 4 * P + 2];
             if (op.type == OP_XROTF && c.coef[op.coef + 3] != 0.f && P < K - 1) { ss = cc; cc = 1.0; }  // (I - i t X)
@@ -250,7 +251,7 @@ static void run_pass(Ctx& c, const LaunchDesc& L, int pi, std::vector<cplx>& tp,
               }
               scratch[(size_t)(P < 4 ? ((op.aux1 >> (8 * P)) & 0xff) : op.p1) * nthr + tid] = kap * sacc;
             }
-            for (int which = 0; which < (both ? 2 : 1); ++which) {
+            for (int which = 0; rotate && which < (both ? 2 : 1); ++which) {
               std::vector<cplx>& v = which ? b : a;
               for (int r = 0; r < R; ++r) if (!(r & (1 << P))) {
                 cplx x0 = v[r], x1 = v[r | (1 << P)];

@@ -833,7 +833,8 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
       }
     }
   }
-  {
+  // (after the last gradient pass of a launch that stores nothing, no one reads the tiles again)
+  if (!(BOTH && last && !(ka.L.flags & (LF_STORE_PSI | LF_STORE_LAM)))) {
     const uint4* ep = reinterpret_cast<const uint4*>(ps->eoff8);
 #pragma unroll
     for (int i = 0; i < R / 4; ++i) {
@@ -929,8 +930,10 @@ __device__ __forceinline__ void run_hpass(const KernelArgs& ka, PassCtx& cx, con
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         a[4 * i + r] = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(s_psi) + (B8 ^ eo[r]));
-        if constexpr (BOTH)
-          b[4 * i + r] = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(s_lam) + (B8 ^ eo[r]));
+        if constexpr (BOTH) {  // the first observable pass starts h = H psi from zero (the lambda tile is not cleared)
+          b[4 * i + r] = first ? make_float2(0.f, 0.f)
+                               : *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(s_lam) + (B8 ^ eo[r]));
+        }
       }
     }
     float dsum = 0.f;
@@ -1424,11 +1427,6 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   if (flags & LF_EXPECT) {
     const bool hpasses = ka.L.pass_h_end > ka.L.pass_h_begin;
     if (hpasses) {
-      if constexpr (ADJ) {
-        const uint32_t pz = swz(threadIdx.x);
-#pragma unroll
-        for (int m = 0; m < (1 << K); ++m) s_lam[pz ^ ka.L.soff[m]] = make_float2(0.f, 0.f);
-      }
       for (int p = ka.L.pass_h_begin; p < ka.L.pass_h_end; ++p)
         run_hpass<K, ADJ>(ka, cx, p, p == ka.L.pass_h_begin, p + 1 == ka.L.pass_h_end, s_psi, s_lam, goff, u);
     }

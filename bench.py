@@ -670,12 +670,22 @@ def run_gpu_ebm(args, cfg, world, rank, local_rank, dev):
     b.record()
     sweep_evs.append((a, b))
   barrier()
+  # the sampling part alone (max, block + sub-block sums, scan, draw of this rank's share)
+  samp_evs = []
+  for i in range(args.steps):
+    flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    engine.categorical_sample(state["logits"], int(state["split"][rank]), (3, 4), first_sample=0, row_offset=lo)
+    b.record()
+    samp_evs.append((a, b))
+  barrier()
   clocks = sampler.stop() if rank == 0 else None
-  dev_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs), sum(a.elapsed_time(b) for a, b in sweep_evs)],
-                        dtype=torch.float64, device=dev)
+  dev_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs), sum(a.elapsed_time(b) for a, b in sweep_evs),
+                         sum(a.elapsed_time(b) for a, b in samp_evs)], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
-  ms_per_step, ms_sweep = (dev_ms / args.steps).tolist()
+  ms_per_step, ms_sweep, ms_sampling = (dev_ms / args.steps).tolist()
   value = rows / (ms_per_step / 1e3)
 
   # ---- end to end: weights from pinned host memory in, samples + log Z out, every step
@@ -743,7 +753,9 @@ def run_gpu_ebm(args, cfg, world, rank, local_rank, dev):
         "config": {"workload": cfg["label"], "rows": rows, "rows_per_gpu": hi - lo, "samples": n_samples,
                    "parallelism": f"row range sharded x{world}; all-gather of (max, sum exp, sum exp*l) per rank; "
                                   "rank-level multinomial split of the samples from the shared seed",
-                   "l2": "256 MiB buffer written between timed steps (untimed)", "ms_sweep_kernel": ms_sweep},
+                   "l2": "256 MiB buffer written between timed steps (untimed)", "ms_sweep_kernel": ms_sweep,
+                   "ms_sampling": ms_sampling,
+                   "sampling_logits_GBps": (hi - lo) * 4 * 2 / (ms_sampling / 1e3) / 1e9},
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf, "traffic": None,
                      "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 "

@@ -781,14 +781,21 @@ __global__ void __launch_bounds__(256) cat_max_kernel(const float* __restrict__ 
     else atomicMin(reinterpret_cast<unsigned int*>(a), __float_as_uint(m));
   }
 }
+// Block sums of exp(l - max) over 256 rows, plus the 8 sub-block sums over 32 rows each (`sub`): a sample
+// then scans 8 sub-block sums and at most 32 rows instead of up to 256 rows.  The block sum is the
+// sequential sum of its sub-block sums, the order the sample kernel repeats.
 __global__ void __launch_bounds__(kCatBlock) cat_blocksum_kernel(const float* __restrict__ logits, int64_t n,
-                                                                 const float* __restrict__ gmax, double* __restrict__ bsum) {
+                                                                 const float* __restrict__ gmax, double* __restrict__ bsum,
+                                                                 double* __restrict__ sub) {
   __shared__ double s_w[kCatBlock / 32];
   const int64_t i = (int64_t)blockIdx.x * kCatBlock + threadIdx.x;
   double v = i < n ? exp((double)logits[i] - (double)*gmax) : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  if ((threadIdx.x & 31) == 0) {
+    s_w[threadIdx.x >> 5] = v;
+    sub[(int64_t)blockIdx.x * (kCatBlock / 32) + (threadIdx.x >> 5)] = v;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
@@ -803,9 +810,12 @@ __global__ void __launch_bounds__(1024) cat_scan_kernel(double* __restrict__ bsu
   if (threadIdx.x == 0) s_carry = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int64_t b0 = 0; b0 < nblocks; b0 += 1024) {
-    const int64_t i = b0 + threadIdx.x;
-    const double f = i < nblocks ? bsum[i] : 0.0;
+  for (int64_t b0 = 0; b0 < nblocks; b0 += 4096) {  // four consecutive entries per thread
+    const int64_t i4 = b0 + 4 * (int64_t)threadIdx.x;
+    double f4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f4[k] = i4 + k < nblocks ? bsum[i4 + k] : 0.0;
+    const double f = ((f4[0] + f4[1]) + f4[2]) + f4[3];
     double v = f;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -825,7 +835,12 @@ __global__ void __launch_bounds__(1024) cat_scan_kernel(double* __restrict__ bsu
     }
     __syncthreads();
     const double incl = v + (wid ? s_w[wid - 1] : 0.0) + s_carry;
-    if (i < nblocks) bsum[i] = incl - f;
+    double run = incl - f;  // exclusive prefix of this thread's first entry
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i4 + k < nblocks) bsum[i4 + k] = run;
+      run += f4[k];
+    }
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = incl;
     __syncthreads();
@@ -833,7 +848,8 @@ __global__ void __launch_bounds__(1024) cat_scan_kernel(double* __restrict__ bsu
   if (threadIdx.x == 0) bsum[nblocks] = s_carry;
 }
 __global__ void cat_sample_kernel(const float* __restrict__ logits, int64_t n, const float* __restrict__ gmax,
-                                  const double* __restrict__ bpre, int64_t nblocks, uint64_t row_offset,
+                                  const double* __restrict__ bpre, const double* __restrict__ sub, int64_t nblocks,
+                                  uint64_t row_offset,
                                   uint64_t seed0, uint64_t seed1, uint64_t first, int64_t n_samples,
                                   uint64_t* __restrict__ out, double mass_begin, double mass_end, double mass_total) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -858,16 +874,23 @@ __global__ void cat_sample_kernel(const float* __restrict__ logits, int64_t n, c
   }
   const double m = (double)*gmax;
   double acc = bpre[lo];
-  const int64_t i0 = lo * kCatBlock, i1 = min(n, i0 + kCatBlock);
+  // the 32-row sub-block inside block lo (the last one if rounding pushed the target past the block)
+  int w = 0;
+  for (; w < kCatBlock / 32 - 1; ++w) {
+    const double sw = sub[lo * (kCatBlock / 32) + w];
+    if (target < acc + sw) break;
+    acc += sw;
+  }
+  const int64_t i0 = min(n - 1, lo * kCatBlock + 32 * (int64_t)w), i1 = min(n, lo * kCatBlock + 32 * (int64_t)(w + 1));
   int64_t pick = i1 - 1;
   int64_t last_pos = -1;
   for (int64_t i = i0; i < i1; ++i) {
-    const double w = exp((double)logits[i] - m);
-    if (w > 0.0) last_pos = i;
-    acc += w;
+    const double wt = exp((double)logits[i] - m);
+    if (wt > 0.0) last_pos = i;
+    acc += wt;
     if (target < acc) { pick = i; last_pos = -2; break; }
   }
-  if (last_pos >= 0) pick = last_pos;  // rounding pushed the target past the block: last positive weight
+  if (last_pos >= 0) pick = last_pos;  // rounding pushed the target past the sub-block: last positive weight
   out[k] = row_offset + (uint64_t)pick;
 }
 
@@ -1107,7 +1130,7 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
 int64_t qhbm_sample_workspace_bytes(int64_t n_rows) {
   if (n_rows < 0) return -1;
   const int64_t nblocks = (n_rows + kCatBlock - 1) / kCatBlock;
-  return 256 + 8 * (nblocks + 2);
+  return 256 + 8 * (nblocks + 2) + 8 * (kCatBlock / 32) * nblocks;  // max | block prefix + total | sub-block sums
 }
 
 static void cat_prepare(const float* d_logits, int64_t n_rows, bool use_given_max, float given_max, void* d_workspace,
@@ -1121,7 +1144,7 @@ static void cat_prepare(const float* d_logits, int64_t n_rows, bool use_given_ma
   QHBM_CUDA(cudaMemcpyAsync(gmax, &init, sizeof(float), cudaMemcpyHostToDevice, s));
   if (!use_given_max)
     cat_max_kernel<<<(unsigned)std::min<int64_t>((n_rows + 255) / 256, 148 * 8), 256, 0, s>>>(d_logits, n_rows, gmax);
-  cat_blocksum_kernel<<<(unsigned)nblocks, kCatBlock, 0, s>>>(d_logits, n_rows, gmax, bsum);
+  cat_blocksum_kernel<<<(unsigned)nblocks, kCatBlock, 0, s>>>(d_logits, n_rows, gmax, bsum, bsum + nblocks + 2);
   cat_scan_kernel<<<1, 1024, 0, s>>>(bsum, nblocks);
   QHBM_CUDA(cudaGetLastError());
 }
@@ -1134,7 +1157,7 @@ static void cat_draw(const float* d_logits, int64_t n_rows, uint64_t row_offset,
   const float* gmax = reinterpret_cast<const float*>(d_workspace);
   const double* bsum = reinterpret_cast<const double*>(reinterpret_cast<const char*>(d_workspace) + 256);
   const int64_t nblocks = (n_rows + kCatBlock - 1) / kCatBlock;
-  cat_sample_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, s>>>(d_logits, n_rows, gmax, bsum, nblocks, row_offset,
+  cat_sample_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, s>>>(d_logits, n_rows, gmax, bsum, bsum + nblocks + 2, nblocks, row_offset,
                                                                        seed0, seed1, first_sample, n_samples, d_samples,
                                                                        mass_begin, mass_end, mass_total);
   QHBM_CUDA(cudaGetLastError());

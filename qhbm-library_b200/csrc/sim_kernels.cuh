@@ -1142,6 +1142,7 @@ __device__ __forceinline__ bool uniform_coefficient(const DevTerm* terms, const 
 template <bool ADJ>
 constexpr bool kScalarGroups = !ADJ || QHBM_ADJ_SCALAR;
 
+
 template <int MC, bool CPLX, bool GLOBAL, bool SCALAR>
 __device__ __forceinline__ void group_offdiag(const KernelArgs& ka, const DevTerm* terms, const float2* s_psi,
                                               const float2* __restrict__ psi_u, float2 (&h)[MC],

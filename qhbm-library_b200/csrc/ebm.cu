@@ -461,10 +461,16 @@ __device__ __forceinline__ float mlp_act(float y, int act) {
   return y;
 }
 
+// Padded output width of layer l in shared memory: multiples of 8 for the register-tiled layers, unpadded
+// for the last layer (one output per row; the 2 KB this saves is what lets a fourth CTA fit on the SM).
+__host__ __device__ inline int mlp_out_pad(const qhbm_energy_desc_t& d, int l) {
+  const int out = d.widths[l + 1];
+  return l == d.n_layers - 1 ? out : ((out + 7) & ~7);
+}
 size_t mlp_sweep_weight_floats(const qhbm_energy_desc_t& d) {
   size_t f = 0;
   for (int l = 0; l < d.n_layers; ++l) {
-    const int out8 = (d.widths[l + 1] + 7) & ~7;
+    const int out8 = mlp_out_pad(d, l);
     f += (size_t)d.widths[l] * out8 + out8;
   }
   return f;
@@ -481,7 +487,7 @@ __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid
   int wfloats = 0;
   for (int l = 0; l < d.n_layers; ++l) {
     const int in = d.widths[l], out = d.widths[l + 1];
-    const int out8 = (out + 7) & ~7;
+    const int out8 = mlp_out_pad(d, l);
     for (int i = tid; i < in * out8; i += kMlpThreads) {
       const int r = i / out8, c = i - r * out8;
       s_f[wfloats + i] = c < out ? d.d_weights[l][r * out + c] : 0.f;
@@ -560,13 +566,16 @@ __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid
       const float* W = s_f + off;
       const float* Bv = W + in * out8;
       const bool mine = ty * 8 < out8;
-      float acc[8][8];
+      // Packed accumulators: acc2[r][jj] = outputs (2jj, 2jj+1) of row r.  One FFMA2 (sm_100 packed fp32: two
+      // independent round-to-nearest FMAs, the activation broadcast as an operand modifier) per pair, so a
+      // k-step is 32 issue slots for 64 FMAs and the loads / address updates issue in the FMA pipe's shadow.
+      float2 acc2[8][4];
       if (mine) {
         const float4 b0 = *reinterpret_cast<const float4*>(Bv + ty * 8), b1 = *reinterpret_cast<const float4*>(Bv + ty * 8 + 4);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
-          acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
+          acc2[r][0] = make_float2(b0.x, b0.y); acc2[r][1] = make_float2(b0.z, b0.w);
+          acc2[r][2] = make_float2(b1.x, b1.y); acc2[r][3] = make_float2(b1.z, b1.w);
         }
 #pragma unroll 2
         for (int k = 0; k < in; ++k) {
@@ -575,11 +584,12 @@ __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid
           const float4 w0 = *reinterpret_cast<const float4*>(W + k * out8 + ty * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(W + k * out8 + ty * 8 + 4);
           const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-          const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const float2 ws2[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                                 make_float2(w1.z, w1.w)};
 #pragma unroll
           for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(xs[r], ws[j], acc[r][j]);
+            for (int jj = 0; jj < 4; ++jj) acc2[r][jj] = __ffma2_rn(make_float2(xs[r], xs[r]), ws2[jj], acc2[r][jj]);
         }
       }
       __syncthreads();  // every thread has read its inputs: the buffer can take the outputs
@@ -588,10 +598,11 @@ __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float* o = buf + (ty * 8 + j) * kMlpRows + tx * 4;
-          *reinterpret_cast<float4*>(o) = make_float4(mlp_act(acc[0][j], act), mlp_act(acc[1][j], act),
-                                                      mlp_act(acc[2][j], act), mlp_act(acc[3][j], act));
-          *reinterpret_cast<float4*>(o + 64) = make_float4(mlp_act(acc[4][j], act), mlp_act(acc[5][j], act),
-                                                           mlp_act(acc[6][j], act), mlp_act(acc[7][j], act));
+          auto A = [&](int r) { return (j & 1) ? acc2[r][j >> 1].y : acc2[r][j >> 1].x; };
+          *reinterpret_cast<float4*>(o) = make_float4(mlp_act(A(0), act), mlp_act(A(1), act), mlp_act(A(2), act),
+                                                      mlp_act(A(3), act));
+          *reinterpret_cast<float4*>(o + 64) = make_float4(mlp_act(A(4), act), mlp_act(A(5), act), mlp_act(A(6), act),
+                                                           mlp_act(A(7), act));
         }
       }
       off += in * out8 + out8;
@@ -601,7 +612,7 @@ __global__ void __launch_bounds__(kMlpThreads) ebm_mlp_sweep_kernel(const __grid
     {
       const int l = d.n_layers - 1;
       const int in = d.widths[l];
-      const int out8 = (d.widths[l + 1] + 7) & ~7;
+      const int out8 = mlp_out_pad(d, l);
       const float* W = s_f + off;
       const uint64_t row = row0 + (uint64_t)tid;
       float e0 = W[in * out8], e1 = 0.f, e2 = 0.f, e3 = 0.f;
@@ -1109,7 +1120,7 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
                            sizeof(float) * kMaxWidth * kMlpRows;
       QHBM_CUDA(cudaFuncSetAttribute(ebm_mlp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
       const uint64_t ntiles = (hi - 1) / kMlpRows - lo / kMlpRows + 1;
-      blocks = (int)std::min<uint64_t>(ntiles, 148 * 3);
+      blocks = (int)std::min<uint64_t>(ntiles, 148 * 4);  // four 57 KB CTAs per SM
       ebm_mlp_sweep_kernel<<<blocks, kMlpThreads, msmem, s>>>(ea, lo, hi, d_logits, (Stat*)partial);
     } else if (e->kind != QHBM_ENERGY_MLP && big && (size_t)e->n_terms * 12 <= 200 * 1024) {
       // Walsh-Hadamard tiles of 256 rows: theta, masks and the bucket order in shared memory

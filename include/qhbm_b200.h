@@ -227,6 +227,9 @@ int qhbm_ebm_sweep(const qhbm_energy_desc_t* e, uint64_t lo, uint64_t hi, float*
 /* Replaces tfd.Categorical(logits).sample(N, seed) + gather (ebm.py:487-492) over
  * the local logits f32[n_rows]: inverse-CDF sampling with a counter-based Philox
  * stream keyed by (seed0, seed1, sample number).  Writes row indices (+ row_offset).
+ * qhbm_ebm_sweep chooses its kernel from 2^n_bits, never from hi - lo, so a sweep of a shard
+ * [lo, hi) writes the same logits, bit for bit, as a sweep of the whole range: rank-sharded
+ * sampling (below) reproduces the single-GPU draw exactly.
  * d_workspace: at least qhbm_sample_workspace_bytes(n_rows). */
 int64_t qhbm_sample_workspace_bytes(int64_t n_rows);
 int qhbm_categorical_sample(const float* d_logits, int64_t n_rows, uint64_t row_offset,
@@ -236,7 +239,9 @@ int qhbm_categorical_sample(const float* d_logits, int64_t n_rows, uint64_t row_
 
 /* The same sampler in two steps, for (a) many draws from unchanged logits and (b) a row range that is
  * sharded over ranks.
- *   qhbm_categorical_prepare: block prefix sums of exp(l - max) into d_workspace.  use_given_max != 0:
+ *   qhbm_categorical_prepare: prefix sums of exp(l - max) over blocks of 256 rows, plus the sums of their
+ *     eight 32-row sub-blocks, into d_workspace (a draw then scans 8 sums and at most 32 rows).
+ *     use_given_max != 0:
  *     `given_max` (the GLOBAL maximum from the merged sweep statistics) replaces the local maximum, which
  *     also saves the max pass over the logits.  The local mass sum_rows exp(l - max) is the float64 at
  *     byte offset 256 + 8 * ceil(n_rows / 256) of the workspace.

@@ -1172,6 +1172,13 @@ class Compiler {
       hp_.launches.push_back(L);
     }
     hp_.n_fwd_launches = (int)fs.size();
+    if (fs.size() >= 2 && std::getenv("QHBM_NO_SPARSE_INIT") == nullptr) {
+      LaunchDesc& first = hp_.launches[hp_.launches.size() - fs.size()];
+      LaunchDesc& second = hp_.launches[hp_.launches.size() - fs.size() + 1];
+      first.flags |= LF_SPARSE_OUT;
+      second.flags |= LF_SPARSE_IN;
+      second.sparse_mask = ~first.tile_mask & (hp_.n_eff >= 32 ? 0xffffffffu : ((1u << hp_.n_eff) - 1u));
+    }
     // The expectation phase needs the contiguous tile map.  When the first backward sweep uses the same
     // map it runs in the same launch: psi and lambda stay in shared memory instead of a round trip
     // through global memory.  psi then goes to the alternate buffer, because other tiles of this launch

@@ -149,6 +149,12 @@ enum LaunchFlags : uint32_t {
   LF_WRITE_STATE = 1u << 6, // debug: store psi into a caller buffer
   LF_PSI_ALT = 1u << 7,     // psi is stored into the alternate workspace buffer (other CTAs of this launch
                             // still read the old psi across tiles); later launches load from there
+  // After the first forward sweep the state is zero outside the tile that held the basis state.  That sweep
+  // does not store its all-zero tiles (their CTAs exit at once) and the next sweep does not load them: an
+  // amplitude whose out-of-first-tile index bits (`sparse_mask`) differ from the basis index is zero-filled
+  // without a memory access.  Halves the DRAM traffic of a forward computation with two sweeps.
+  LF_SPARSE_OUT = 1u << 8,
+  LF_SPARSE_IN = 1u << 9,
 };
 
 // One kernel launch = one sweep of one chunk of states.
@@ -166,6 +172,7 @@ struct LaunchDesc {
   int32_t rng_begin, rng_end;        // its slice of the observable ranges (DevOpRange)
   int32_t grp_begin, grp_end;        // that stage's slice of the group / term tables (staged in shared memory)
   int32_t term_begin, term_end;
+  uint32_t sparse_mask;              // LF_SPARSE_IN: state-index bits that must equal the basis index's
   // the thread's m-th tile element is local index (m << (T-K)) | tid:
   uint32_t moff[1 << kMaxRegQubits]; // its state-index contribution scatter(m << (T-K))
   uint16_t soff[1 << kMaxRegQubits]; // its swizzled smem contribution swz(m << (T-K))

@@ -1316,12 +1316,32 @@ __device__ __forceinline__ void expect_phase(const KernelArgs& ka, float2* s_psi
   }
 }
 
+// `sparse` != 0 (LF_SPARSE_IN, psi only): amplitudes whose index differs from `basis` in those bits are known
+// to be zero and were never stored: they are zero-filled without touching memory.
 template <int K>
-__device__ __forceinline__ void load_tile(float2* s, const float2* __restrict__ g, uint32_t goff, const KernelArgs& ka) {
+__device__ __forceinline__ void load_tile(float2* s, const float2* __restrict__ g, uint32_t goff, const KernelArgs& ka,
+                                          const uint32_t sparse = 0u, const uint32_t basis = 0u) {
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x;
   const uint32_t gt = goff | scatter_bits(tid, ka.L.runs, ka.L.n_runs);
   const uint32_t pt = swz(tid);
+  if (sparse) {
+    if (ka.async_tile) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const uint32_t gi = gt | ka.L.moff[m];
+        __pipeline_memcpy_async(s + (pt ^ ka.L.soff[m]), g + gi, 8, ((gi ^ basis) & sparse) ? 8 : 0);
+      }
+      __pipeline_commit();
+    } else {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const uint32_t gi = gt | ka.L.moff[m];
+        s[pt ^ ka.L.soff[m]] = ((gi ^ basis) & sparse) ? make_float2(0.f, 0.f) : g[gi];
+      }
+    }
+    return;
+  }
   if (ka.async_tile) {
     // Measured in profiles/r2_tile_copy_experiment.md: global -> shared without the register round trip,
     // 8-byte cp.async per amplitude (the nibble-XOR swizzle permutes amplitudes inside 128-byte groups, so a
@@ -1400,6 +1420,7 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   if (flags & LF_INIT_BASIS) {
     const uint32_t basis = (uint32_t)ka.basis[u];
     active = (basis & ~ka.L.tile_mask) == goff;
+    if (!active && (flags & LF_SPARSE_OUT)) return;  // an all-zero tile: the next sweep will not read it
     const uint32_t lb = gather_bits(basis, ka.L.runs, ka.L.n_runs);
     const uint32_t pt = swz(tid);
 #pragma unroll
@@ -1408,7 +1429,8 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
       s_psi[pt ^ ka.L.soff[m]] = make_float2((active && l == lb) ? 1.f : 0.f, 0.f);
     }
   } else if (flags & LF_LOAD_PSI) {
-    load_tile<K>(s_psi, psi_u, goff, ka);
+    if (flags & LF_SPARSE_IN) load_tile<K>(s_psi, psi_u, goff, ka, ka.L.sparse_mask, (uint32_t)ka.basis[u]);
+    else load_tile<K>(s_psi, psi_u, goff, ka);
   }
   if constexpr (ADJ) {
     if (flags & LF_LOAD_LAM) load_tile<K>(s_lam, lam_u, goff, ka);

@@ -400,9 +400,14 @@ static void run_launch(Ctx& c, LaunchDesc L, uint32_t basis, bool adjoint) {
     bool active = true;
     if (L.flags & LF_INIT_BASIS) {
       active = (basis & ~L.tile_mask) == goff;
+      if (!active && (L.flags & LF_SPARSE_OUT)) continue;  // the CTA exits: nothing is stored for this tile
       for (int l = 0; l < tsz; ++l) if (active && (goff | scatter(l, L.runs, L.n_runs)) == basis) tp[l] = 1;
     } else if (L.flags & LF_LOAD_PSI) {
-      for (int l = 0; l < tsz; ++l) tp[l] = c.psi[goff | scatter(l, L.runs, L.n_runs)];
+      for (int l = 0; l < tsz; ++l) {
+        const uint32_t gi = goff | scatter(l, L.runs, L.n_runs);
+        const bool zero = (L.flags & LF_SPARSE_IN) && ((gi ^ (uint32_t)basis) & L.sparse_mask);
+        tp[l] = zero ? cplx(0, 0) : c.psi[gi];
+      }
     }
     if (L.flags & LF_LOAD_LAM) for (int l = 0; l < tsz; ++l) tl[l] = c.lam[goff | scatter(l, L.runs, L.n_runs)];
     if (active) for (int p = L.pass_a_begin; p < L.pass_a_end; ++p) run_pass(c, L, p, tp, tl, goff, false);
@@ -478,7 +483,9 @@ int verify_run(const qhbm_gate_t* gates, int n_gates, int n, int P, const qhbm_p
     HostPlan hp = compile_plan(c, o, with_grad != 0, T, K);
     Ctx ctx; ctx.hp = &hp; ctx.dgrad = dgrad;
     prep(hp, symbols, mode, ctx.coef);
-    ctx.psi.assign((size_t)1 << hp.n_eff, 0); ctx.lam.assign((size_t)1 << hp.n_eff, 0);
+    // (the global state starts as NaN: a sweep that reads what an LF_SPARSE_OUT sweep did not store shows up)
+    ctx.psi.assign((size_t)1 << hp.n_eff, hp.tiles() > 1 ? cplx(NAN, NAN) : cplx(0, 0));
+    ctx.lam.assign((size_t)1 << hp.n_eff, 0);
     ctx.eacc.assign(O, 0); ctx.gacc.assign(std::max(P, 1), 0);
     for (size_t li = 0; li < hp.launches.size(); ++li) {
       LaunchDesc L = hp.launches[li];

@@ -118,7 +118,8 @@ void launch_any(const qhbm_plan* p, bool adj, const KernelArgs& ka, int n_states
   const int threads = 1 << (hp.T - hp.K);
   static const bool no_lean = std::getenv("QHBM_NO_LEAN") != nullptr;
   const auto launch = (hp.lean && !no_lean) ? launch_sweep_lean : launch_sweep_gen;
-  const unsigned grid = (unsigned)(n_states * hp.tiles());
+  // (the sparse first forward sweep only launches the one tile per state that holds its basis index)
+  const unsigned grid = (ka.L.flags & LF_SPARSE_OUT) ? (unsigned)n_states : (unsigned)(n_states * hp.tiles());
   // forward sweeps of an adjoint plan (psi only, no expectation phase, no backward passes) run on the dense
   // forward kernel: one tile of shared memory and ~80 registers instead of two tiles and 128
   const bool psi_only = !(ka.L.flags & (LF_EXPECT | LF_LOAD_LAM | LF_STORE_LAM | LF_WRITE_STATE)) &&

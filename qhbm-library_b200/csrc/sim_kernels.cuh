@@ -1394,9 +1394,12 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
   const uint32_t tshift = (uint32_t)(ka.n - ka.T);
-  const uint32_t u = blockIdx.x >> tshift;
-  const uint32_t tile = blockIdx.x & ((1u << tshift) - 1u);
-  const uint32_t goff = scatter_bits(tile, ka.L.oruns, ka.L.n_oruns);
+  // LF_SPARSE_OUT (first forward sweep of a multi-sweep computation): one CTA per state, on the tile that
+  // holds its basis index; the other tiles stay all-zero and are neither computed nor stored.
+  const bool one_tile = (ka.L.flags & LF_SPARSE_OUT) != 0u;
+  const uint32_t u = one_tile ? blockIdx.x : blockIdx.x >> tshift;
+  const uint32_t goff = one_tile ? ((uint32_t)ka.basis[u] & ~ka.L.tile_mask)
+                                 : scatter_bits(blockIdx.x & ((1u << tshift) - 1u), ka.L.oruns, ka.L.n_oruns);
   float2* psi_u = ka.psi ? ka.psi + ((size_t)u << ka.n) : nullptr;
   float2* lam_u = ka.lam ? ka.lam + ((size_t)u << ka.n) : nullptr;
   const uint32_t flags = ka.L.flags;
@@ -1420,7 +1423,7 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   if (flags & LF_INIT_BASIS) {
     const uint32_t basis = (uint32_t)ka.basis[u];
     active = (basis & ~ka.L.tile_mask) == goff;
-    if (!active && (flags & LF_SPARSE_OUT)) return;  // an all-zero tile: the next sweep will not read it
+    if (!active && (flags & LF_SPARSE_OUT)) return;  // (cannot happen: the grid only holds the active tiles)
     const uint32_t lb = gather_bits(basis, ka.L.runs, ka.L.n_runs);
     const uint32_t pt = swz(tid);
 #pragma unroll

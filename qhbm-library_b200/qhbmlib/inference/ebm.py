@@ -398,7 +398,14 @@ def energy_descriptor(energy):
   if hasattr(energy, "kernel_descriptor"):
     kind, masks, theta = energy.kernel_descriptor()
     dev = theta.device
-    masks_t = torch.tensor(masks, dtype=torch.int64, device=dev).to(torch.int32)
+    # the masks never change: one host -> device copy per (energy, device), not one per parameter update
+    cache = energy.__dict__.setdefault("_masks_dev_cache", {})
+    key = (str(dev), len(masks))
+    masks_t = cache.get(key)
+    if masks_t is None:
+      masks_t = torch.tensor(masks, dtype=torch.int64, device=dev).to(torch.int32)
+      cache.clear()
+      cache[key] = masks_t
     code = nat.ENERGY_BERNOULLI if kind == "bernoulli" else nat.ENERGY_KOBE
     return engine.EnergyDescriptor(code, energy.num_bits, masks_t, theta.detach().contiguous().float())
   layers = _mlp_layers(energy)

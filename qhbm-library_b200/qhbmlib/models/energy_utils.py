@@ -102,9 +102,14 @@ class Parity(torch.nn.Module):
     self.register_buffer("_member", member, persistent=False)
 
   def masks(self):
-    """Index-bit mask of each group for the CUDA energy kernels (column j <-> bit n-1-j)."""
-    n = self._num_bits
-    return [sum(1 << (n - 1 - j) for j in g) for g in self.indices]
+    """Index-bit mask of each group for the CUDA energy kernels (column j <-> bit n-1-j).  The groups never
+    change after construction, so the list is built once (it is asked for on every inference call)."""
+    cached = self.__dict__.get("_masks_cache")
+    if cached is None:
+      n = self._num_bits
+      cached = [sum(1 << (n - 1 - j) for j in g) for g in self.indices]
+      self.__dict__["_masks_cache"] = cached
+    return cached
 
   def forward(self, inputs):
     """Inputs are spins (+-1, any numeric dtype).  prod over a group = (-1)^{#(-1) in the group},

@@ -535,6 +535,7 @@ def run_gpu(args, cfg):
     sweep_launches = chunks * plan.info["launches"]
     achieved = total * bytes_per / (ms_per_step / 1e3) / 1e9 / world  # per GPU
     counters = ncu_counters(args.config)
+    dom = (counters or {}).get("dominant_launch", {}) if (counters or {}).get("current") else {}
     par = merge_parity([g for g in gathered if g is not None])
     if par is not None and fixture is not None and "loss" in fixture:
       # the whole-job count-weighted mean against the oracle's value over ALL bitstrings (float64)
@@ -561,6 +562,10 @@ def run_gpu(args, cfg):
                      "actual_limiter": "SM instruction issue (fp32 pipe): the state stays in shared memory / L2, "
                                        "so the HBM-equivalent frac exceeds 1 by on-chip reuse, not skipped work",
                      "sm_counters": counters,
+                     # the dominant launch's utilisation, flat (None unless the capture matches this build)
+                     "sm_issue_pct": dom.get("sm_issue_pct"), "fma_pipe_pct": dom.get("fma_pipe_pct"),
+                     "smem_pct": dom.get("smem_wavefronts_pct"), "lsu_pct": dom.get("lsu_wavefronts_pct"),
+                     "dram_pct": dom.get("dram_pct"),
                      "note": "achieved = algorithmic (6F+2) x 8 x 2^n bytes per bitstring / device time, per GPU; "
                              "sm_counters / traffic come from the ncu capture named in sm_counters.source and are "
                              "only quoted when sm_counters.current (same kernel source hash)"},

@@ -87,7 +87,7 @@ DevOp make_op(int type) {
 
 class Compiler {
  public:
-  explicit Compiler(HostPlan& hp) : hp_(hp) {}
+  explicit Compiler(HostPlan& hp, bool defer_tails = false) : hp_(hp), defer_tails_(defer_tails) {}
 
   int bit_of(int q) const { return hp_.n - 1 - q; }
 
@@ -291,11 +291,14 @@ class Compiler {
       while (remaining > 0) {
         // -- tentative scan: pick the register qubits
         RegAlloc ra(K);
+        bool placed_only_tails = true, outside_left = false;
         {
           Block blk(n);
           for (size_t ai = 0; ai < atoms.size(); ++ai) {
             if (done[ai]) continue;
             const Atom& a = atoms[ai];
+            if (!a.diag)
+              for (int i = 0; i < a.nq; ++i) outside_left = outside_left || local_of[a.bit[i]] < 0;
             if (!blk.ready(a)) { blk.block(a); continue; }
             if (a.diag) continue;
             bool ok = true;
@@ -304,12 +307,18 @@ class Compiler {
               RegAlloc trial = ra;
               ok = a.nq == 1 ? trial.place1(local_of[a.bit[0]])
                              : trial.place2(local_of[a.bit[0]], local_of[a.bit[1]]);
-              if (ok) ra = trial;
+              if (ok) { ra = trial; placed_only_tails = placed_only_tails && a.tail; }
             }
             if (!ok) blk.block(a);
           }
         }
         const bool have_nondiag = ra.nfree() < K;
+        // A further pass of this sweep that would only take gradients of the circuit's first gates (they are
+        // not un-applied, so nothing waits for them) is not worth its shared-memory round trip when another
+        // sweep follows anyway: those gates join that sweep's passes instead.
+        if (defer_tails_ && backward && (int)hp_.passes.size() > sw.pass_begin && have_nondiag && placed_only_tails &&
+            outside_left)
+          break;
         // pad the register set from the top of the tile
         for (int lb = Tloc - 1; lb >= 0 && ra.nfree() > 0; --lb)
           if (ra.pos_of(lb) < 0) ra.place1(lb);
@@ -382,8 +391,21 @@ class Compiler {
           const int ops_now = (int)hp_.ops.size() - ps.op_begin + rops;
           const int coef_now = hp_.ncoef - ps.coef_begin + rcoef + n_rot * (4 * K + 4);
           // (a gradient pass also stages its reduction tasks: <= 1 per float slot, <= 3 + 1 per diagonal op)
+          // coefficient floats the atom itself may add (its tables are in the constant headroom below):
+          // X/Y rotation 4 + a merged table; diagonal gate 8 per gradient; 2x2 block 8 + 8 per gradient;
+          // 4x4 block 32 + 32 per gradient
+          int own = 0;
+          for (int gi : a.gates) {
+            const qhbm_gate_t& g = hp_.gates[gi];
+            int nsym = 0;
+            for (int k = 0; k < g.nparams; ++k) nsym += g.sym[k] >= 0;
+            if (a.diag) own += 8 * nsym;
+            else if (a.nq == 2) own += 32 + 32 * nsym + 8;
+            else if (g.type == QHBM_GATE_XPOW || g.type == QHBM_GATE_YPOW) own += 4 + 4 * K + 4;
+            else own += 8 + 8 * nsym + 8;
+          }
           return ops_now + 6 * ng + 4 + (backward ? tasks_bound_ + 4 * ng + 1 : 0) <= stage_ops &&
-                 coef_now + 136 * ng + (2 << kConstGroupBits) + (4 << K) + (4 * K + 4) <= kStageCoef;
+                 coef_now + own + (2 << kConstGroupBits) + (4 << K) + (4 * K + 4) <= kStageCoef;
         };
         for (size_t ai = 0; ai < atoms.size(); ++ai) {
           if (done[ai]) continue;
@@ -1223,6 +1245,7 @@ class Compiler {
   std::vector<std::vector<int>> stage_bits_;  // tile map of every expectation stage
   std::vector<StageRange> stage_ranges_;
   bool no_hpass_ = std::getenv("QHBM_NO_HPASS") != nullptr;  // development switch: generic tables only
+  bool defer_tails_ = false;  // end a backward sweep instead of opening a pass of first-gate gradients only
   int units_ = 0;        // gradient scratch units committed by the pass being scheduled (flushed runs + float slots)
   int tasks_bound_ = 0;  // upper bound on the reduction tasks that pass will stage
 };
@@ -1465,8 +1488,26 @@ void lower_device_program(HostPlan& hp) {
 
 }  // namespace
 
+static HostPlan compile_plan_variant(const CircuitIR& c, const OpsIR& o, bool with_gradient, int tile_qubits,
+                                     int reg_qubits, bool defer_tails);
+
+// The scheduler has one heuristic whose benefit depends on the circuit: deferring passes that would only take
+// gradients of the circuit's first gates to the next backward sweep (Compiler::defer_tails_).  It saves a pass
+// when that sweep has register positions to spare (HEA(16, 2): 15 -> 14 passes) and costs a whole extra sweep
+// when it has not (HEA + inverse HEA).  Scheduling is milliseconds of host work, so both variants are
+// compiled and the one with fewer launches, then fewer passes, is kept.
 HostPlan compile_plan(const CircuitIR& c, const OpsIR& o, bool with_gradient, int tile_qubits,
                       int reg_qubits) {
+  HostPlan plain = compile_plan_variant(c, o, with_gradient, tile_qubits, reg_qubits, false);
+  if (!with_gradient || plain.tiles() == 1 || std::getenv("QHBM_NO_TAIL_DEFER") != nullptr) return plain;
+  HostPlan deferred = compile_plan_variant(c, o, with_gradient, tile_qubits, reg_qubits, true);
+  const bool better = deferred.launches.size() < plain.launches.size() ||
+                      (deferred.launches.size() == plain.launches.size() && deferred.passes.size() < plain.passes.size());
+  return better ? deferred : plain;
+}
+
+static HostPlan compile_plan_variant(const CircuitIR& c, const OpsIR& o, bool with_gradient, int tile_qubits,
+                                     int reg_qubits, bool defer_tails) {
   validate_circuit(c);
   validate_ops(o);
   if (c.n_qubits != o.n_qubits) throw std::runtime_error("circuit and observables act on different qubit counts");
@@ -1490,7 +1531,7 @@ HostPlan compile_plan(const CircuitIR& c, const OpsIR& o, bool with_gradient, in
   if (hp.K != 4 && hp.K != 5) throw std::runtime_error("reg_qubits must be 4 or 5");
   hp.T = std::min(T, hp.n_eff);
   hp.gates = c.gates;
-  Compiler comp(hp);
+  Compiler comp(hp, defer_tails);
   comp.compile(c, o);
   // Prefetch links and gradient-slot ranges.  Inside a launch's pass range the programs are consecutive
   // (pass i + 1 starts where pass i ends), which is what lets the kernel prefetch the next program from

@@ -22,7 +22,7 @@ def last_json(path):
 for c in ("c1", "c2", "c3q", "c3l7"):
   open(os.path.join(P, f"r2_bench_{c}_n1.json"), "w").write(last_json(os.path.join(D, f"bench_{c}.json")) + "\n")
 open(os.path.join(P, "r2_bench_reference_arm.json"), "w").write(last_json(os.path.join(D, "bench_ref.json")) + "\n")
-open(os.path.join(P, "r2_bench_c3_n1_with_cpu_baseline.json"), "w").write(last_json(os.path.join(D, "bench_c3.json")) + "\n")
+open(os.path.join(P, "r2_bench_c3_n1.json"), "w").write(last_json(os.path.join(D, "bench_c3.json")) + "\n")
 with open(os.path.join(P, "r2_bench_ebm_2p24.jsonl"), "w") as f:
   f.write("".join(l for l in open(os.path.join(D, "bench_ebm.txt")) if l.startswith("{")))
 with open(os.path.join(P, "r2_bench_api_vqt.txt"), "w") as f:

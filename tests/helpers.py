@@ -3,6 +3,7 @@ import ctypes
 import math
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -123,3 +124,29 @@ def verify_run(gates, n, nsym, ops, symbols, basis, dgrad, with_grad=True, T=0, 
     raise RuntimeError(lib.verify_last_error().decode())
   state = (st[0::2] + 1j * st[1::2])[:1 << n]
   return e, g[:nsym], state, info
+
+
+def dump_plan(gates, n, nsym, ops, with_grad=True, T=0, K=0):
+  """Text dump of the compiled plan (launches, passes, op histograms) from the TEST-ONLY verifier library;
+  the C code prints to stdout, which is captured through a temporary file descriptor."""
+  import tempfile
+  lib = verify_lib()
+  terms, offs = ops_to_tables(ops, n)
+  gates = np.ascontiguousarray(gates)
+  sys.stdout.flush()
+  with tempfile.TemporaryFile(mode="w+b") as tmp:
+    saved = os.dup(1)
+    try:
+      os.dup2(tmp.fileno(), 1)
+      rc = lib.verify_dump(ctypes.c_void_p(gates.ctypes.data), len(gates), n, nsym, ctypes.c_void_p(terms.ctypes.data),
+                           ctypes.c_void_p(offs.ctypes.data), len(ops), int(with_grad), T, K)
+      libc = ctypes.CDLL(None)
+      libc.fflush(None)
+    finally:
+      os.dup2(saved, 1)
+      os.close(saved)
+    tmp.seek(0)
+    text = tmp.read().decode()
+  if rc != 0:
+    raise RuntimeError(lib.verify_last_error().decode())
+  return text

@@ -559,8 +559,10 @@ def run_gpu(args, cfg):
                      "traffic": (counters or {}).get("dram_bytes_per_4096_bitstrings") if (counters or {}).get("current") else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_bitstring": bytes_per,
                      "sweep_kernel_launches_per_step": sweep_launches,
-                     "actual_limiter": "SM instruction issue (fp32 pipe): the state stays in shared memory / L2, "
-                                       "so the HBM-equivalent frac exceeds 1 by on-chip reuse, not skipped work",
+                     "actual_limiter": "on-chip latency at the occupancy the register file allows (16 warps/SM, 128 "
+                                       "registers): no unit is saturated (see sm_issue_pct / fma_pipe_pct / smem_pct); "
+                                       "the state stays in shared memory / L2, so the HBM-equivalent frac exceeds 1 "
+                                       "by on-chip reuse, not skipped work",
                      "sm_counters": counters,
                      # the dominant launch's utilisation, flat (None unless the capture matches this build)
                      "sm_issue_pct": dom.get("sm_issue_pct"), "fma_pipe_pct": dom.get("fma_pipe_pct"),

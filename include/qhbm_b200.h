@@ -132,6 +132,19 @@ int qhbm_expectation_adjoint(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_
                              float* d_grad_out, int32_t per_state, int32_t grad_mode,
                              void* stream);
 
+/* The same two operators with ONE ROW OF SYMBOL VALUES PER STATE: the general form of the TFQ ops
+ * (tfq_simulate_expectation / tfq_adjoint_gradient take symbol_values f32[U,P]; the reference always
+ * tiles one row, qnn.py:74-76, which is the f32[P] form above and the fast path).
+ *   d_symbol_rows f32[U,P]   row u holds the symbol values of state u
+ * The gate coefficient tables are built per state (chunks of at most 1 GiB of tables); everything else,
+ * including per_state / grad_mode and the outputs, is as in the shared-row entry points. */
+int qhbm_expectation_forward_rows(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_states,
+                                  const float* d_symbol_rows, float* d_out, void* stream);
+int qhbm_expectation_adjoint_rows(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_states,
+                                  const float* d_symbol_rows, const float* d_dgrad, float* d_out,
+                                  float* d_grad_out, int32_t per_state, int32_t grad_mode,
+                                  void* stream);
+
 /* Same two entry points with HOST buffers (pageable or pinned): copies in, runs,
  * copies out and synchronises `stream`.  This is the call a TF custom-op shim binds. */
 int qhbm_expectation_host(qhbm_plan_t* p, const uint64_t* h_basis_idx, int64_t n_states,
@@ -282,6 +295,28 @@ int qhbm_score_gradient(const uint64_t* d_keys, const int32_t* d_counts, int64_t
                         const float* d_average, const int32_t* d_masks, int32_t n_terms,
                         const double* d_total_count, float scale, float* d_grad_theta,
                         float* d_workspace, void* stream);
+
+/* ---------------------------------------------------------------- collective
+ * Replaces: the cross-replica sum behind utils.weighted_average (utils.py:43-58) when the unique
+ * bitstrings, or the 2^n energy sweep, are sharded one process per GPU.  The only data ever exchanged
+ * on the path is ONE small packed vector per step ([sum c<H_j> (O) | sum c | gradient (P) | score-function
+ * partials]), summed in place over the ranks of the communicator with ncclAllReduce on
+ * the caller's stream.  NCCL is bound at run time (libnccl.so.2 already in the process, else the system
+ * copy; QHBM_NCCL_LIB overrides), so single-GPU users never load it.
+ *   qhbm_comm_unique_id  rank 0 fills QHBM_COMM_ID_BYTES bytes and hands them to the other ranks by any
+ *                        out-of-band means (the Python side broadcasts them through torch.distributed)
+ *   qhbm_comm_create     collective over all ranks: communicator on the CURRENT device of the calling thread
+ *   qhbm_comm_adopt      wraps an ncclComm_t the caller already owns (never destroyed by the library)
+ *   qhbm_allreduce       d_buf[count] <- sum over ranks, in place, dtype QHBM_F32 or QHBM_F64 */
+#define QHBM_COMM_ID_BYTES 128
+enum { QHBM_F32 = 0, QHBM_F64 = 1 };
+typedef struct qhbm_comm qhbm_comm_t;
+int qhbm_comm_unique_id(uint8_t* out, int32_t out_bytes);
+int qhbm_comm_create(const uint8_t* id, int32_t rank, int32_t nranks, qhbm_comm_t** out);
+int qhbm_comm_adopt(void* nccl_comm, qhbm_comm_t** out);
+int qhbm_comm_info(const qhbm_comm_t* c, int32_t* rank, int32_t* nranks, int32_t* nccl_version);
+void qhbm_comm_destroy(qhbm_comm_t* c);
+int qhbm_allreduce(qhbm_comm_t* c, void* d_buf, int64_t count, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -186,22 +186,27 @@ void fill_common(const qhbm_plan* p, KernelArgs& ka) {
 }
 
 // Coefficient jobs + clearing of the call's float64 accumulators in one launch.
+// rows > 1: one coefficient table per symbol row (symbols f32[rows, P], tables coef_stride floats apart).
 void run_prep(qhbm_plan* p, const float* d_symbols, int mode, cudaStream_t s, double* zero_a = nullptr,
-              int64_t n_a = 0, double* zero_b = nullptr, int64_t n_b = 0) {
+              int64_t n_a = 0, double* zero_b = nullptr, int64_t n_b = 0, int rows = 1, uint32_t coef_stride = 0) {
   const HostPlan& hp = p->hp;
   const int n_jobs = (int)hp.jobs.size();
   const int64_t nz = n_a + n_b;
   const int zero_blocks = nz > 0 ? (int)std::min<int64_t>((nz + kPrepThreads - 1) / kPrepThreads, 148 * 4) : 0;
   if (n_jobs + zero_blocks == 0) return;
-  prep_kernel<<<(unsigned)(n_jobs + zero_blocks), kPrepThreads, 0, s>>>(p->d_jobs.p, n_jobs, p->d_lists.p, p->d_gates.p,
-                                                                       d_symbols, p->d_coef.p, mode, zero_a, n_a, zero_b, n_b);
+  const dim3 grid((unsigned)(n_jobs + zero_blocks), (unsigned)(n_jobs > 0 ? rows : 1));
+  prep_kernel<<<grid, kPrepThreads, 0, s>>>(p->d_jobs.p, n_jobs, p->d_lists.p, p->d_gates.p, d_symbols, p->d_coef.p, mode,
+                                            zero_a, n_a, zero_b, n_b, rows > 1 ? (uint32_t)hp.P : 0u,
+                                            rows > 1 ? coef_stride : 0u);
   QHBM_CUDA(cudaGetLastError());
 }
 
 // Core driver shared by the forward and adjoint entry points.
+// sym_rows: d_symbols is f32[U, P], one row of symbol values per state (the TFQ op's general form); the
+// coefficient tables are then built per state, chunk by chunk, and the sweeps read table u of the chunk.
 void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const float* d_symbols,
                      const float* d_dgrad, float* d_out, float* d_grad_out, int per_state, int mode,
-                     bool adjoint, cudaStream_t s) {
+                     bool adjoint, cudaStream_t s, bool sym_rows = false) {
   const HostPlan& hp = p->hp;
   if (adjoint && !hp.grad) throw std::runtime_error("plan was created without with_gradient");
   if (U < 0) throw std::runtime_error("n_states must be >= 0");
@@ -216,8 +221,13 @@ void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const flo
   p->d_eacc.reserve((size_t)U * hp.O);
   if (grows) p->d_gacc.reserve((size_t)std::max<int64_t>(1, grows * hp.P));
   // equal chunks no larger than the workspace allows (one chunk when everything fits)
-  const int64_t n_chunks = (U + p->chunk - 1) / p->chunk;
+  // (per-state tables: a chunk holds at most 1 GiB of them and fits the prep grid's y extent)
+  const uint32_t coef_stride = sym_rows ? (uint32_t)((std::max(hp.ncoef, 4) + 3) & ~3) : 0u;
+  const int64_t max_chunk = sym_rows ? std::min<int64_t>({(int64_t)p->chunk, 65535, std::max<int64_t>(1, ((int64_t)1 << 28) / coef_stride)})
+                                     : (int64_t)p->chunk;
+  const int64_t n_chunks = (U + max_chunk - 1) / max_chunk;
   const int chunk = (int)((U + n_chunks - 1) / n_chunks);
+  if (sym_rows) p->d_coef.reserve((size_t)chunk * coef_stride);
   bool pingpong = false;
   for (const LaunchDesc& L : hp.launches) pingpong = pingpong || (L.flags & LF_PSI_ALT);
   if (multi) {
@@ -225,15 +235,22 @@ void run_expectation(qhbm_plan* p, const uint64_t* d_basis, int64_t U, const flo
     if (adjoint) p->d_lam.reserve((size_t)chunk << hp.n_eff);
     if (adjoint && pingpong) p->d_psi_alt.reserve((size_t)chunk << hp.n_eff);
   }
-  run_prep(p, d_symbols, mode, s, p->d_eacc.p, U * hp.O, p->d_gacc.p, (grows && hp.P > 0) ? grows * hp.P : 0);
+  if (!sym_rows)
+    run_prep(p, d_symbols, mode, s, p->d_eacc.p, U * hp.O, p->d_gacc.p, (grows && hp.P > 0) ? grows * hp.P : 0);
 
   KernelArgs ka;
   fill_common(p, ka);
+  ka.coef_stride = coef_stride;
   ka.per_state = per_state;
   ka.gacc = p->d_gacc.p;
   // forward-only runs on an adjoint plan stop after the expectation launch
   for (int64_t u0 = 0; u0 < U; u0 += chunk) {
     const int c = (int)std::min<int64_t>(chunk, U - u0);
+    if (sym_rows) {  // this chunk's tables (the first chunk's launch also clears the call's accumulators)
+      const bool z = u0 == 0;
+      run_prep(p, d_symbols + u0 * hp.P, mode, s, z ? p->d_eacc.p : nullptr, z ? U * hp.O : 0, z ? p->d_gacc.p : nullptr,
+               (z && grows && hp.P > 0) ? grows * hp.P : 0, c, coef_stride);
+    }
     ka.basis = d_basis + u0;
     ka.dgrad = (adjoint && d_dgrad) ? d_dgrad + u0 * hp.O : nullptr;
     ka.eacc = p->d_eacc.p + u0 * hp.O;
@@ -435,6 +452,29 @@ int qhbm_expectation_adjoint(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_
     PlanUse use(p, (cudaStream_t)stream);
     run_expectation(p, d_basis_idx, n_states, d_symbols, d_dgrad, d_out, d_grad_out, per_state, grad_mode, true,
                     (cudaStream_t)stream);
+  });
+}
+
+int qhbm_expectation_forward_rows(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_states,
+                                  const float* d_symbol_rows, float* d_out, void* stream) {
+  return guarded([&] {
+    if (!p) throw std::runtime_error("null plan");
+    PlanUse use(p, (cudaStream_t)stream);
+    run_expectation(p, d_basis_idx, n_states, d_symbol_rows, nullptr, d_out, nullptr, 0, QHBM_GRAD_EXACT, false,
+                    (cudaStream_t)stream, true);
+  });
+}
+
+int qhbm_expectation_adjoint_rows(qhbm_plan_t* p, const uint64_t* d_basis_idx, int64_t n_states,
+                                  const float* d_symbol_rows, const float* d_dgrad, float* d_out,
+                                  float* d_grad_out, int32_t per_state, int32_t grad_mode, void* stream) {
+  return guarded([&] {
+    if (!p) throw std::runtime_error("null plan");
+    if (grad_mode < 0 || grad_mode > 2) throw std::runtime_error("bad grad_mode");
+    if (!d_dgrad) throw std::runtime_error("d_dgrad is null");
+    PlanUse use(p, (cudaStream_t)stream);
+    run_expectation(p, d_basis_idx, n_states, d_symbol_rows, d_dgrad, d_out, d_grad_out, per_state, grad_mode, true,
+                    (cudaStream_t)stream, true);
   });
 }
 

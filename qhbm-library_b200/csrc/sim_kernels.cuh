@@ -47,6 +47,8 @@ struct KernelArgs {
   int32_t async_tile;     // tiles are loaded with cp.async (default; QHBM_SYNC_TILE=1 turns it off)
   int32_t bulk_stage;     // pass programs are staged by the bulk-copy engine (cp.async.bulk + mbarrier; default;
                           // QHBM_NO_BULK_STAGE=1 restores the per-thread 16-byte copies)
+  uint32_t coef_stride;   // floats between the coefficient tables of consecutive states: 0 = one table shared by
+                          // all states (symbols f32[P]); else a multiple of 4 (symbols f32[U,P], one table per state)
 };
 
 // ---- bulk asynchronous copies (TMA engine, 1-D) completed through an mbarrier ----------------------
@@ -454,14 +456,14 @@ static_assert(sizeof(DevPass) % 16 == 0, "DevPass is copied in 16-byte pieces");
 // Copies pass p's program into stage buffer `buf`.  ASYNC: cp.async, completed by stage_wait().
 template <bool ASYNC>
 __device__ __forceinline__ void stage_program(const KernelArgs& ka, float4* buf, const int ops_cap, const int p,
-                                              const int op_begin, const int op_end, const int cb, const int ce) {
+                                              const int op_begin, const int op_end, const uint32_t cb, const int n_cf) {
   const int tid = (int)threadIdx.x, nthr = (int)blockDim.x;
   const float4* g_ps = reinterpret_cast<const float4*>(ka.passes + p);
   const float4* g_ops = reinterpret_cast<const float4*>(ka.ops + op_begin);
   const float4* g_cf = reinterpret_cast<const float4*>(ka.coef + cb);  // coefficient slots are 16-byte aligned
   float4* s_ops = buf + kPassF4;
   float4* s_cf = buf + kPassF4 + ops_cap;
-  const int n_ops = op_end - op_begin, n_cf = (ce - cb + 3) / 4;
+  const int n_ops = op_end - op_begin;
   if constexpr (ASYNC) {
     if (tid < kPassF4) __pipeline_memcpy_async(buf + tid, g_ps + tid, 16);
     for (int i = tid; i < n_ops; i += nthr) __pipeline_memcpy_async(s_ops + i, g_ops + i, 16);
@@ -477,9 +479,9 @@ __device__ __forceinline__ void stage_program(const KernelArgs& ka, float4* buf,
 // The same copy issued by ONE thread to the bulk-copy engine: three cp.async.bulk (descriptor, ops,
 // coefficients) that complete on the buffer's mbarrier.  Sizes are multiples of 16 bytes by construction.
 __device__ __forceinline__ void stage_program_bulk(const KernelArgs& ka, float4* buf, uint64_t* bar, const int ops_cap,
-                                                   const int p, const int op_begin, const int op_end, const int cb,
-                                                   const int ce) {
-  const uint32_t n_ops = (uint32_t)(op_end - op_begin), n_cf = (uint32_t)((ce - cb + 3) / 4);
+                                                   const int p, const int op_begin, const int op_end,
+                                                   const uint32_t cb, const uint32_t n_cf) {
+  const uint32_t n_ops = (uint32_t)(op_end - op_begin);
   mbar_expect_tx(bar, (uint32_t)sizeof(DevPass) + 16u * (n_ops + n_cf));
   bulk_g2s(buf, ka.passes + p, (uint32_t)sizeof(DevPass), bar);
   if (n_ops) bulk_g2s(buf + kPassF4, ka.ops + op_begin, 16u * n_ops, bar);
@@ -495,19 +497,23 @@ struct PassView {
   int op_begin, op_end;   // op_end = end of the per-thread ops (DevPass::exec_end); tasks follow up to task_end
   int task_end;
 };
+// cu: float offset of this state's coefficient table (0 unless the call has one row of symbols per state).
 __device__ __forceinline__ PassView begin_pass(const KernelArgs& ka, PassCtx& cx, const int p, const bool first,
-                                               const bool last) {
+                                               const bool last, const uint32_t cu) {
   const bool bulk = ka.bulk_stage != 0;
   if (first || !cx.dbuf) {
     __syncthreads();  // the previous phase is done with the tiles and the stage buffers
     const DevPass* gp = ka.passes + p;
     if (bulk) {
-      if (threadIdx.x == 0)
+      if (threadIdx.x == 0) {
+        const int cb0 = __ldg(&gp->coef_begin), ce0 = __ldg(&gp->coef_end);
         stage_program_bulk(ka, cx.stage + cx.buf * cx.stride(), cx.bars + cx.buf, cx.ops_cap, p, __ldg(&gp->op_begin),
-                           __ldg(&gp->op_end), __ldg(&gp->coef_begin), __ldg(&gp->coef_end));
+                           __ldg(&gp->op_end), cu + (uint32_t)cb0, (uint32_t)((ce0 - cb0 + 3) / 4));
+      }
     } else {
+      const int cb0 = __ldg(&gp->coef_begin), ce0 = __ldg(&gp->coef_end);
       stage_program<false>(ka, cx.stage + cx.buf * cx.stride(), cx.ops_cap, p, __ldg(&gp->op_begin), __ldg(&gp->op_end),
-                           __ldg(&gp->coef_begin), __ldg(&gp->coef_end));
+                           cu + (uint32_t)cb0, (ce0 - cb0 + 3) / 4);
     }
     if (ka.async_tile) __pipeline_wait_prior(0);  // cp.async tile loads of this thread (experiment switch)
   } else if (!bulk) {
@@ -532,10 +538,11 @@ __device__ __forceinline__ PassView begin_pass(const KernelArgs& ka, PassCtx& cx
       if (bulk) {
         if (threadIdx.x == 0)
           stage_program_bulk(ka, cx.stage + (cx.buf ^ 1) * cx.stride(), cx.bars + (cx.buf ^ 1), cx.ops_cap, p + 1,
-                             v.task_end, v.ps->next_op_end, v.ps->coef_end, v.ps->next_coef_end);
+                             v.task_end, v.ps->next_op_end, cu + (uint32_t)v.ps->coef_end,
+                             (uint32_t)((v.ps->next_coef_end - v.ps->coef_end + 3) / 4));
       } else {
         stage_program<true>(ka, cx.stage + (cx.buf ^ 1) * cx.stride(), cx.ops_cap, p + 1, v.task_end, v.ps->next_op_end,
-                            v.ps->coef_end, v.ps->next_coef_end);
+                            cu + (uint32_t)v.ps->coef_end, (v.ps->next_coef_end - v.ps->coef_end + 3) / 4);
       }
     }
     cx.buf ^= 1;
@@ -552,7 +559,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
                                          const bool last, float2* s_psi, float2* s_lam, uint32_t goff, uint32_t u) {
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-  const PassView pv = begin_pass(ka, cx, p, first, last);
+  const PassView pv = begin_pass(ka, cx, p, first, last, u * ka.coef_stride);
   const DevPass* ps = pv.ps;
   const int op_begin = pv.op_begin, op_end = pv.op_end;
   const PackedOp* ops_base = pv.ops;
@@ -813,7 +820,7 @@ __device__ __forceinline__ void run_pass(const KernelArgs& ka, PassCtx& cx, cons
           const bool ok_a = ca < 0 || ((goff >> ca) & 1u), ok_b = cb < 0 || ((goff >> cb) & 1u);
           const float2 tot = make_float2(G[i_tot], G[i_tot + 1]);
           const float2 A = ok_a ? make_float2(G[i_a], G[i_a + 1]) : make_float2(0.f, 0.f);
-          const float* m = ka.coef + d0.z;
+          const float* m = ka.coef + (size_t)u * ka.coef_stride + d0.z;
           const float4 m01 = __ldg(reinterpret_cast<const float4*>(m));
           if (kind == 1) {
             const float2 U0 = make_float2(tot.x - A.x, tot.y - A.y);
@@ -903,7 +910,7 @@ __device__ __forceinline__ void run_hpass(const KernelArgs& ka, PassCtx& cx, con
                                           uint32_t u) {
   constexpr int R = 1 << K;
   const uint32_t tid = threadIdx.x;
-  const PassView pv = begin_pass(ka, cx, p, first, last);
+  const PassView pv = begin_pass(ka, cx, p, first, last, u * ka.coef_stride);
   const DevPass* ps = pv.ps;
   const int op_begin = pv.op_begin, op_end = pv.op_end;
   const PackedOp* ops_base = pv.ops;
@@ -1447,7 +1454,7 @@ __global__ void __launch_bounds__(DENSE ? 256 : sweep_max_threads<K, ADJ>(), DEN
   if constexpr (!DENSE) {  // (the dense forward variant only ever runs plain forward sweeps)
   if (flags & LF_WRITE_STATE) {
     __syncthreads();
-    const float2 phase = ka.phase_coef >= 0 ? ldg2(ka.coef + ka.phase_coef) : one;
+    const float2 phase = ka.phase_coef >= 0 ? ldg2(ka.coef + (size_t)u * ka.coef_stride + ka.phase_coef) : one;
     store_tile<K>(s_psi, ka.state_out + ((size_t)u << ka.n), goff, ka, phase);
   }
   if (flags & LF_EXPECT) {
@@ -1486,15 +1493,21 @@ constexpr int kPrepThreads = 128;
 constexpr int kPrepBatch = 64;
 
 // CTAs [0, n_jobs) run one coefficient job each; the CTAs after them clear the float64 accumulators of
-// the call (so a call needs no separate memsets).
+// the call (so a call needs no separate memsets).  gridDim.y = number of symbol rows: row y reads
+// symbols + y * sym_stride and writes its table at coef + y * coef_stride (one row, strides 0, when all
+// states share the symbol values).
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const PrepJob* __restrict__ jobs, int n_jobs,
                                                             const int32_t* __restrict__ lists,
                                                             const qhbm_gate_t* __restrict__ gates,
                                                             const float* __restrict__ symbols,
                                                             float* __restrict__ coef, int mode,
                                                             double* __restrict__ zero_a, int64_t n_a,
-                                                            double* __restrict__ zero_b, int64_t n_b) {
+                                                            double* __restrict__ zero_b, int64_t n_b,
+                                                            uint32_t sym_stride, uint32_t coef_stride) {
+  symbols += (size_t)blockIdx.y * sym_stride;
+  coef += (size_t)blockIdx.y * coef_stride;
   if ((int)blockIdx.x >= n_jobs) {
+    if (blockIdx.y != 0) return;
     const int64_t stride = (int64_t)(gridDim.x - n_jobs) * kPrepThreads;
     for (int64_t i = (int64_t)(blockIdx.x - n_jobs) * kPrepThreads + threadIdx.x; i < n_a + n_b; i += stride) {
       if (i < n_a) zero_a[i] = 0.0;

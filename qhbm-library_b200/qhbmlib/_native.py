@@ -22,6 +22,7 @@ TERM_DTYPE = np.dtype([("coeff", np.float32), ("xmask", np.uint32), ("zmask", np
 
 GRAD_EXACT, GRAD_TFQ_FD, GRAD_TFQ_FD_F32 = 0, 1, 2
 ENERGY_BERNOULLI, ENERGY_KOBE, ENERGY_MLP = 0, 1, 2
+COMM_ID_BYTES = 128  # QHBM_COMM_ID_BYTES
 
 
 class EnergyDesc(ctypes.Structure):
@@ -55,6 +56,8 @@ SIGNATURES = {
     "qhbm_plan_info": (ctypes.c_int, [_VP, ctypes.POINTER(_I64)]),
     "qhbm_expectation_forward": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP]),
     "qhbm_expectation_adjoint": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, _I32, _VP]),
+    "qhbm_expectation_forward_rows": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP]),
+    "qhbm_expectation_adjoint_rows": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, _I32, _VP]),
     "qhbm_expectation_host": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP, _VP, _I32, _VP]),
     "qhbm_debug_state": (ctypes.c_int, [_VP, _U64, _VP, _VP, _VP]),
     "qhbm_final_states": (ctypes.c_int, [_VP, _VP, _I64, _VP, _VP, _VP]),
@@ -75,6 +78,12 @@ SIGNATURES = {
                                              _U64, _U64, _U64, _I64, _VP, _VP]),
     "qhbm_bernoulli_sample": (ctypes.c_int, [_VP, _I32, _VP, _U64, _U64, _U64, _I64, _VP, _VP]),
     "qhbm_weighted_sum": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP, _VP]),
+    "qhbm_comm_unique_id": (ctypes.c_int, [_VP, _I32]),
+    "qhbm_comm_create": (ctypes.c_int, [_VP, _I32, _I32, ctypes.POINTER(_VP)]),
+    "qhbm_comm_adopt": (ctypes.c_int, [_VP, ctypes.POINTER(_VP)]),
+    "qhbm_comm_info": (ctypes.c_int, [_VP, ctypes.POINTER(_I32), ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),
+    "qhbm_comm_destroy": (None, [_VP]),
+    "qhbm_allreduce": (ctypes.c_int, [_VP, _VP, _I64, _I32, _VP]),
 }
 
 

@@ -64,10 +64,82 @@ def unpack(packed, n_ops):
   return sums / total, total, grad
 
 
+class NativeComm:
+  """The C-ABI collective (`qhbm_comm_*`, `qhbm_allreduce`; include/qhbm_b200.h): the communicator a host
+  without torch would use.  Rank 0 draws the NCCL unique id, `torch.distributed` (any backend) hands it to the
+  other ranks, every rank joins on its current CUDA device.  `all_reduce_` sums a float32 / float64 CUDA
+  tensor in place over the ranks on torch's current stream."""
+
+  def __init__(self, group=None, rank=None, world_size=None, unique_id=None):
+    import ctypes
+    from qhbmlib import _native as nat
+    self._nat, self._handle = nat, ctypes.c_void_p()
+    if rank is None:
+      rank, world_size = world(group)
+    if unique_id is None:
+      ident = np.zeros(nat.COMM_ID_BYTES, dtype=np.uint8)
+      if rank == 0:
+        nat.check(nat.lib().qhbm_comm_unique_id(ident.ctypes.data, ident.size))
+      if world_size > 1:
+        box = [ident.tobytes()]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = np.frombuffer(box[0], dtype=np.uint8).copy()
+      unique_id = ident
+    unique_id = np.ascontiguousarray(unique_id, dtype=np.uint8)
+    if unique_id.size != nat.COMM_ID_BYTES:
+      raise ValueError(f"unique_id must hold {nat.COMM_ID_BYTES} bytes")
+    nat.check(nat.lib().qhbm_comm_create(unique_id.ctypes.data, int(rank), int(world_size), ctypes.byref(self._handle)))
+    self.rank, self.world_size = int(rank), int(world_size)
+
+  @property
+  def nccl_version(self):
+    import ctypes
+    v = ctypes.c_int32()
+    self._nat.check(self._nat.lib().qhbm_comm_info(self._handle, None, None, ctypes.byref(v)))
+    return int(v.value)
+
+  def all_reduce_(self, t):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+      raise TypeError("all_reduce_ needs a contiguous CUDA tensor")
+    if t.dtype not in (torch.float32, torch.float64):
+      raise TypeError("all_reduce_ sums float32 or float64 tensors")
+    from qhbmlib.engine import _stream
+    self._nat.check(self._nat.lib().qhbm_allreduce(self._handle, t.data_ptr(), t.numel(),
+                                                   0 if t.dtype == torch.float32 else 1, _stream()))
+    return t
+
+  def close(self):
+    if self._handle:
+      self._nat.lib().qhbm_comm_destroy(self._handle)
+      self._handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # interpreter shutdown
+      pass
+
+
+_native_comms = {}
+
+
+def native_comm(group=None):
+  """The process's NativeComm of `group` (created collectively on first use)."""
+  key = id(group) if group is not None else None
+  if key not in _native_comms:
+    _native_comms[key] = NativeComm(group)
+  return _native_comms[key]
+
+
 def all_reduce_packed(packed, group=None):
-  """The single collective of an expectation(+gradient) step."""
+  """The single collective of an expectation(+gradient) step.  QHBM_NATIVE_ALLREDUCE=1 routes it through the
+  library's own communicator (`qhbm_allreduce`) instead of torch.distributed's; the sums are the same."""
   if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    import os
+    if packed.is_cuda and os.environ.get("QHBM_NATIVE_ALLREDUCE") == "1":
+      native_comm(group).all_reduce_(packed)  # (packed comes from torch.cat: contiguous)
+    else:
+      dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
   return packed
 
 

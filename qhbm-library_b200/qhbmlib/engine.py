@@ -94,30 +94,42 @@ class ExpectationPlan:
     # int64 storage is reinterpreted as the uint64 the ABI names (indices are < 2^30)
     return _require_cuda(basis_idx, "basis_idx", torch.int64)
 
+  def _symbols(self, symbols, u):
+    """symbols f32[P] (one row shared by all states, the reference's case: qnn.py:74-76) or f32[U, P]
+    (one row per state, the TFQ op's general form).  Returns (tensor, has_rows)."""
+    symbols = _require_cuda(symbols, "symbols", torch.float32)
+    if symbols.dim() == 2:
+      if tuple(symbols.shape) != (u, self.n_symbols):
+        raise ValueError(f"per-state symbols must have shape {(u, self.n_symbols)}, got {tuple(symbols.shape)}")
+      return symbols, True
+    if symbols.numel() < self.n_symbols:
+      raise ValueError(f"symbols must have {self.n_symbols} entries, got {symbols.numel()}")
+    return symbols, False
+
   def forward(self, basis_idx, symbols):
     """f32[U, O] expectation values (TfqSimulateExpectation)."""
     basis_idx = self._basis(basis_idx)
-    symbols = _require_cuda(symbols, "symbols", torch.float32)
     u = basis_idx.shape[0]
+    symbols, rows = self._symbols(symbols, u)
     out = torch.empty((u, self.n_ops), dtype=torch.float32, device=basis_idx.device)
-    nat.check(nat.lib().qhbm_expectation_forward(self._plan, nat.ptr(basis_idx), u, nat.ptr(symbols),
-                                                 nat.ptr(out), _stream()))
+    fn = nat.lib().qhbm_expectation_forward_rows if rows else nat.lib().qhbm_expectation_forward
+    nat.check(fn(self._plan, nat.ptr(basis_idx), u, nat.ptr(symbols), nat.ptr(out), _stream()))
     return out
 
   def forward_adjoint(self, basis_idx, symbols, dgrad, per_state=False, grad_mode="exact"):
     """(f32[U,O], f32[P] or f32[U,P]): expectations and adjoint gradient (TfqAdjointGradient)."""
     basis_idx = self._basis(basis_idx)
-    symbols = _require_cuda(symbols, "symbols", torch.float32)
     dgrad = _require_cuda(dgrad, "dgrad", torch.float32)
     u = basis_idx.shape[0]
+    symbols, rows = self._symbols(symbols, u)
     if tuple(dgrad.shape) != (u, self.n_ops):
       raise ValueError(f"dgrad must have shape {(u, self.n_ops)}")
     out = torch.empty((u, self.n_ops), dtype=torch.float32, device=basis_idx.device)
     gshape = (u, self.n_symbols) if per_state else (self.n_symbols,)
     grad = torch.zeros(gshape, dtype=torch.float32, device=basis_idx.device)
-    nat.check(nat.lib().qhbm_expectation_adjoint(
-        self._plan, nat.ptr(basis_idx), u, nat.ptr(symbols), nat.ptr(dgrad), nat.ptr(out), nat.ptr(grad),
-        int(per_state), GRAD_MODES[grad_mode], _stream()))
+    fn = nat.lib().qhbm_expectation_adjoint_rows if rows else nat.lib().qhbm_expectation_adjoint
+    nat.check(fn(self._plan, nat.ptr(basis_idx), u, nat.ptr(symbols), nat.ptr(dgrad), nat.ptr(out), nat.ptr(grad),
+                 int(per_state), GRAD_MODES[grad_mode], _stream()))
     return out, grad
 
   def run_host(self, basis_idx, symbols, dgrad=None, grad_mode="exact", stream=None):

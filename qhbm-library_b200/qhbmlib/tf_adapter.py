@@ -41,7 +41,8 @@ def _to_tf(t):
 
 
 def expectation(plan, basis_idx, symbol_values, grad_mode="tfq_fd"):
-  """f32[U, O] expectations, differentiable w.r.t. `symbol_values` (f32[P]) under tf.GradientTape.
+  """f32[U, O] expectations, differentiable w.r.t. `symbol_values` (f32[P], or f32[U, P] with one row per
+  state) under tf.GradientTape.
   `plan` is a qhbmlib.engine.ExpectationPlan; `basis_idx` an int64 GPU tensor [U]."""
   if tf is None:
     raise ImportError("TensorFlow is required for qhbmlib.tf_adapter")
@@ -54,7 +55,8 @@ def expectation(plan, basis_idx, symbol_values, grad_mode="tfq_fd"):
 
     def grad(upstream):
       up = _to_torch(tf.identity(upstream)).to(torch.float32).contiguous()
-      _, g = plan.forward_adjoint(basis, vals, up, per_state=False, grad_mode=grad_mode)
+      # symbol_values f32[U, P] (one row per state, the TFQ op's own signature): gradient f32[U, P] as well
+      _, g = plan.forward_adjoint(basis, vals, up, per_state=vals.dim() == 2, grad_mode=grad_mode)
       return _to_tf(g)
 
     return _to_tf(out), grad

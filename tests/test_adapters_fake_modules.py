@@ -67,9 +67,12 @@ class _FakePlan:
     return values.sum() * u[:, None] * j[None, :]
 
   def forward_adjoint(self, basis, values, upstream, per_state=False, grad_mode="exact"):
-    assert not per_state and grad_mode in ("exact", "tfq_fd")
+    assert grad_mode in ("exact", "tfq_fd") and per_state == (values.dim() == 2)
     u = basis.to(torch.float32) + 1.0
     j = torch.arange(1, self.n_ops + 1, dtype=torch.float32)
+    if per_state:  # rows of symbol values: <op_j>_u = sum_p phi_up (u + 1)(j + 1)
+      g = (upstream * u[:, None] * j[None, :]).sum(1, keepdim=True) * torch.ones_like(values)
+      return values.sum(1)[:, None] * u[:, None] * j[None, :], g
     g = (upstream * u[:, None] * j[None, :]).sum() * torch.ones_like(values)
     return self.forward(basis, values), g
 
@@ -92,6 +95,12 @@ def test_tf_adapter_runs_against_a_fake_tensorflow(monkeypatch):
     np.testing.assert_allclose(g.t.numpy(), np.full(3, 18.0))  # sum_u (u+1) sum_j (j+1) = 6 * 3
     # inputs crossed as consumed DLPack capsules, outputs were allocated on the adapter's side
     assert fake._calls["to_dlpack"] == 3 and fake._calls["from_dlpack"] == 2 and fake._calls["identity"] == 1
+    # one row of symbol values per state: the gradient keeps the [U, P] shape of the TFQ op
+    rows = _FakeTFTensor(torch.tensor([[0.5, -0.25, 1.0]]).repeat(3, 1))
+    out_r = adapter.expectation(_FakePlan(), basis, rows, grad_mode="tfq_fd")
+    g_r = out_r.grad_fn(upstream)
+    assert g_r.shape == (3, 3)
+    np.testing.assert_allclose(g_r.t.numpy(), np.outer([3.0, 6.0, 9.0], np.ones(3)))
   finally:
     monkeypatch.delitem(sys.modules, "tensorflow")
     importlib.reload(adapter)

@@ -29,6 +29,25 @@ def test_c_abi_library_exports_every_declared_symbol():
   assert lib.qhbm_version() >= 100
 
 
+def test_collective_entry_points_bind_nccl_at_run_time_and_validate():
+  """qhbm_comm_unique_id works without a GPU (it only needs libnccl.so.2); bad arguments come back as status 1
+  with a message, before NCCL is touched."""
+  import ctypes
+  lib = nat.lib()
+  a, b = np.zeros(nat.COMM_ID_BYTES, np.uint8), np.zeros(nat.COMM_ID_BYTES, np.uint8)
+  nat.check(lib.qhbm_comm_unique_id(a.ctypes.data, a.size))
+  nat.check(lib.qhbm_comm_unique_id(b.ctypes.data, b.size))
+  assert a.any() and (a != b).any()
+  assert lib.qhbm_comm_unique_id(a.ctypes.data, 64) == 1
+  assert b"QHBM_COMM_ID_BYTES" in lib.qhbm_last_error()
+  handle = ctypes.c_void_p()
+  assert lib.qhbm_comm_create(a.ctypes.data, 2, 2, ctypes.byref(handle)) == 1
+  assert b"rank out of range" in lib.qhbm_last_error()
+  assert lib.qhbm_allreduce(None, None, 4, 0, None) == 1
+  assert b"null communicator" in lib.qhbm_last_error()
+  lib.qhbm_comm_destroy(None)  # a null handle is ignored
+
+
 def test_no_cuda_device_fails_loudly():
   if torch.cuda.is_available():
     pytest.skip("needs a machine without a GPU")

@@ -423,3 +423,75 @@ def test_adjoint_in_small_chunks_matches_one_chunk(n, ham, monkeypatch):
                                                     dg.cpu().numpy())
   _check(e1.cpu().numpy(), e_ref, FLOOR * _scale(ops)[None, :], "chunked expectations")
   _check(g1.cpu().numpy(), g_ref, FLOOR * np.abs(dg.cpu().numpy()) * _scale(ops).max(), "chunked per-state gradient")
+
+
+# ------------------------------------------------------------------ one row of symbol values per state
+def _compare_rows(gates, n, nsym, ops, rng, n_states, T=0, K=0, mode="exact"):
+  """symbols f32[U, P] (tfq_simulate_expectation / tfq_adjoint_gradient's general form): state u is simulated
+  with row u; oracle = one single-state call per row."""
+  plan = _plan(gates, n, nsym, ops, True, T, K)
+  basis = rng.choice(1 << n, size=min(n_states, 1 << n), replace=False).astype(np.int64)
+  u = len(basis)
+  phi = rng.uniform(-1, 1, (u, nsym)).astype(np.float32)
+  dg = rng.uniform(-1, 1, (u, len(ops))).astype(np.float32)
+  e_ref = np.zeros((u, len(ops)))
+  g_ref = np.zeros((u, nsym))
+  for i in range(u):
+    e1, g1 = orc.batch_expectation_and_gradient(gates, n, phi[i], basis[i:i + 1], ops, dg[i:i + 1], mode)
+    e_ref[i], g_ref[i] = e1[0], g1[0]
+  d_phi, d_basis, d_dg = (torch.tensor(a, device="cuda") for a in (phi, basis, dg))
+  scale = _scale(ops)
+  gfloor_state = FLOOR * (np.abs(dg) * scale[None, :]).sum(1)
+  _check(plan.forward(d_basis, d_phi).cpu().numpy(), e_ref, FLOOR * scale[None, :], "forward, symbol rows")
+  e, gp = plan.forward_adjoint(d_basis, d_phi, d_dg, per_state=True, grad_mode=mode)
+  _check(e.cpu().numpy(), e_ref, FLOOR * scale[None, :], "expectations, symbol rows")
+  _check(gp.cpu().numpy(), g_ref, gfloor_state[:, None], "per-state gradient, symbol rows")
+  _, g = plan.forward_adjoint(d_basis, d_phi, d_dg, grad_mode=mode)
+  _check(g.cpu().numpy(), g_ref.sum(0), gfloor_state.sum(), "reduced gradient, symbol rows")
+  return plan, d_basis, d_phi, d_dg
+
+
+@pytest.mark.parametrize("n,layers,T,K,mode", [(4, 2, 0, 4, "exact"), (10, 2, 10, 5, "tfq_fd"), (12, 2, 9, 4, "exact"),
+                                                (13, 2, 0, 0, "exact"), (16, 2, 0, 0, "tfq_fd")])
+def test_symbol_rows_hea(n, layers, T, K, mode):
+  rng = np.random.default_rng(300 + n)
+  gates, names = orc.hea_circuit(n, layers)
+  ops = [orc.xxz_ring(n), orc.tfim_ring(n)] if n < 16 else [orc.xxz_ring(n)]
+  _compare_rows(gates, n, len(names), ops, rng, 6 if n < 16 else 3, T, K, mode)
+
+
+@pytest.mark.parametrize("seed", range(3))
+@pytest.mark.parametrize("n,T,K", [(5, 0, 5), (11, 9, 4), (13, 12, 4)])
+def test_symbol_rows_all_gate_types(seed, n, T, K):
+  rng = np.random.default_rng(7000 * n + seed)
+  gates = hp.random_circuit(n, 24, 5, rng)
+  _compare_rows(gates, n, 5, hp.random_ops(n, 2, rng), rng, 5, T, K)
+
+
+def test_symbol_rows_equal_rows_match_shared_row(monkeypatch):
+  """U identical rows give the results of the shared-row call (same tables, same sweeps), also when
+  the call is split into several chunks of tables (QHBM_CHUNK)."""
+  from qhbmlib import engine
+  n = 14
+  rng = np.random.default_rng(14)
+  gates, names = orc.hea_circuit(n, 2)
+  terms, offs = hp.ops_to_tables([orc.xxz_ring(n)], n)
+  phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+  basis = torch.tensor(rng.choice(1 << n, 37, replace=False).astype(np.int64), device="cuda")
+  dg = torch.tensor(rng.uniform(-1, 1, (37, 1)).astype(np.float32), device="cuda")
+  rows = phi[None, :].repeat(37, 1).contiguous()
+  for chunk in (None, "8"):
+    if chunk:
+      monkeypatch.setenv("QHBM_CHUNK", chunk)
+    plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, True)
+    def same(x, y):  # (float64 atomics of the tiles of a state arrive in any order: last-bit differences)
+      np.testing.assert_allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=2e-6, atol=2e-7)
+    e0, g0 = plan.forward_adjoint(basis, phi, dg, per_state=True)
+    e1, g1 = plan.forward_adjoint(basis, rows, dg, per_state=True)
+    same(e0, e1), same(g0, g1)
+    same(plan.forward(basis, phi), plan.forward(basis, rows))
+    # and the shared-row path still works on the plan after its table buffer grew
+    e2, g2 = plan.forward_adjoint(basis, phi, dg, per_state=True)
+    same(e0, e2), same(g0, g2)
+  with pytest.raises(ValueError, match="per-state symbols"):
+    plan.forward(basis, rows[:5])

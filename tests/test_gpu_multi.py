@@ -67,9 +67,24 @@ def _worker(rank, world_size, port, out_dir):
     rows = engine.categorical_sample(logits, int(split[rank]), (7, 8 + rank), row_offset=lo)
     hist = torch.bincount(rows, minlength=1 << n_bits).double()
     dist.all_reduce(hist)
+    # the library's own collective (qhbm_comm_* / qhbm_allreduce) against torch.distributed's
+    comm = qd.NativeComm()
+    probe64 = torch.arange(97, dtype=torch.float64, device=dev) * (rank + 1) + 0.25 * rank
+    probe32 = torch.arange(5, dtype=torch.float32, device=dev) - rank
+    want64, want32 = probe64.clone(), probe32.clone()
+    dist.all_reduce(want64), dist.all_reduce(want32)
+    comm.all_reduce_(probe64), comm.all_reduce_(probe32)
+    native_ok = bool(torch.equal(probe64, want64) and torch.equal(probe32, want32) and comm.world_size == world_size)
+    os.environ["QHBM_NATIVE_ALLREDUCE"] = "1"
+    avg_n, total_n, grad_n = sharded(torch.tensor(basis, device=dev), torch.tensor(counts, device=dev),
+                                     torch.tensor(phi, device=dev), grad_mode="exact")
+    del os.environ["QHBM_NATIVE_ALLREDUCE"]
+    torch.cuda.synchronize()
+    comm.close()
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), avg=avg.cpu().numpy(), total=float(total), grad=grad.cpu().numpy(),
              log_z=log_z, entropy=entropy, split=split, hist=hist.cpu().numpy(), lo=lo, hi=hi,
-             rows_min=int(rows.min()), rows_max=int(rows.max()))
+             rows_min=int(rows.min()), rows_max=int(rows.max()), native_ok=native_ok, avg_n=avg_n.cpu().numpy(),
+             grad_n=grad_n.cpu().numpy(), total_n=float(total_n))
   finally:
     dist.destroy_process_group()
 
@@ -81,6 +96,13 @@ def test_two_gpu_sharded_expectation_and_ebm_sweep(tmp_path):
   r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
   for key in ("avg", "total", "grad", "log_z", "entropy", "split", "hist"):
     np.testing.assert_array_equal(r0[key], r1[key])  # identical on every rank after the collectives
+  # qhbm_allreduce (the library's own NCCL communicator) gives torch.distributed's sums, alone and behind the
+  # sharded expectation (the per-rank partial sums may differ in their last float64 bit between two runs: atomics)
+  assert bool(r0["native_ok"]) and bool(r1["native_ok"])
+  np.testing.assert_allclose(r0["avg_n"], r0["avg"], rtol=1e-6, atol=1e-7)
+  np.testing.assert_allclose(r0["grad_n"], r0["grad"], rtol=1e-6, atol=1e-7)
+  np.testing.assert_array_equal(r0["avg_n"], r1["avg_n"])
+  assert float(r0["total_n"]) == float(r0["total"])
   n, gates, names, phi, basis, counts, ops, n_bits, thetas = _inputs()
   dg = np.tile((counts / counts.sum())[:, None], (1, 2))
   e, g = orc.batch_expectation_and_gradient(gates, n, phi, basis, ops, dg)

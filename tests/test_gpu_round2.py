@@ -289,3 +289,25 @@ def test_shard_sweeps_reproduce_the_full_sweep_bit_for_bit(kind):
       triples.append(st.cpu().tolist())
     m, s, _ = qd.merge_log_stats(triples)
     np.testing.assert_allclose(m + math.log(s), log_z, rtol=1e-6)
+
+
+def test_native_communicator_of_one_rank():
+  """qhbm_comm_create / qhbm_allreduce on a one-rank communicator: NCCL binds at run time, the in-place sum of one
+  rank is the identity for both dtypes, on torch's current stream."""
+  from qhbmlib import distributed as qd
+  comm = qd.NativeComm(rank=0, world_size=1)
+  assert (comm.rank, comm.world_size) == (0, 1) and comm.nccl_version >= 22000
+  x64 = torch.linspace(-3, 3, 97, dtype=torch.float64, device="cuda")
+  x32 = torch.arange(1000, dtype=torch.float32, device="cuda")
+  w64, w32 = x64.clone(), x32.clone()
+  side = torch.cuda.Stream()
+  side.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(side):
+    comm.all_reduce_(x64)
+  comm.all_reduce_(x32)
+  side.synchronize()
+  torch.cuda.synchronize()
+  assert torch.equal(x64, w64) and torch.equal(x32, w32)
+  with pytest.raises(TypeError, match="float32 or float64"):
+    comm.all_reduce_(torch.zeros(3, dtype=torch.int32, device="cuda"))
+  comm.close()

@@ -171,8 +171,8 @@ def kernel_source_sha():
   h = hashlib.sha256()
   csrc = os.path.join(ROOT, "qhbm-library_b200", "csrc")
   # the sources that compile into the state-vector kernels and their plans (the counters are of sweep_kernel);
-  # the EBM-side, measurement and collective translation units do not change them
-  other = {"ebm.cu", "measure.cu", "comm.cu", "philox.h"}
+  # the EBM-side, measurement, collective and coefficient-preparation sources do not change them
+  other = {"ebm.cu", "measure.cu", "comm.cu", "philox.h", "prep_kernels.cuh"}
   for f in sorted(os.listdir(csrc)):
     if not os.path.isfile(os.path.join(csrc, f)) or f.startswith(".") or f in other:
       continue

@@ -194,9 +194,9 @@ void run_prep(qhbm_plan* p, const float* d_symbols, int mode, cudaStream_t s, do
   const int64_t nz = n_a + n_b;
   const int zero_blocks = nz > 0 ? (int)std::min<int64_t>((nz + kPrepThreads - 1) / kPrepThreads, 148 * 4) : 0;
   if (n_jobs + zero_blocks == 0) return;
-  const dim3 grid((unsigned)(n_jobs + zero_blocks), (unsigned)(n_jobs > 0 ? rows : 1));
+  const dim3 grid((unsigned)(n_jobs + zero_blocks), (unsigned)((n_jobs > 0 && rows > 1) ? (rows + kPrepRows - 1) / kPrepRows : 1));
   prep_kernel<<<grid, kPrepThreads, 0, s>>>(p->d_jobs.p, n_jobs, p->d_lists.p, p->d_gates.p, d_symbols, p->d_coef.p, mode,
-                                            zero_a, n_a, zero_b, n_b, rows > 1 ? (uint32_t)hp.P : 0u,
+                                            zero_a, n_a, zero_b, n_b, rows, rows > 1 ? (uint32_t)hp.P : 0u,
                                             rows > 1 ? coef_stride : 0u);
   QHBM_CUDA(cudaGetLastError());
 }

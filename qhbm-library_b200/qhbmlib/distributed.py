@@ -114,13 +114,22 @@ class NativeComm:
       self._handle = None
 
   def __del__(self):
+    import sys
+    if sys.is_finalizing():  # the CUDA context may already be gone: leave the communicator to process exit
+      return
     try:
       self.close()
-    except Exception:  # interpreter shutdown
+    except Exception:
       pass
 
 
 _native_comms = {}
+
+
+def close_native_comms():
+  """Destroys the communicators `native_comm` created (call before `destroy_process_group`)."""
+  while _native_comms:
+    _native_comms.popitem()[1].close()
 
 
 def native_comm(group=None):

@@ -19,15 +19,22 @@ def last_json(path):
 
 
 # ---- bench lines
+have = lambda n: os.path.exists(os.path.join(D, n))  # (a reduced session only re-measures what changed)
 for c in ("c1", "c2", "c3q", "c3l7"):
-  open(os.path.join(P, f"r2_bench_{c}_n1.json"), "w").write(last_json(os.path.join(D, f"bench_{c}.json")) + "\n")
-open(os.path.join(P, "r2_bench_reference_arm.json"), "w").write(last_json(os.path.join(D, "bench_ref.json")) + "\n")
+  if have(f"bench_{c}.json"):
+    open(os.path.join(P, f"r2_bench_{c}_n1.json"), "w").write(last_json(os.path.join(D, f"bench_{c}.json")) + "\n")
+if have("bench_ref.json"):
+  open(os.path.join(P, "r2_bench_reference_arm.json"), "w").write(last_json(os.path.join(D, "bench_ref.json")) + "\n")
 open(os.path.join(P, "r2_bench_c3_n1.json"), "w").write(last_json(os.path.join(D, "bench_c3.json")) + "\n")
-with open(os.path.join(P, "r2_bench_ebm_2p24.jsonl"), "w") as f:
-  f.write("".join(l for l in open(os.path.join(D, "bench_ebm.txt")) if l.startswith("{")))
-with open(os.path.join(P, "r2_bench_api_vqt.txt"), "w") as f:
-  for n in ("bench_api_500.txt", "bench_api_100k.txt"):
-    f.write("".join(l for l in open(os.path.join(D, n)) if l.startswith("VQT")))
+if have("bench_ebm.txt"):
+  with open(os.path.join(P, "r2_bench_ebm_2p24.jsonl"), "w") as f:
+    f.write("".join(l for l in open(os.path.join(D, "bench_ebm.txt")) if l.startswith("{")))
+if have("bench_api_500.txt"):
+  with open(os.path.join(P, "r2_bench_api_vqt.txt"), "w") as f:
+    for n in ("bench_api_500.txt", "bench_api_100k.txt"):
+      f.write("".join(l for l in open(os.path.join(D, n)) if l.startswith("VQT")))
+if have("bench_rows.json"):
+  shutil.copy(os.path.join(D, "bench_rows.json"), os.path.join(P, "r2_bench_symbol_rows.json"))
 
 # ---- launch list of one bench step
 rows = list(csv.reader(l for l in open(os.path.join(D, "launches_c3.csv")) if l.startswith('"')))

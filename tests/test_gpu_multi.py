@@ -81,6 +81,7 @@ def _worker(rank, world_size, port, out_dir):
     del os.environ["QHBM_NATIVE_ALLREDUCE"]
     torch.cuda.synchronize()
     comm.close()
+    qd.close_native_comms()
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), avg=avg.cpu().numpy(), total=float(total), grad=grad.cpu().numpy(),
              log_z=log_z, entropy=entropy, split=split, hist=hist.cpu().numpy(), lo=lo, hi=hi,
              rows_min=int(rows.min()), rows_max=int(rows.max()), native_ok=native_ok, avg_n=avg_n.cpu().numpy(),

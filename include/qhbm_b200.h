@@ -17,7 +17,11 @@
  *   - (widened) the simulation and measurement halves of
  *     `tfq.layers.Sample`, `tfq.layers.SampledExpectation` and `tfq.layers.Unitary`
  *     as used by SampledQuantumInference and the dense metrics
- *     (qhbmlib/inference/qnn.py:142-292, qnn_utils.py:23-33).
+ *     (qhbmlib/inference/qnn.py:142-292, qnn_utils.py:23-33);
+ *   - the TFQ ops' general symbol signature, `symbol_values f32[U,P]` with one
+ *     row per circuit (qhbm_expectation_*_rows), and the one collective of a
+ *     sharded step: the sum over ranks of the packed count-weighted partial sums
+ *     behind `weighted_average` (qhbmlib/utils.py:43-58; qhbm_comm_*, qhbm_allreduce).
  *
  * Conventions: every function returns 0 on success, non-zero on error; the
  * message is available from qhbm_last_error() (thread-local).  All `d_` pointers
@@ -25,8 +29,10 @@
  * them past the call.  Work is enqueued on `stream` (a cudaStream_t passed as
  * void*); no call synchronises the device unless documented.  Handles are
  * immutable after creation and may be used from several streams, except that
- * one plan owns one workspace: concurrent calls on the SAME plan must be
- * stream-ordered by the caller.
+ * one plan owns one workspace: the library orders the device work of calls on
+ * the SAME plan (a call that arrives on another stream than the previous one
+ * waits for it through an event), so they never race; use several plans for
+ * real concurrency.
  *
  * There is no CPU fallback anywhere behind this header.
  */

@@ -133,6 +133,9 @@ class EnergyInferenceBase(torch.nn.Module, abc.ABC):
     for v, vc in zip(self._tracked_variables, self._tracked_variables_checkpoint):
       if vc.device != v.device or vc.shape != v.shape:
         return True
+    if len(self._tracked_variables) == 1:  # (KOBE, Bernoulli: one fused compare-and-reduce launch)
+      return not torch.equal(self._tracked_variables[0].detach(), self._tracked_variables_checkpoint[0])
+    for v, vc in zip(self._tracked_variables, self._tracked_variables_checkpoint):
       flags.append((v.detach() != vc).any())
     return bool(torch.stack(flags).any().item()) if flags else False
 
@@ -191,7 +194,7 @@ class EnergyInferenceBase(torch.nn.Module, abc.ABC):
       return utils.unique_bitstrings_with_counts(self._sample(num_samples).detach())
     n = self.energy.num_bits
     uniq, idx, count = engine.unique_with_counts(keys)
-    return engine.unpack_bits(uniq, n, utils._natural_shifts(n)), idx, count
+    return utils.mark_unique_rows(engine.unpack_bits(uniq, n, utils._natural_shifts(n))), idx, count
 
   def _sample_keys(self, num_samples):
     """Packed uint64 keys (bit n-1-j of the key = column j) of `num_samples` samples, or None."""
@@ -217,6 +220,27 @@ class EnergyInferenceBase(torch.nn.Module, abc.ABC):
   @abc.abstractmethod
   def _sample(self, num_samples):
     raise NotImplementedError()
+
+
+class _LogPartitionGrad(torch.autograd.Function):
+  """log Z with the reference's gradient estimator attached LAZILY, as `tf.custom_gradient` does it
+  (ebm.py:331-343 forward, 396-415 grad_fn): the samples behind -E_{x~p}[dE/dtheta] are drawn in backward,
+  i.e. only when somebody differentiates through log Z.  `vqt` detaches it (vqt_loss.py:52-54), so a VQT step
+  pays no sampling, dedup or energy evaluation for a gradient nobody takes; `qmhl` takes it."""
+
+  @staticmethod
+  def forward(ctx, owner, result, sharded, *params):
+    ctx.owner, ctx.sharded, ctx.params = owner, sharded, params  # (leaf variables: no version check wanted)
+    return result.detach().clone()
+
+  @staticmethod
+  def backward(ctx, upstream):
+    params = ctx.params
+    with torch.enable_grad():
+      surrogate = ctx.owner._log_partition_surrogate(ctx.sharded)  # pylint: disable=protected-access
+      grads = torch.autograd.grad(surrogate, params, upstream.to(surrogate.dtype).reshape(surrogate.shape),
+                                  allow_unused=True)
+    return (None, None, None) + tuple(grads)
 
 
 class EnergyInference(EnergyInferenceBase):
@@ -246,7 +270,7 @@ class EnergyInference(EnergyInferenceBase):
       rank, world = qd.world()
       lo, hi = qd.shard_range(bitstrings.shape[0], rank, world)
       total = counts.sum()
-      bitstrings, counts = bitstrings[lo:hi].contiguous(), counts[lo:hi].contiguous()
+      bitstrings, counts = utils.mark_unique_rows(bitstrings[lo:hi].contiguous()), counts[lo:hi].contiguous()
       with qd.local_shard():
         values = function(bitstrings)
       leaves = []
@@ -318,18 +342,21 @@ class EnergyInference(EnergyInferenceBase):
     result = self._log_partition_forward_pass().detach()
     if not self._energy_needs_grad():
       return result
+    params = [p for p in self.energy.parameters() if p.requires_grad]
+    return _LogPartitionGrad.apply(self, result, qd.active(), *params)
+
+  def _log_partition_surrogate(self, sharded):
+    """-E_{x~p}[E(x)] over fresh samples as a differentiable function of the energy's variables: its gradient is
+    the reference's log-partition gradient estimator (ebm.py:396-415)."""
     unique_samples, _, counts = self.unique_samples(self.num_expectation_samples)
-    if qd.active():
+    if sharded:
       rank, world = qd.world()
       lo, hi = qd.shard_range(unique_samples.shape[0], rank, world)
       total = counts.sum()
       e = self.energy(unique_samples[lo:hi].contiguous())
       w = counts[lo:hi].to(e.dtype) / total.to(e.dtype)
-      surrogate = qd.shard_term(-(w * e).sum())
-      return result + (surrogate - surrogate.detach())
-    unique_energies = self.energy(unique_samples)
-    surrogate = -utils.weighted_average(counts, unique_energies)
-    return result + (surrogate - surrogate.detach())
+      return qd.shard_term(-(w * e).sum())
+    return -utils.weighted_average(counts, self.energy(unique_samples))
 
   def _log_partition_forward_pass(self):
     """Monte-Carlo estimate with uniform samples: n log 2 - log N_s + logsumexp(-E(x_i))

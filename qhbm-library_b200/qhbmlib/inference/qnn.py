@@ -124,7 +124,12 @@ class QuantumInference(torch.nn.Module, abc.ABC):
     (`circuits.convert_to_tensor([PauliSum, ...])`) or a `Hamiltonian`, in which case the
     circuit is extended by the Hamiltonian's inverse eigenvector circuit and its Z-string shards are
     measured (reference qnn.py:50-80)."""
-    unique_states, idx, _ = utils.unique_bitstrings_with_counts(initial_states)
+    if utils.rows_known_unique(initial_states):
+      # the rows come straight from a dedup (EnergyInference._expectation hands its unique samples to the
+      # user's function): deduplicating them again would be the identity, six launches and a host sync
+      unique_states, idx = initial_states, None
+    else:
+      unique_states, idx, _ = utils.unique_bitstrings_with_counts(initial_states)
     if isinstance(observables, cq.OperatorTensor):
       total_circuit = self.circuit
     else:
@@ -142,7 +147,7 @@ class QuantumInference(torch.nn.Module, abc.ABC):
       circuits = total_circuit(unique_states)
       unique_expectations = self._expectation(circuits, total_circuit.symbol_names, total_circuit.symbol_values,
                                               observables)
-    return utils.expand_unique_results(unique_expectations, idx)
+    return unique_expectations if idx is None else utils.expand_unique_results(unique_expectations, idx)
 
   def _total_circuit(self, observables):
     """circuit + observables.circuit_dagger (reference qnn.py:69-72), kept for the few Hamiltonians in

@@ -111,6 +111,18 @@ def _natural_shifts(n):
   return [n - 1 - j for j in range(n)]
 
 
+def mark_unique_rows(bitstrings):
+  """Tags a tensor whose rows are known to be distinct (the output of a dedup): `QuantumInference.expectation`
+  then skips its own dedup (reference qnn.py:68), which would be the identity on it.  The tag lives on the
+  tensor OBJECT: any op on it (slice, cast, clone) yields an untagged tensor, which is deduplicated as usual."""
+  bitstrings._qhbm_unique_rows = True
+  return bitstrings
+
+
+def rows_known_unique(bitstrings):
+  return getattr(bitstrings, "_qhbm_unique_rows", False)
+
+
 def unique_bitstrings_with_counts(bitstrings, out_idx=torch.int32):
   """Unique rows in first-occurrence order, inverse index and counts (reference utils.py:61-78,
   tf.raw_ops.UniqueWithCountsV2 on axis 0)."""
@@ -123,7 +135,7 @@ def unique_bitstrings_with_counts(bitstrings, out_idx=torch.int32):
   keys = engine.pack_bits(bitstrings.to(torch.int8), shifts)
   uniq, idx, count = engine.unique_with_counts(keys)
   y = engine.unpack_bits(uniq, n, shifts).to(bitstrings.dtype)
-  return y, idx.to(out_idx), count.to(out_idx)
+  return mark_unique_rows(y), idx.to(out_idx), count.to(out_idx)
 
 
 class _Expand(torch.autograd.Function):

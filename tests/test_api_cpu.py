@@ -324,3 +324,33 @@ def test_plan_cache_lru_is_bounded_and_content_keyed():
   h2 = cq.convert_to_tensor([cq.Z(qubits[0]) * cq.Z(qubits[1]) + 0.5 * cq.X(qubits[2])])
   h3 = cq.convert_to_tensor([cq.Z(qubits[0]) * cq.Z(qubits[1]) + 0.25 * cq.X(qubits[2])])
   assert h1 is not h2 and h1.tables_digest(qubits) == h2.tables_digest(qubits) != h3.tables_digest(qubits)
+
+
+def test_log_partition_gradient_is_drawn_lazily_in_backward():
+  """reference ebm.py:331-343, 396-415: the log-partition gradient estimator samples inside grad_fn, i.e. only
+  when the gradient is taken.  `_LogPartitionGrad` on a stand-in owner: no surrogate evaluation in forward or
+  when the result is detached (vqt), one per backward, gradient = upstream * d surrogate / d theta."""
+  from qhbmlib.inference import ebm
+
+  class Owner:
+    calls = 0
+
+    def __init__(self):
+      self.theta = torch.nn.Parameter(torch.tensor([0.5, -1.0, 2.0]))
+      self.unused = torch.nn.Parameter(torch.tensor([1.0]))
+
+    def _log_partition_surrogate(self, sharded):
+      assert sharded is False and torch.is_grad_enabled()
+      Owner.calls += 1
+      return -(self.theta * torch.tensor([1.0, 2.0, 3.0])).sum()
+
+  owner = Owner()
+  value = torch.tensor(1.25)
+  out = ebm._LogPartitionGrad.apply(owner, value, False, owner.theta, owner.unused)
+  assert float(out) == 1.25 and out.requires_grad and Owner.calls == 0
+  _ = out.detach() * 3.0  # vqt's use: nothing is sampled
+  assert Owner.calls == 0
+  (2.0 * out).backward()
+  assert Owner.calls == 1
+  np.testing.assert_allclose(owner.theta.grad.numpy(), [-2.0, -4.0, -6.0])
+  assert owner.unused.grad is None

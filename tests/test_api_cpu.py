@@ -29,6 +29,33 @@ def test_c_abi_library_exports_every_declared_symbol():
   assert lib.qhbm_version() >= 100
 
 
+def test_header_is_plain_c99_and_links_from_c(tmp_path):
+  """The drop-in boundary is a C ABI: include/qhbm_b200.h must compile as strict C99 (no C++ or torch types in
+  the signatures) and a C program must link against the shared library and call into it."""
+  import shutil
+  import subprocess
+  if shutil.which("gcc") is None:
+    pytest.skip("no gcc")
+  root = os.path.join(os.path.dirname(__file__), "..")
+  src = tmp_path / "abi.c"
+  src.write_text(
+      '#include <stdio.h>\n#include "qhbm_b200.h"\n'
+      "int main(void) {\n"
+      "  qhbm_gate_t g; qhbm_pauli_term_t t; qhbm_energy_desc_t e; qhbm_comm_t* c = 0; qhbm_plan_t* p = 0;\n"
+      "  (void)g; (void)t; (void)e; (void)c; (void)p;\n"
+      "  if (qhbm_version() < 100) return 2;\n"
+      "  /* an invalid call must come back as a status + message, not crash */\n"
+      "  if (qhbm_allreduce(0, 0, 4, QHBM_F32, 0) == 0) return 3;\n"
+      '  printf("%s\\n", qhbm_last_error());\n'
+      "  return 0;\n}\n")
+  exe = tmp_path / "abi"
+  lib_dir = os.path.dirname(nat.LIB_PATH)
+  subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                         str(src), "-o", str(exe), "-L", lib_dir, "-l:libqhbm_b200.so", f"-Wl,-rpath,{lib_dir}"])
+  out = subprocess.run([str(exe)], capture_output=True, text=True)
+  assert out.returncode == 0 and "null communicator" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
 def test_collective_entry_points_bind_nccl_at_run_time_and_validate():
   """qhbm_comm_unique_id works without a GPU (it only needs libnccl.so.2); bad arguments come back as status 1
   with a message, before NCCL is touched."""

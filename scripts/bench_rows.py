@@ -10,15 +10,14 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "qhbm-library_b200"), os.path.join(ROOT, "tests")):
   sys.path.insert(0, p)
-from oracle import qhbm_oracle as orc  # noqa: E402  (circuit / Hamiltonian builders only)
+from _workloads import hea_tables  # noqa: E402
 from qhbmlib import engine  # noqa: E402
 
 n, u = 16, 4096
-gates, names = orc.hea_circuit(n, 2)
-terms, offs = engine.terms_from_pauli_sums([orc.xxz_ring(n)], n)
-plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, True)
+gates, nsym, terms, offs = hea_tables(n, 2, "xxz")
+plan = engine.ExpectationPlan(gates, n, nsym, terms, offs, True)
 rng = np.random.default_rng(3)
-phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+phi = torch.tensor(rng.uniform(-1, 1, nsym).astype(np.float32), device="cuda")
 rows = phi[None, :].repeat(u, 1).contiguous()
 basis = torch.tensor(rng.choice(1 << n, u, replace=False).astype(np.int64), device="cuda")
 dg = torch.full((u, 1), 1.0 / u, device="cuda")

@@ -7,20 +7,18 @@ for p in (ROOT, os.path.join(ROOT, "qhbm-library_b200"), os.path.join(ROOT, "tes
   sys.path.insert(0, p)
 import numpy as np
 import torch
-from oracle import qhbm_oracle as orc
+from _workloads import hea_tables
 from qhbmlib import engine
 
 n, layers, u, T, K, grad = (int(x) for x in sys.argv[1:7])
 ham = sys.argv[7] if len(sys.argv) > 7 else "xxz"
 reps = int(sys.argv[8]) if len(sys.argv) > 8 else 1
-gates, names = orc.hea_circuit(n, layers)
-ops = orc.kobe_shards(n, 2) if ham == "kobe" else [orc.xxz_ring(n) if ham == "xxz" else orc.tfim_ring(n)]
-terms, offs = engine.terms_from_pauli_sums(ops, n)
-plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, bool(grad), T, K)
+gates, nsym, terms, offs = hea_tables(n, layers, ham)
+plan = engine.ExpectationPlan(gates, n, nsym, terms, offs, bool(grad), T, K)
 rng = np.random.default_rng(0)
-phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+phi = torch.tensor(rng.uniform(-1, 1, nsym).astype(np.float32), device="cuda")
 basis = torch.tensor(rng.choice(1 << n, u, replace=False).astype(np.int64), device="cuda")
-dg = torch.tensor(rng.uniform(0, 1, (u, len(ops))).astype(np.float32), device="cuda")
+dg = torch.tensor(rng.uniform(0, 1, (u, len(offs) - 1)).astype(np.float32), device="cuda")
 best = None
 for _ in range(reps):
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -7,17 +7,15 @@ for p in (ROOT, os.path.join(ROOT, "qhbm-library_b200"), os.path.join(ROOT, "tes
   sys.path.insert(0, p)
 import numpy as np
 import torch
-from oracle import qhbm_oracle as orc
+from _workloads import hea_tables
 from qhbmlib import engine
 
 
 def run(n, layers, u, T, K, grad, ham="xxz", reps=3):
-  gates, names = orc.hea_circuit(n, layers)
-  ops = [orc.xxz_ring(n) if ham == "xxz" else orc.tfim_ring(n)]
-  terms, offs = engine.terms_from_pauli_sums(ops, n)
-  plan = engine.ExpectationPlan(gates, n, len(names), terms, offs, grad, T, K)
+  gates, nsym, terms, offs = hea_tables(n, layers, ham)
+  plan = engine.ExpectationPlan(gates, n, nsym, terms, offs, grad, T, K)
   rng = np.random.default_rng(0)
-  phi = torch.tensor(rng.uniform(-1, 1, len(names)).astype(np.float32), device="cuda")
+  phi = torch.tensor(rng.uniform(-1, 1, nsym).astype(np.float32), device="cuda")
   basis = torch.tensor(rng.choice(1 << n, u, replace=False).astype(np.int64), device="cuda")
   dg = torch.tensor(rng.uniform(0, 1, (u, 1)).astype(np.float32), device="cuda")
   f = (lambda: plan.forward_adjoint(basis, phi, dg)) if grad else (lambda: plan.forward(basis, phi))

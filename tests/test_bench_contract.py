@@ -36,3 +36,14 @@ def test_cuda_arm_refuses_to_run_without_a_gpu():
   assert out.returncode != 0
   assert "no CPU fallback" in (out.stderr + out.stdout)
   assert not any(l.startswith("{") for l in out.stdout.splitlines())
+
+
+def test_committed_ncu_counters_belong_to_the_committed_sweep_kernel_sources():
+  """bench.py only quotes `roofline.traffic` / `roofline.sm_counters` from profiles/kernel_counters.json while the
+  hash stored there equals the hash of the sweep-kernel sources: an edit to those sources without a new ncu
+  capture shows up here instead of silently dropping the counters from the bench line."""
+  sys.path.insert(0, ROOT)
+  import bench
+  c = bench.ncu_counters("c3")
+  assert c is not None and c["current"], (c and c.get("kernel_src_sha"), bench.kernel_source_sha())
+  assert c["dram_bytes_per_4096_bitstrings"] > 0 and 0 < c["dominant_launch"]["share_of_step"] < 1
